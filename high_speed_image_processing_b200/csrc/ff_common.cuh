@@ -1,0 +1,126 @@
+// Shared device/host helpers for libflamefront (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/flamefront.h"
+
+namespace ff {
+
+// ---- error plumbing --------------------------------------------------------------------
+void set_cuda_error(cudaError_t e, const char* where);
+
+#define FF_CUDA_TRY(expr)                                        \
+  do {                                                           \
+    cudaError_t _e = (expr);                                     \
+    if (_e != cudaSuccess) {                                     \
+      ::ff::set_cuda_error(_e, #expr);                           \
+      return FF_ERR_CUDA;                                        \
+    }                                                            \
+  } while (0)
+
+// ---- tiling shared by ff_partial_len / ff_stream_frames / ff_detect ---------------------
+// A "group" is 8 consecutive pixels = `bits` bytes of the packed stream.  A tile is
+// kThreads*K groups; the streaming kernel assigns one CTA to (tile, frame-chunk).
+constexpr int kThreads = 256;
+constexpr int kGroupPx = 8;
+
+struct Tiling {
+  int k;                // groups per thread per tile (1 or 4)
+  int tile_px;          // kThreads * k * 8
+  int tiles_per_frame;  // ceil(P / tile_px)
+  bool fast;            // TMA-staged path usable (P % 32 == 0)
+};
+
+inline Tiling choose_tiling(int64_t px_per_frame) {
+  Tiling t;
+  t.fast = (px_per_frame % 32) == 0 && px_per_frame > 0;
+  t.k = (px_per_frame >= 16 * kThreads * 4 * kGroupPx) ? 4 : 1;   // >= 16 big tiles -> K=4
+  t.tile_px = kThreads * t.k * kGroupPx;
+  if (!t.fast) {        // generic kernel accumulates one count per frame
+    t.k = 0;
+    t.tile_px = 0;
+    t.tiles_per_frame = 1;
+    return t;
+  }
+  t.tiles_per_frame = (int)((px_per_frame + t.tile_px - 1) / t.tile_px);
+  return t;
+}
+
+inline int64_t frame_bytes_of(int64_t px, int bits) { return px * bits / 8; }
+
+#if defined(__CUDACC__)
+// ---- mbarrier + bulk async copy (TMA 1-D) ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// L2 eviction policy for read-once streams.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                         uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+// ---- 12-bit decode: 12 bytes (3 LE words) -> 8 pixels -------------------------------------
+// bytes b0..b11; pair j = (b[3j], b[3j+1], b[3j+2]) -> hi = b0<<4 | b1>>4, lo = (b1&15)<<8 | b2.
+__device__ __forceinline__ void decode12x8(uint32_t w0, uint32_t w1, uint32_t w2, int (&v)[8]) {
+  const uint32_t t0 = __byte_perm(w0, 0u, 0x4012);  // 0  b0 b1 b2
+  const uint32_t t1 = __byte_perm(w0, w1, 0x3345);  // b3 b3 b4 b5 (top byte masked below)
+  const uint32_t t2 = __byte_perm(w1, w2, 0x2234);  // b6 b6 b7 b8
+  const uint32_t t3 = __byte_perm(w2, 0u, 0x4123);  // 0  b9 b10 b11
+  v[0] = (int)(t0 >> 12);
+  v[1] = (int)(t0 & 0xFFFu);
+  v[2] = (int)((t1 >> 12) & 0xFFFu);
+  v[3] = (int)(t1 & 0xFFFu);
+  v[4] = (int)((t2 >> 12) & 0xFFFu);
+  v[5] = (int)(t2 & 0xFFFu);
+  v[6] = (int)(t3 >> 12);
+  v[7] = (int)(t3 & 0xFFFu);
+}
+
+// One pixel out of a packed buffer whose first byte holds flat pixel 0 (any bit depth).
+template <int BITS>
+__device__ __forceinline__ int load_px_generic(const uint8_t* __restrict__ base, int64_t q) {
+  if (BITS == 8) return base[q];
+  if (BITS == 16) return (int)base[2 * q] | ((int)base[2 * q + 1] << 8);
+  const uint8_t* t = base + (q >> 1) * 3;
+  return (q & 1) ? (((int)(t[1] & 15) << 8) | (int)t[2]) : (((int)t[0] << 4) | ((int)t[1] >> 4));
+}
+#endif  // __CUDACC__
+
+}  // namespace ff

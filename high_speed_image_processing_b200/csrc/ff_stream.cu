@@ -1,0 +1,455 @@
+// Stage 1 + 2b: the frame-streaming kernels.
+//
+// One kernel template serves the packed-12-bit unpack (ff_unpack) and the fused front end
+// (ff_stream_frames): a CTA owns one pixel tile and marches over a chunk of consecutive
+// frames, so each frame is fetched from HBM exactly once even when the frame difference
+// needs the previous frame (it is carried in registers; the only re-read is one halo tile
+// per chunk).  Tiles are staged into shared memory by 1-D TMA bulk copies
+// (cp.async.bulk -> UBLKCP) through a kStages-deep mbarrier ring and decoded from there:
+// thread t takes 8-pixel groups t, t+256, ... (12 bytes = 3 conflict-free LDS.32 for packed
+// 12-bit, one LDS.128 for 16-bit, one LDS.64 for 8-bit) and writes 16-byte vectors.
+//
+// Everything is integer arithmetic on values the reference holds as integer-valued float64
+// (scripts/process_videos.py:670-674, :397-399, :759), so results are bit-exact.
+#include "ff_common.cuh"
+
+namespace ff {
+namespace {
+
+constexpr int kStages = 4;
+
+struct StreamParams {
+  const uint8_t* frames;
+  const uint8_t* halo;
+  int64_t frame_bytes;
+  int64_t px_per_frame;
+  int n_frames;
+  int tiles_per_frame;
+  int frames_per_chunk;
+  const int32_t* bg_dev;
+  int empty_thr;
+  int diff_thr;
+  const uint8_t* skip;
+  int32_t* partial;
+  void* diff_out;
+  uint16_t* decoded_out;
+};
+
+template <int BITS>
+__device__ __forceinline__ void load_group(const uint8_t* stage, int g, int (&v)[8]) {
+  if (BITS == 12) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(stage) + 3 * g;
+    decode12x8(w[0], w[1], w[2], v);
+  } else if (BITS == 16) {
+    const uint4 q = reinterpret_cast<const uint4*>(stage)[g];
+    v[0] = q.x & 0xFFFF; v[1] = q.x >> 16; v[2] = q.y & 0xFFFF; v[3] = q.y >> 16;
+    v[4] = q.z & 0xFFFF; v[5] = q.z >> 16; v[6] = q.w & 0xFFFF; v[7] = q.w >> 16;
+  } else {
+    const uint2 q = reinterpret_cast<const uint2*>(stage)[g];
+    v[0] = q.x & 0xFF; v[1] = (q.x >> 8) & 0xFF; v[2] = (q.x >> 16) & 0xFF; v[3] = q.x >> 24;
+    v[4] = q.y & 0xFF; v[5] = (q.y >> 8) & 0xFF; v[6] = (q.y >> 16) & 0xFF; v[7] = q.y >> 24;
+  }
+}
+
+template <int DIFF>
+__device__ __forceinline__ void store_diff(void* base, int64_t px, const int (&d)[8]) {
+  if (DIFF == FF_DIFF_U16) {
+    uint4 q;
+    q.x = (uint32_t)d[0] | ((uint32_t)d[1] << 16);
+    q.y = (uint32_t)d[2] | ((uint32_t)d[3] << 16);
+    q.z = (uint32_t)d[4] | ((uint32_t)d[5] << 16);
+    q.w = (uint32_t)d[6] | ((uint32_t)d[7] << 16);
+    __stcs(reinterpret_cast<uint4*>(static_cast<uint16_t*>(base) + px), q);
+  } else if (DIFF == FF_DIFF_F32) {
+    float4* o = reinterpret_cast<float4*>(static_cast<float*>(base) + px);
+    __stcs(o, make_float4((float)d[0], (float)d[1], (float)d[2], (float)d[3]));
+    __stcs(o + 1, make_float4((float)d[4], (float)d[5], (float)d[6], (float)d[7]));
+  } else if (DIFF == FF_DIFF_F64) {
+    double2* o = reinterpret_cast<double2*>(static_cast<double*>(base) + px);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) __stcs(o + j, make_double2((double)d[2 * j], (double)d[2 * j + 1]));
+  }
+}
+
+// COUNT: emit per-(frame,tile) above-noise counts.  DIFF: retained difference dtype.
+// DECODED: also write decoded uint16 pixels.  K: groups per thread per tile.
+template <int BITS, bool COUNT, int DIFF, bool DECODED, int K>
+__global__ void __launch_bounds__(kThreads) stream_kernel(const StreamParams p) {
+  constexpr int kGroups = K * kThreads;
+  constexpr int kStageBytes = kGroups * BITS;
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  int* warp_cnt = reinterpret_cast<int*>(full + kStages);  // [2][8]
+
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x % p.tiles_per_frame;
+  const int chunk = blockIdx.x / p.tiles_per_frame;
+  const int f_begin = chunk * p.frames_per_chunk;
+  const int f_end = min(f_begin + p.frames_per_chunk, p.n_frames);
+
+  const int64_t tile_px0 = (int64_t)tile * (kGroups * kGroupPx);
+  const int tile_groups = (int)min((int64_t)kGroups, (p.px_per_frame - tile_px0) / kGroupPx);
+  const uint32_t tile_bytes = (uint32_t)tile_groups * BITS;
+  const int64_t tile_off = (int64_t)tile * kStageBytes;
+
+  // Frame feeding prev[] before the first frame of this chunk (difference modes only).
+  const uint8_t* halo_ptr = nullptr;
+  if (DIFF != FF_DIFF_NONE) {
+    int hf = f_begin - 1;
+    if (p.skip != nullptr)
+      while (hf >= 0 && p.skip[hf]) --hf;
+    halo_ptr = hf >= 0 ? p.frames + (int64_t)hf * p.frame_bytes : p.halo;
+  }
+  const int has_halo = halo_ptr != nullptr ? 1 : 0;
+  const int n_items = (f_end - f_begin) + has_halo;
+
+  auto src_of = [&](int item) -> const uint8_t* {
+    const int f = item - has_halo;
+    const uint8_t* fr = f < 0 ? halo_ptr : p.frames + (int64_t)(f_begin + f) * p.frame_bytes;
+    return fr + tile_off;
+  };
+
+  uint64_t policy = 0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+    policy = policy_evict_first();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int pre = min(kStages - 1, n_items);
+    for (int i = 0; i < pre; ++i) {
+      mbar_arrive_expect_tx(&full[i], tile_bytes);
+      bulk_g2s(smem + i * kStageBytes, src_of(i), tile_bytes, &full[i], policy);
+    }
+  }
+
+  int bg = 0, cthr = 0;
+  if (COUNT || DIFF != FF_DIFF_NONE) {
+    bg = __ldg(p.bg_dev);
+    const int ethr = p.empty_thr >= 0 ? p.empty_thr : max(10, bg >> 1);
+    cthr = bg + ethr;  // max(x-bg,0) > ethr  <=>  x > bg + ethr   (ethr >= 0)
+  }
+
+  uint32_t prev[K][4];  // background-subtracted previous frame, two uint16 per register
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) prev[k][j] = 0;
+  bool have_prev = false;
+
+  for (int it = 0; it < n_items; ++it) {
+    const int s = it % kStages;
+    const uint32_t parity = (uint32_t)(it / kStages) & 1u;
+    if (tid == 0) {
+      const int nx = it + kStages - 1;  // its stage was drained in iteration it-1
+      if (nx < n_items) {
+        const int ns = nx % kStages;
+        mbar_arrive_expect_tx(&full[ns], tile_bytes);
+        bulk_g2s(smem + ns * kStageBytes, src_of(nx), tile_bytes, &full[ns], policy);
+      }
+    }
+    mbar_wait(&full[s], parity);
+
+    const uint8_t* stage = smem + s * kStageBytes;
+    const bool is_halo = it < has_halo;
+    const int f = f_begin + it - has_halo;
+    const bool skipped = !is_halo && p.skip != nullptr && p.skip[f] != 0;
+    const bool emit_diff = (DIFF != FF_DIFF_NONE) && !is_halo;
+    const bool diff_valid = have_prev && !skipped;
+    int cnt = 0;
+
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int g = tid + k * kThreads;
+      if (g < tile_groups) {
+        int v[8];
+        load_group<BITS>(stage, g, v);
+        const int64_t px = (int64_t)f * p.px_per_frame + tile_px0 + (int64_t)g * kGroupPx;
+        if (COUNT) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cnt += (v[j] > cthr) ? 1 : 0;
+        }
+        if (DECODED && !is_halo) {
+          uint4 q;
+          q.x = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
+          q.y = (uint32_t)v[2] | ((uint32_t)v[3] << 16);
+          q.z = (uint32_t)v[4] | ((uint32_t)v[5] << 16);
+          q.w = (uint32_t)v[6] | ((uint32_t)v[7] << 16);
+          __stcs(reinterpret_cast<uint4*>(p.decoded_out + px), q);
+        }
+        if (DIFF != FF_DIFF_NONE) {
+          int d[8];
+          uint32_t cur[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int s0 = max(v[2 * j] - bg, 0);
+            const int s1 = max(v[2 * j + 1] - bg, 0);
+            int d0 = s0 - (int)(prev[k][j] & 0xFFFFu);
+            int d1 = s1 - (int)(prev[k][j] >> 16);
+            d[2 * j] = (diff_valid && d0 >= p.diff_thr) ? d0 : 0;
+            d[2 * j + 1] = (diff_valid && d1 >= p.diff_thr) ? d1 : 0;
+            cur[j] = (uint32_t)s0 | ((uint32_t)s1 << 16);
+          }
+          if (emit_diff) store_diff<DIFF>(p.diff_out, px, d);
+          if (!skipped) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) prev[k][j] = cur[j];
+          }
+        }
+      }
+    }
+    if (DIFF != FF_DIFF_NONE && !skipped) have_prev = true;
+
+    if (COUNT && !is_halo) {
+      cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+      if ((tid & 31) == 0) warp_cnt[(it & 1) * 8 + (tid >> 5)] = cnt;
+    }
+    __syncthreads();  // stage s drained by every thread; warp_cnt visible
+    if (COUNT && !is_halo && tid == 0) {
+      const int* wc = warp_cnt + (it & 1) * 8;
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) tot += wc[w];
+      p.partial[(int64_t)f * p.tiles_per_frame + tile] = tot;
+    }
+  }
+}
+
+// Shapes the TMA path cannot take (P % 32 != 0): one thread per pixel pair, plain loads,
+// the previous frame is simply re-read.  Correct for every even P; not a performance path.
+template <int BITS, int DIFF>
+__global__ void stream_generic_kernel(const StreamParams p, int64_t pairs_per_frame) {
+  const int64_t total = (int64_t)p.n_frames * pairs_per_frame;
+  const int bg = __ldg(p.bg_dev);
+  const int ethr = p.empty_thr >= 0 ? p.empty_thr : max(10, bg >> 1);
+  const int cthr = bg + ethr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(i / pairs_per_frame);
+    const int64_t q = (i - (int64_t)f * pairs_per_frame) * 2;
+    const uint8_t* fr = p.frames + (int64_t)f * p.frame_bytes;
+    const bool two = q + 1 < p.px_per_frame;
+    const int v0 = load_px_generic<BITS>(fr, q);
+    const int v1 = two ? load_px_generic<BITS>(fr, q + 1) : 0;
+    const int c = (v0 > cthr ? 1 : 0) + ((two && v1 > cthr) ? 1 : 0);
+    if (c) atomicAdd(p.partial + f, c);
+    if (p.decoded_out != nullptr) {
+      p.decoded_out[(int64_t)f * p.px_per_frame + q] = (uint16_t)v0;
+      if (two) p.decoded_out[(int64_t)f * p.px_per_frame + q + 1] = (uint16_t)v1;
+    }
+    if (DIFF != FF_DIFF_NONE) {
+      const bool skipped = p.skip != nullptr && p.skip[f] != 0;
+      int hf = f - 1;
+      if (p.skip != nullptr)
+        while (hf >= 0 && p.skip[hf]) --hf;
+      const uint8_t* pr = hf >= 0 ? p.frames + (int64_t)hf * p.frame_bytes : p.halo;
+      int d0 = 0, d1 = 0;
+      if (pr != nullptr && !skipped) {
+        d0 = max(v0 - bg, 0) - max(load_px_generic<BITS>(pr, q) - bg, 0);
+        if (d0 < p.diff_thr) d0 = 0;
+        if (two) {
+          d1 = max(v1 - bg, 0) - max(load_px_generic<BITS>(pr, q + 1) - bg, 0);
+          if (d1 < p.diff_thr) d1 = 0;
+        }
+      }
+      const int64_t o = (int64_t)f * p.px_per_frame + q;
+      if (DIFF == FF_DIFF_U16) {
+        static_cast<uint16_t*>(p.diff_out)[o] = (uint16_t)d0;
+        if (two) static_cast<uint16_t*>(p.diff_out)[o + 1] = (uint16_t)d1;
+      } else if (DIFF == FF_DIFF_F32) {
+        static_cast<float*>(p.diff_out)[o] = (float)d0;
+        if (two) static_cast<float*>(p.diff_out)[o + 1] = (float)d1;
+      } else {
+        static_cast<double*>(p.diff_out)[o] = (double)d0;
+        if (two) static_cast<double*>(p.diff_out)[o + 1] = (double)d1;
+      }
+    }
+  }
+}
+
+// Decode-only generic kernel (no background known): ff_unpack on odd shapes.
+__global__ void unpack12_generic_kernel(const uint8_t* __restrict__ in, uint16_t* __restrict__ out,
+                                        int64_t n_px) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_px;
+       q += (int64_t)gridDim.x * blockDim.x)
+    out[q] = (uint16_t)load_px_generic<12>(in, q);
+}
+
+int sm_count_cached() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+template <int BITS, bool COUNT, int DIFF, bool DECODED, int K>
+int launch_stream(StreamParams p, cudaStream_t st) {
+  auto kern = stream_kernel<BITS, COUNT, DIFF, DECODED, K>;
+  constexpr int kStageBytes = K * kThreads * BITS;
+  constexpr int kSmem = kStages * kStageBytes + kStages * 8 + 2 * 8 * 4;
+  static bool configured[64] = {false};
+  static int ctas_per_sm[64] = {0};
+  int dev = 0;
+  FF_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return FF_ERR_INVALID;
+  if (!configured[dev]) {
+    FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    int occ = 0;
+    FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, kSmem));
+    ctas_per_sm[dev] = occ > 0 ? occ : 1;
+    configured[dev] = true;
+  }
+  // One resident wave: every CTA is long-lived and marches over its own frame chunk.
+  const int64_t wave = (int64_t)sm_count_cached() * ctas_per_sm[dev];
+  int64_t chunks = wave / p.tiles_per_frame;
+  if (chunks < 1) chunks = 1;
+  if (chunks > p.n_frames) chunks = p.n_frames;
+  p.frames_per_chunk = (int)((p.n_frames + chunks - 1) / chunks);
+  chunks = (p.n_frames + p.frames_per_chunk - 1) / p.frames_per_chunk;
+  const int64_t grid = chunks * p.tiles_per_frame;
+  if (grid > 0x7FFFFFFF) return FF_ERR_UNSUPPORTED;
+  kern<<<(unsigned)grid, kThreads, kSmem, st>>>(p);
+  FF_CUDA_TRY(cudaGetLastError());
+  return FF_OK;
+}
+
+template <int BITS, bool COUNT, int DIFF, bool DECODED>
+int launch_stream_k(const StreamParams& p, int k, cudaStream_t st) {
+  return k == 4 ? launch_stream<BITS, COUNT, DIFF, DECODED, 4>(p, st)
+                : launch_stream<BITS, COUNT, DIFF, DECODED, 1>(p, st);
+}
+
+template <int BITS>
+int dispatch_stream(const StreamParams& p, int k, int diff, bool decoded, cudaStream_t st) {
+  if (decoded) {
+    if (BITS != 12) return FF_ERR_UNSUPPORTED;
+    switch (diff) {
+      case FF_DIFF_NONE: return launch_stream_k<12, true, FF_DIFF_NONE, true>(p, k, st);
+      case FF_DIFF_U16: return launch_stream_k<12, true, FF_DIFF_U16, true>(p, k, st);
+      case FF_DIFF_F32: return launch_stream_k<12, true, FF_DIFF_F32, true>(p, k, st);
+      case FF_DIFF_F64: return launch_stream_k<12, true, FF_DIFF_F64, true>(p, k, st);
+    }
+    return FF_ERR_INVALID;
+  }
+  switch (diff) {
+    case FF_DIFF_NONE: return launch_stream_k<BITS, true, FF_DIFF_NONE, false>(p, k, st);
+    case FF_DIFF_U16: return launch_stream_k<BITS, true, FF_DIFF_U16, false>(p, k, st);
+    case FF_DIFF_F32: return launch_stream_k<BITS, true, FF_DIFF_F32, false>(p, k, st);
+    case FF_DIFF_F64: return launch_stream_k<BITS, true, FF_DIFF_F64, false>(p, k, st);
+  }
+  return FF_ERR_INVALID;
+}
+
+template <int BITS>
+int dispatch_generic(const StreamParams& p, int diff, cudaStream_t st) {
+  const int64_t pairs = (p.px_per_frame + 1) / 2;
+  const int64_t total = pairs * p.n_frames;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)sm_count_cached() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  FF_CUDA_TRY(cudaMemsetAsync(p.partial, 0, sizeof(int32_t) * (size_t)p.n_frames, st));
+  switch (diff) {
+    case FF_DIFF_NONE: stream_generic_kernel<BITS, FF_DIFF_NONE><<<(unsigned)blocks, 256, 0, st>>>(p, pairs); break;
+    case FF_DIFF_U16: stream_generic_kernel<BITS, FF_DIFF_U16><<<(unsigned)blocks, 256, 0, st>>>(p, pairs); break;
+    case FF_DIFF_F32: stream_generic_kernel<BITS, FF_DIFF_F32><<<(unsigned)blocks, 256, 0, st>>>(p, pairs); break;
+    case FF_DIFF_F64: stream_generic_kernel<BITS, FF_DIFF_F64><<<(unsigned)blocks, 256, 0, st>>>(p, pairs); break;
+    default: return FF_ERR_INVALID;
+  }
+  FF_CUDA_TRY(cudaGetLastError());
+  return FF_OK;
+}
+
+}  // namespace
+
+int stream_frames_impl(const void* frames, const void* halo, int64_t n_frames, int height, int width,
+                       int bits, const int32_t* bg_dev, int32_t empty_thr, int32_t diff_thr,
+                       const uint8_t* skip, int32_t* partial, void* diff_out, int diff_dtype,
+                       uint16_t* decoded_out, cudaStream_t st) {
+  if (frames == nullptr || bg_dev == nullptr || partial == nullptr) return FF_ERR_INVALID;
+  if (n_frames <= 0 || height <= 0 || width <= 0 || n_frames > 0x7FFFFFFF) return FF_ERR_INVALID;
+  if (bits != 8 && bits != 12 && bits != 16) return FF_ERR_UNSUPPORTED;
+  if (diff_dtype < FF_DIFF_NONE || diff_dtype > FF_DIFF_F64) return FF_ERR_INVALID;
+  if ((diff_dtype != FF_DIFF_NONE) != (diff_out != nullptr)) return FF_ERR_INVALID;
+  if (diff_dtype == FF_DIFF_U16 && diff_thr < 0) return FF_ERR_UNSUPPORTED;
+  if (decoded_out != nullptr && bits != 12) return FF_ERR_UNSUPPORTED;
+  const int64_t px = (int64_t)height * width;
+  if (bits == 12 && (px & 1)) return FF_ERR_UNSUPPORTED;  // frames must start on a byte triple
+
+  const Tiling t = choose_tiling(px);
+  StreamParams p{};
+  p.frames = static_cast<const uint8_t*>(frames);
+  p.halo = static_cast<const uint8_t*>(halo);
+  p.frame_bytes = frame_bytes_of(px, bits);
+  p.px_per_frame = px;
+  p.n_frames = (int)n_frames;
+  p.tiles_per_frame = t.tiles_per_frame;
+  p.frames_per_chunk = 1;
+  p.bg_dev = bg_dev;
+  p.empty_thr = empty_thr;
+  p.diff_thr = diff_thr;
+  p.skip = skip;
+  p.partial = partial;
+  p.diff_out = diff_out;
+  p.decoded_out = decoded_out;
+
+  const bool aligned = ((reinterpret_cast<uintptr_t>(frames) | reinterpret_cast<uintptr_t>(halo) |
+                         reinterpret_cast<uintptr_t>(diff_out) | reinterpret_cast<uintptr_t>(decoded_out)) & 15u) == 0;
+  if (t.fast && aligned) {
+    switch (bits) {
+      case 8: return dispatch_stream<8>(p, t.k, diff_dtype, decoded_out != nullptr, st);
+      case 12: return dispatch_stream<12>(p, t.k, diff_dtype, decoded_out != nullptr, st);
+      default: return dispatch_stream<16>(p, t.k, diff_dtype, decoded_out != nullptr, st);
+    }
+  }
+  if (t.fast && !aligned) return FF_ERR_ALIGNMENT;
+  switch (bits) {
+    case 8: return dispatch_generic<8>(p, diff_dtype, st);
+    case 12: return dispatch_generic<12>(p, diff_dtype, st);
+    default: return dispatch_generic<16>(p, diff_dtype, st);
+  }
+}
+
+int unpack_impl(const void* packed, void* out, int64_t n_frames, int height, int width, int bits,
+                cudaStream_t st) {
+  if (packed == nullptr || out == nullptr) return FF_ERR_INVALID;
+  if (n_frames <= 0 || height <= 0 || width <= 0 || n_frames > 0x7FFFFFFF) return FF_ERR_INVALID;
+  const int64_t px = (int64_t)height * width;
+  if (bits == 8 || bits == 16) {  // already byte-addressable: a plain device copy
+    FF_CUDA_TRY(cudaMemcpyAsync(out, packed, (size_t)(n_frames * px * bits / 8), cudaMemcpyDeviceToDevice, st));
+    return FF_OK;
+  }
+  if (bits != 12) return FF_ERR_UNSUPPORTED;
+  if ((n_frames * px) & 1) return FF_ERR_UNSUPPORTED;
+  const Tiling t = choose_tiling(px);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(packed) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+  if (t.fast && aligned) {
+    StreamParams p{};
+    p.frames = static_cast<const uint8_t*>(packed);
+    p.frame_bytes = frame_bytes_of(px, 12);
+    p.px_per_frame = px;
+    p.n_frames = (int)n_frames;
+    p.tiles_per_frame = t.tiles_per_frame;
+    p.decoded_out = static_cast<uint16_t*>(out);
+    return t.k == 4 ? launch_stream<12, false, FF_DIFF_NONE, true, 4>(p, st)
+                    : launch_stream<12, false, FF_DIFF_NONE, true, 1>(p, st);
+  }
+  const int64_t n_px = n_frames * px;
+  int64_t blocks = (n_px + 255) / 256;
+  const int64_t cap = (int64_t)sm_count_cached() * 16;
+  if (blocks > cap) blocks = cap;
+  unpack12_generic_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<const uint8_t*>(packed),
+                                                           static_cast<uint16_t*>(out), n_px);
+  FF_CUDA_TRY(cudaGetLastError());
+  return FF_OK;
+}
+
+}  // namespace ff

@@ -1,0 +1,434 @@
+"""FlameFrontEngine - the Python face of libflamefront.so.
+
+PyTorch supplies device memory and streams; every computation on frames happens in the
+hand-written sm_100a kernels behind the C-ABI (include/flamefront.h).  The few float64
+scalars the reference derives per clip (centre-row mean/std, thresholds, the empty-frame
+fraction) are evaluated on the host with the reference's own NumPy expressions and handed to
+the kernels as exact integer bounds - see ``derive_kernel_bounds``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import FF_DIFF_F32, FF_DIFF_F64, FF_DIFF_NONE, FF_DIFF_U16, FF_METHOD, FF_NO_EXIT
+
+DETECTION_METHODS = tuple(FF_METHOD)  # ("threshold", "gradient", "half_maximum")
+INT32_MAX = 2**31 - 1
+INT32_MIN = -(2**31)
+
+_DIFF_DTYPES = {
+    None: (FF_DIFF_NONE, None),
+    "uint16": (FF_DIFF_U16, torch.uint16),
+    "float32": (FF_DIFF_F32, torch.float32),
+    "float64": (FF_DIFF_F64, torch.float64),
+}
+
+
+def frame_nbytes(height: int, width: int, bits: int) -> int:
+    if bits not in (8, 12, 16):
+        raise ValueError(f"unsupported bit depth {bits} (8, 12 or 16)")
+    px = height * width
+    if bits == 12 and px % 2:
+        raise ValueError("packed 12-bit frames need an even pixel count")
+    return px * bits // 8
+
+
+@dataclass
+class DetectionParams:
+    """Tunables of the per-frame path.  Defaults are the reference's
+    (scripts/process_videos.py:112,169,174,1459) except ``exit_margin_px`` = 10
+    (README.md:146; HEAD's FlameDetectorConfig uses 15, :193)."""
+    method: str = "half_maximum"
+    use_frame_diff: bool = True
+    frame_diff_threshold: float = 5.0
+    min_gradient_strength: float = 10.0
+    min_run_px: int = 1
+    exit_margin_px: int = 10
+    min_signal_fraction: float = 0.0005
+
+    def __post_init__(self) -> None:
+        if self.method not in FF_METHOD:
+            raise ValueError(
+                f"unknown detection_method {self.method!r}; options: {', '.join(DETECTION_METHODS)}")
+        if self.min_run_px < 1:
+            raise ValueError("min_run_px must be >= 1")
+
+
+@dataclass
+class ClipScalars:
+    """Per-clip scalars taken from frame 0 (scripts/process_videos.py:1357-1370, :1458)."""
+    background: float
+    centerline_mean: float
+    centerline_std: float
+    centerline_max: float
+    flame_threshold: float
+    noise_threshold: float
+
+    @staticmethod
+    def from_frame0_stats(bg_max: int, centerline: np.ndarray) -> "ClipScalars":
+        background = float(bg_max)                              # :1358 float(np.max(frame))
+        line = np.asarray(centerline).astype(np.float64)        # :1362
+        mean = np.mean(line)                                    # :1363
+        std = np.std(line)                                      # :1364
+        mx = np.max(line)                                       # :1365
+        thr = max(mean + 5 * std, mx * 2.0)                     # :1367-1370
+        noise = max(10.0, background * 0.5)                     # :1458
+        return ClipScalars(background, float(mean), float(std), float(mx), float(thr), float(noise))
+
+
+@dataclass
+class KernelBounds:
+    empty_thr: int
+    min_signal_count: int
+    diff_thr: int
+    threshold_floor: int
+    grad2_bound: int
+
+
+def _clamp_i32(v: int) -> int:
+    return max(INT32_MIN, min(INT32_MAX, int(v)))
+
+
+def min_signal_count(n_pixels: int, fraction: float) -> int:
+    """Smallest integer count c for which ``c / n_pixels < fraction`` is False, evaluated with
+    the same float64 division/compare as is_empty_frame (scripts/process_videos.py:759-763)."""
+    c = max(0, int(fraction * n_pixels) - 2)
+    while c <= n_pixels and (c / n_pixels < fraction):
+        c += 1
+    while c > 0 and not ((c - 1) / n_pixels < fraction):
+        c -= 1
+    return c
+
+
+def derive_kernel_bounds(scalars: ClipScalars, params: DetectionParams, n_pixels: int) -> KernelBounds:
+    """Turn the reference's float comparisons on integer-valued data into exact integer ones:
+    for integer v and real t:  v > t <=> v > floor(t);  v < t <=> v < ceil(t)."""
+    return KernelBounds(
+        empty_thr=_clamp_i32(math.floor(scalars.noise_threshold)),
+        min_signal_count=min_signal_count(n_pixels, params.min_signal_fraction),
+        diff_thr=_clamp_i32(math.ceil(params.frame_diff_threshold)),
+        threshold_floor=_clamp_i32(math.floor(scalars.flame_threshold)),
+        grad2_bound=_clamp_i32(math.ceil(-2.0 * params.min_gradient_strength)),
+    )
+
+
+@dataclass
+class RangeResult:
+    """Device-resident outputs of one contiguous frame range."""
+    first_frame: int
+    pos: torch.Tensor                 # int32[n]  (>=0, -1 none, -2 dropped after truncate)
+    counts: torch.Tensor              # int32[n]  above-noise pixel count
+    first_exit: torch.Tensor          # int32[1]  global frame index or FF_NO_EXIT
+    diff: Optional[torch.Tensor] = None       # [n,H,W]
+    profiles: Optional[torch.Tensor] = None   # int32[n,W]
+    decoded: Optional[torch.Tensor] = None    # uint16[n,H,W]
+    scalars: Optional[ClipScalars] = None
+
+
+@dataclass
+class HostResult:
+    first_frame: int
+    pos: np.ndarray
+    counts: np.ndarray
+    first_exit: int
+    frames_done: int
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class FlameFrontEngine:
+    """One engine per GPU.  All methods launch on the current torch CUDA stream."""
+
+    def __init__(self, device: Union[int, str, torch.device, None] = None,
+                 host_chunk_bytes: int = 64 << 20):
+        self._lib = _cabi.load()                      # raises if the .so is missing
+        if not torch.cuda.is_available():
+            raise RuntimeError("FlameFrontEngine needs a CUDA device (no CPU fallback exists)")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("FlameFrontEngine runs on CUDA devices only")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._host_chunk_bytes = int(host_chunk_bytes)
+        self._host_ctx: Optional[C.c_void_p] = None
+        self.launches = 0                             # kernels launched through this engine
+        self._side_stream = None
+        self._pinned = {}
+        self._stream_events = None                    # bench hook: [(start, stop)] around ff_stream_frames
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _check_dev(self, t: torch.Tensor, name: str) -> None:
+        if t.device != self.device:
+            raise ValueError(f"{name} must live on {self.device}, got {t.device}")
+        if not t.is_contiguous():
+            raise ValueError(f"{name} must be contiguous")
+
+    def close(self) -> None:
+        if self._host_ctx is not None:
+            self._lib.ff_host_ctx_destroy(self._host_ctx)
+            self._host_ctx = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ stage 1
+    def unpack(self, packed: torch.Tensor, n_frames: int, height: int, width: int, bits: int) -> torch.Tensor:
+        """Decode ``n_frames`` device-resident frames to [n,H,W] (uint16; uint8 for 8-bit)."""
+        self._check_dev(packed, "packed")
+        need = n_frames * frame_nbytes(height, width, bits)
+        if packed.dtype != torch.uint8 or packed.numel() < need:
+            raise ValueError(f"packed must be uint8 with at least {need} bytes")
+        out = torch.empty((n_frames, height, width), dtype=torch.uint8 if bits == 8 else torch.uint16,
+                          device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.ff_unpack(packed.data_ptr(), out.data_ptr(), n_frames, height, width, bits,
+                                            self._stream()), "ff_unpack")
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ stage 2a
+    def background(self, frame0: torch.Tensor, height: int, width: int, bits: int):
+        """Launch the background reduction on frame 0.  Returns device tensors
+        ``(bg_max int32[1], centerline uint16[W])`` without synchronising."""
+        self._check_dev(frame0, "frame0")
+        if frame0.dtype != torch.uint8 or frame0.numel() < frame_nbytes(height, width, bits):
+            raise ValueError("frame0 must be a uint8 tensor holding one whole frame")
+        bg = torch.empty(1, dtype=torch.int32, device=self.device)
+        line = torch.empty(width, dtype=torch.uint16, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.ff_background(frame0.data_ptr(), height, width, bits, bg.data_ptr(),
+                                                line.data_ptr(), self._stream()), "ff_background")
+        self.launches += 1
+        return bg, line
+
+    def _fetch_frame0_stats_async(self, bg_dev: torch.Tensor, line_dev: torch.Tensor):
+        """Copy the background scalar and centre row to pinned host memory on a side stream
+        that depends only on the background kernel, so later work on the main stream does not
+        delay them.  Returns (event, bg_host, line_host)."""
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        side = self._side_stream
+        side.wait_event(ready)
+        key = line_dev.numel()
+        if key not in self._pinned:       # reused: the previous values were consumed under a sync
+            self._pinned[key] = (torch.empty(1, dtype=torch.int32).pin_memory(),
+                                 torch.empty(key, dtype=torch.uint16).pin_memory())
+        bg_host, line_host = self._pinned[key]
+        with torch.cuda.stream(side):
+            bg_host.copy_(bg_dev, non_blocking=True)
+            line_host.copy_(line_dev, non_blocking=True)
+            bg_dev.record_stream(side)
+            line_dev.record_stream(side)
+            done = torch.cuda.Event()
+            done.record(side)
+        return done, bg_host, line_host
+
+    def clip_scalars(self, frame0: torch.Tensor, height: int, width: int, bits: int):
+        """Background reduction + host-side float64 statistics.  Synchronises on two tiny D2H
+        copies.  Returns ``(ClipScalars, bg_dev)``."""
+        bg, line = self.background(frame0, height, width, bits)
+        bg_host = int(bg.cpu().item())
+        line_host = line.cpu().numpy()
+        return ClipScalars.from_frame0_stats(bg_host, line_host), bg
+
+    # ------------------------------------------------------------------ stages 2b-4
+    def process_range(self, frames: torch.Tensor, n_frames: int, height: int, width: int, bits: int,
+                      params: DetectionParams, scalars: Optional[ClipScalars] = None,
+                      bg_dev: Optional[torch.Tensor] = None, *, frame0: Optional[torch.Tensor] = None,
+                      first_frame: int = 0, halo: Optional[torch.Tensor] = None,
+                      skip: Optional[torch.Tensor] = None, diff_dtype: Optional[str] = None,
+                      keep_profiles: bool = False, keep_decoded: bool = False,
+                      first_exit: Optional[torch.Tensor] = None, truncate: bool = True,
+                      partial: Optional[torch.Tensor] = None) -> RangeResult:
+        """Fused front end + detection + exit min (+ local truncation) on a device-resident
+        contiguous frame range.  Nothing but two tiny scalars ever goes to the host.
+
+        Either pass ``scalars``/``bg_dev`` from :meth:`clip_scalars`, or pass ``frame0`` (the
+        clip's first frame, packed, on the device; defaults to ``frames[0]`` when
+        ``first_frame == 0``): then the background reduction is launched first, the streaming
+        kernel starts right behind it with device-side thresholds, and the host computes the
+        float64 centre-row statistics while that kernel runs - the GPU never waits for the host."""
+        self._check_dev(frames, "frames")
+        fb = frame_nbytes(height, width, bits)
+        if frames.dtype != torch.uint8 or frames.numel() < n_frames * fb:
+            raise ValueError(f"frames must be uint8 with at least {n_frames * fb} bytes")
+        if halo is not None:
+            self._check_dev(halo, "halo")
+            if halo.dtype != torch.uint8 or halo.numel() < fb:
+                raise ValueError("halo must be a uint8 tensor holding one whole frame")
+        if skip is not None:
+            self._check_dev(skip, "skip")
+            if skip.dtype != torch.uint8 or skip.numel() != n_frames:
+                raise ValueError("skip must be uint8[n_frames]")
+        if diff_dtype not in _DIFF_DTYPES:
+            raise ValueError(f"diff_dtype must be one of {list(_DIFF_DTYPES)}")
+        if params.method == "gradient" and width < 2:
+            raise ValueError("Shape of array too small to calculate a numerical gradient, "
+                             "at least 2 elements are required.")  # np.gradient's own error
+        if (scalars is None) != (bg_dev is None):
+            raise ValueError("pass scalars and bg_dev together (from clip_scalars), or neither")
+        diff_code, diff_torch = _DIFF_DTYPES[diff_dtype]
+        diff_thr = _clamp_i32(math.ceil(params.frame_diff_threshold))
+        if diff_code == FF_DIFF_U16 and diff_thr < 0:
+            raise ValueError("uint16 difference images need frame_diff_threshold >= 0")
+
+        line_dev = None
+        if scalars is None:
+            if frame0 is None:
+                if first_frame != 0:
+                    raise ValueError("frame0 (the clip's first frame) is required for a sub-range")
+                frame0 = frames[:fb]
+            bg_dev, line_dev = self.background(frame0, height, width, bits)
+            fetch = self._fetch_frame0_stats_async(bg_dev, line_dev)
+            empty_thr = -1            # derived on the device: floor(max(10, bg/2))  (:1458)
+        else:
+            empty_thr = _clamp_i32(math.floor(scalars.noise_threshold))
+
+        n_elems = C.c_int64(0)
+        tiles = C.c_int(0)
+        _cabi.check(self._lib.ff_partial_len(n_frames, height, width, bits, C.byref(n_elems), C.byref(tiles)),
+                    "ff_partial_len")
+        if partial is None or partial.numel() < n_elems.value:
+            partial = torch.empty(max(1, n_elems.value), dtype=torch.int32, device=self.device)
+        pos = torch.empty(n_frames, dtype=torch.int32, device=self.device)
+        counts = torch.empty(n_frames, dtype=torch.int32, device=self.device)
+        if first_exit is None:
+            first_exit = torch.full((1,), FF_NO_EXIT, dtype=torch.int32, device=self.device)
+        diff = None if diff_torch is None else torch.empty((n_frames, height, width), dtype=diff_torch,
+                                                           device=self.device)
+        profiles = torch.zeros((n_frames, width), dtype=torch.int32, device=self.device) if keep_profiles else None
+        decoded = torch.empty((n_frames, height, width), dtype=torch.uint16,
+                              device=self.device) if keep_decoded else None
+        st = self._stream()
+        with torch.cuda.device(self.device):
+            ev = self._stream_events
+            if ev is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            _cabi.check(self._lib.ff_stream_frames(
+                frames.data_ptr(), _ptr(halo), n_frames, height, width, bits, bg_dev.data_ptr(),
+                empty_thr, diff_thr, _ptr(skip), partial.data_ptr(), _ptr(diff), diff_code,
+                _ptr(decoded), st), "ff_stream_frames")
+            if ev is not None:
+                e1.record()
+                ev.append((e0, e1))
+            if scalars is None:       # host statistics overlap with the streaming kernel
+                done, bg_host, line_host = fetch
+                done.synchronize()
+                scalars = ClipScalars.from_frame0_stats(int(bg_host.item()), line_host.numpy())
+            kb = derive_kernel_bounds(scalars, params, height * width)
+            _cabi.check(self._lib.ff_detect(
+                frames.data_ptr(), _ptr(halo), n_frames, first_frame, height, width, bits, bg_dev.data_ptr(),
+                partial.data_ptr(), kb.min_signal_count, FF_METHOD[params.method], int(params.use_frame_diff),
+                kb.diff_thr, kb.threshold_floor, kb.grad2_bound, params.min_run_px, params.exit_margin_px,
+                _ptr(skip), pos.data_ptr(), counts.data_ptr(), first_exit.data_ptr(), _ptr(profiles), st),
+                "ff_detect")
+            self.launches += 2
+            if truncate:
+                self.truncate(pos, first_frame, first_exit)
+        return RangeResult(first_frame, pos, counts, first_exit, diff, profiles, decoded, scalars)
+
+    def truncate(self, pos: torch.Tensor, first_frame: int, first_exit: torch.Tensor) -> None:
+        """Mark frames at/after the (global) first exit frame as dropped (README.md:145-149)."""
+        self._check_dev(pos, "pos")
+        self._check_dev(first_exit, "first_exit")
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.ff_truncate(pos.data_ptr(), pos.numel(), first_frame, first_exit.data_ptr(),
+                                              self._stream()), "ff_truncate")
+        self.launches += 1
+
+    # ------------------------------------------------------------------ host-resident clips
+    def process_host(self, frames: Union[np.ndarray, torch.Tensor], n_frames: int, height: int, width: int,
+                     bits: int, params: DetectionParams, scalars: ClipScalars, *, first_frame: int = 0,
+                     halo: Union[np.ndarray, torch.Tensor, None] = None,
+                     skip: Optional[np.ndarray] = None) -> HostResult:
+        """End-to-end form: frames live in host memory (pinned tensor or mmapped file); chunks
+        are copied H2D double-buffered against the kernels; blocks until results are on the host."""
+        fb = frame_nbytes(height, width, bits)
+        src_ptr, src_bytes, _keep = _host_buffer(frames)
+        if src_bytes < n_frames * fb:
+            raise ValueError(f"frames hold {src_bytes} bytes, need {n_frames * fb}")
+        halo_ptr = None
+        if halo is not None:
+            halo_ptr, hb, _keep_h = _host_buffer(halo)
+            if hb < fb:
+                raise ValueError("halo must hold one whole frame")
+        skip_ptr = None
+        if skip is not None:
+            skip = np.ascontiguousarray(skip, dtype=np.uint8)
+            if skip.size != n_frames:
+                raise ValueError("skip must have n_frames entries")
+            skip_ptr = skip.ctypes.data
+        if params.method == "gradient" and width < 2:
+            raise ValueError("Shape of array too small to calculate a numerical gradient, "
+                             "at least 2 elements are required.")
+        kb = derive_kernel_bounds(scalars, params, height * width)
+        if self._host_ctx is None:
+            ctx = C.c_void_p()
+            _cabi.check(self._lib.ff_host_ctx_create(self.device.index, self._host_chunk_bytes, C.byref(ctx)),
+                        "ff_host_ctx_create")
+            self._host_ctx = ctx
+        pos = np.empty(n_frames, dtype=np.int32)
+        counts = np.empty(n_frames, dtype=np.int32)
+        done = C.c_int64(0)
+        fexit = C.c_int32(FF_NO_EXIT)
+        _cabi.check(self._lib.ff_process_host(
+            self._host_ctx, src_ptr, halo_ptr, n_frames, first_frame, height, width, bits,
+            int(scalars.background), kb.empty_thr, kb.min_signal_count, FF_METHOD[params.method],
+            int(params.use_frame_diff), kb.diff_thr, kb.threshold_floor, kb.grad2_bound, params.min_run_px,
+            params.exit_margin_px, skip_ptr, pos.ctypes.data, counts.ctypes.data, C.byref(done), C.byref(fexit)),
+            "ff_process_host")
+        n_chunks = -(-n_frames // max(1, self._host_chunk_bytes // fb))
+        self.launches += 2 * n_chunks + 1
+        return HostResult(first_frame, pos, counts, int(fexit.value), int(done.value))
+
+
+def _host_buffer(buf: Union[np.ndarray, torch.Tensor]):
+    """(pointer, nbytes, keep-alive) of a contiguous host buffer."""
+    if isinstance(buf, torch.Tensor):
+        if buf.device.type != "cpu" or not buf.is_contiguous():
+            raise ValueError("host frames must be a contiguous CPU tensor")
+        return buf.data_ptr(), buf.numel() * buf.element_size(), buf
+    arr = np.asarray(buf)
+    if not arr.flags["C_CONTIGUOUS"]:
+        raise ValueError("host frames must be C-contiguous")
+    return arr.ctypes.data, arr.nbytes, arr
+
+
+_engines = {}
+
+
+def get_engine(device: Union[int, str, torch.device, None] = None) -> FlameFrontEngine:
+    """Process-wide engine per device (created on first use; raises without CUDA/the library)."""
+    _cabi.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "the flame-front path needs a CUDA device: libflamefront has no CPU implementation")
+    if device is None:
+        idx = torch.cuda.current_device()
+    else:
+        dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _engines:
+        _engines[idx] = FlameFrontEngine(idx)
+    return _engines[idx]

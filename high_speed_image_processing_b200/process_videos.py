@@ -1,0 +1,342 @@
+"""Drop-in for the reference's ``scripts/process_videos.py`` on the flame-front path.
+
+Same configuration objects (``VideoSourceConfig`` - with the README's ``detection_method``
+switch, README.md:53-63 -, ``FileCalibration``), same ``process_video_source(config,
+processor)`` / ``main()`` entry points, same result tuples and text output; the frame loop of
+the reference (scripts/process_videos.py:1441-1516) is replaced by the B200 engine:
+
+    frame 0 -> ff_background -> host float64 statistics            (:1357-1370)
+    packed frames -> ff_stream_frames (one HBM read per frame)     (:1455-1463, :397-399)
+                  -> ff_detect (warp per profile) -> exit atomicMin (:1488-1494)
+    [multi-GPU: all-reduce(min) of the exit frame, all-gather of positions]
+    -> ff_truncate -> host: Time_s, Position_m, text files         (:1449-1452, :1512, :1561-1619)
+
+Matplotlib diagnostics (:783-1270) are out of scope and never on this path.
+"""
+from __future__ import annotations
+
+import os
+import re
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .engine import ClipScalars, DetectionParams, DETECTION_METHODS
+from .photron import MPIVideoProcessor, PhotonVideo, SpatialCalibration, open_video
+
+_REPO_ROOT = Path(__file__).resolve().parent.parent
+
+
+# --------------------------------------------------------------------------------------
+# configuration (reference: scripts/process_videos.py:49-161)
+# --------------------------------------------------------------------------------------
+@dataclass
+class FileCalibration:
+    """Calibration for a subset of files.  ``files`` entries are substrings of the file name
+    or ``"a:b"`` ranges compared on the LAST integer in each name (bug-compatible with the
+    reference, :84-101: ``run-5-_C001H001S0001.cihx`` compares as 1)."""
+    calibration: float
+    position_offset: float = 0.0
+    files: List[str] = field(default_factory=list)
+
+    def matches(self, filename: str) -> bool:
+        for pattern in self.files:
+            if ":" in pattern:
+                lo, hi = pattern.split(":", 1)
+                if self._matches_range(filename, lo.strip(), hi.strip()):
+                    return True
+            elif pattern in filename:
+                return True
+        return False
+
+    def _matches_range(self, filename: str, start: str, end: str) -> bool:
+        nums = [re.findall(r"\d+", s) for s in (start, end, filename)]
+        if not all(nums):
+            return False
+        lo, hi, cur = (int(n[-1]) for n in nums)
+        return lo <= cur <= hi
+
+
+@dataclass
+class VideoSourceConfig:
+    name: str
+    enabled: bool = False
+    calibration: float = 1.0
+    position_offset: float = 0.0
+    trigger_frame: Optional[int] = None
+    use_frame_diff: bool = True
+    use_absolute_time: bool = True
+    skip_frames: List[int] = field(default_factory=list)
+    file_calibrations: List[FileCalibration] = field(default_factory=list)
+    # README-era switch (README.md:55,62,132-141), absent from the reference's HEAD dataclass
+    detection_method: str = "half_maximum"
+    exit_margin_px: int = 10                 # README.md:146 (HEAD's detector uses 15, :193)
+    frame_diff_threshold: float = 5.0        # FlameDetectorConfig.frame_diff_threshold (:169)
+    min_gradient_strength: float = 10.0      # FlameDetectorConfig.min_gradient_strength (:174)
+    min_run_px: int = 1
+
+    _video_path: Optional[str] = field(default=None, init=False, repr=False)
+    _output_dir: Optional[str] = field(default=None, init=False, repr=False)
+
+    @property
+    def video_path(self) -> Optional[str]:
+        return self._video_path
+
+    @video_path.setter
+    def video_path(self, path: Optional[str]) -> None:
+        self._video_path = self._resolve_path(path)
+
+    @property
+    def output_dir(self) -> Optional[str]:
+        return self._output_dir
+
+    @output_dir.setter
+    def output_dir(self, path: Optional[str]) -> None:
+        self._output_dir = self._resolve_path(path)
+
+    def _resolve_path(self, path: Optional[str]) -> Optional[str]:
+        if path is None or os.path.isabs(path):
+            return path
+        return str((_REPO_ROOT / path).resolve())     # relative paths hang off the repo root (:136-143)
+
+    def get_calibration_for_file(self, filename: str) -> Tuple[float, float]:
+        for rule in self.file_calibrations:           # first matching rule wins (:158-161)
+            if rule.matches(filename):
+                return (rule.calibration, rule.position_offset)
+        return (self.calibration, self.position_offset)
+
+    def detection_params(self) -> DetectionParams:
+        if self.detection_method not in DETECTION_METHODS:
+            raise ValueError(f"unknown detection_method {self.detection_method!r}; "
+                             f"options: {', '.join(DETECTION_METHODS)}")
+        return DetectionParams(method=self.detection_method, use_frame_diff=self.use_frame_diff,
+                               frame_diff_threshold=self.frame_diff_threshold,
+                               min_gradient_strength=self.min_gradient_strength,
+                               min_run_px=self.min_run_px, exit_margin_px=self.exit_margin_px)
+
+
+# --------------------------------------------------------------------------------------
+# per-video processing
+# --------------------------------------------------------------------------------------
+ResultRow = Tuple[int, float, int, float, bool]     # (frame, time_s, px, pos_m, is_post_ddt)  (:1516)
+
+
+@dataclass
+class VideoResult:
+    scalars: ClipScalars
+    pos_px: np.ndarray            # int32[N]: >= 0 position, -1 none, -2 dropped by exit truncation
+    nonempty_counts: np.ndarray   # int32[N]
+    first_exit: Optional[int]     # first exit frame (not recorded), None if the flame never exits
+    rows: List[ResultRow]
+    empty_frames: int
+
+    @property
+    def frames(self) -> List[int]:
+        return [r[0] for r in self.rows]
+
+
+def build_rows(video: PhotonVideo, pos_px: np.ndarray, calibration: float, offset: float,
+               use_absolute_time: bool) -> List[ResultRow]:
+    """Host-side scalars, with the reference's own expressions so they are bit-identical:
+    time (:1449-1452 -> src/photron/video.py:220,240-241) and pos_m = px*cal + off (:1512)."""
+    rows: List[ResultRow] = []
+    for frame_idx in np.nonzero(pos_px >= 0)[0].tolist():
+        px = int(pos_px[frame_idx])
+        time_s = video.get_absolute_time(frame_idx) if use_absolute_time else video.get_time(frame_idx)
+        rows.append((frame_idx, time_s, px, px * calibration + offset, False))
+    return rows
+
+
+def process_video(video: PhotonVideo, config: VideoSourceConfig, calibration: float, offset: float,
+                  engine=None, exchange=None, residency: str = "auto",
+                  device_budget_bytes: int = 64 << 30) -> VideoResult:
+    """Run the flame-front path on one recording.
+
+    ``residency``: "device" uploads the (rank's) packed frames once and runs the
+    device-resident kernels; "host" streams chunks from the mmapped file through
+    ``ff_process_host``; "auto" picks "device" when the range fits ``device_budget_bytes``.
+    ``exchange`` (a ``sharding.RangeExchange``) splits the clip into contiguous frame ranges
+    across ranks; results are identical on every rank.
+    """
+    import torch
+    from .engine import get_engine
+    from ._cabi import FF_NO_EXIT
+
+    eng = engine if engine is not None else get_engine()
+    params = config.detection_params()
+    n, (h, w), bits = len(video), video.frame_shape, video.storage_bits
+    if n == 0:
+        raise ValueError("video has no frames")
+
+    # per-clip scalars from frame 0 (every rank reads frame 0 itself: 1 frame of H2D)
+    frame0 = torch.from_numpy(np.ascontiguousarray(video.raw_frames(0, 1))).to(eng.device)
+    scalars, bg_dev = eng.clip_scalars(frame0, h, w, bits)
+
+    skip_np = None
+    if config.skip_frames:
+        skip_np = np.zeros(n, dtype=np.uint8)
+        for s in config.skip_frames:
+            if 0 <= s < n:
+                skip_np[s] = 1
+
+    a, b = (0, n) if exchange is None else exchange.my_range(n)
+    halo_idx = a - 1
+    if skip_np is not None:
+        while halo_idx >= 0 and skip_np[halo_idx]:
+            halo_idx -= 1
+    halo_np = video.raw_frames(halo_idx, halo_idx + 1) if halo_idx >= 0 else None
+
+    nbytes = (b - a) * video.frame_store.frame_bytes
+    multi = exchange is not None and exchange.size > 1
+    if residency == "auto":
+        residency = "device" if (nbytes <= device_budget_bytes or multi) else "host"
+    if residency not in ("device", "host"):
+        raise ValueError("residency must be 'auto', 'device' or 'host'")
+
+    if b - a == 0:
+        pos_local = torch.empty(0, dtype=torch.int32, device=eng.device)
+        cnt_local = torch.empty(0, dtype=torch.int32, device=eng.device)
+        fe_local = torch.full((1,), FF_NO_EXIT, dtype=torch.int32, device=eng.device)
+    elif residency == "device" or multi:
+        frames_dev = torch.from_numpy(np.ascontiguousarray(video.raw_frames(a, b))).to(eng.device)
+        halo_dev = None if halo_np is None else torch.from_numpy(np.ascontiguousarray(halo_np)).to(eng.device)
+        skip_dev = None if skip_np is None else torch.from_numpy(skip_np[a:b].copy()).to(eng.device)
+        res = eng.process_range(frames_dev, b - a, h, w, bits, params, scalars, bg_dev, first_frame=a,
+                                halo=halo_dev, skip=skip_dev, truncate=not multi)
+        pos_local, cnt_local, fe_local = res.pos, res.counts, res.first_exit
+    else:
+        hres = eng.process_host(video.raw_frames(a, b), b - a, h, w, bits, params, scalars, first_frame=a,
+                                halo=halo_np, skip=None if skip_np is None else skip_np[a:b])
+        pos_np, cnt_np, first_exit = hres.pos, hres.counts, hres.first_exit
+        pos_local = cnt_local = fe_local = None
+
+    if pos_local is not None:
+        if multi:
+            g = exchange.finish(pos_local, fe_local, n, eng.truncate, counts_local=cnt_local)
+            pos_np, cnt_np, first_exit = g.pos.cpu().numpy(), g.counts.cpu().numpy(), g.first_exit
+        else:
+            pos_np, cnt_np = pos_local.cpu().numpy(), cnt_local.cpu().numpy()
+            first_exit = int(fe_local.cpu().item())
+
+    kb_min = eng_min_signal(params, h * w)
+    processed = np.ones(n, dtype=bool) if skip_np is None else skip_np == 0
+    limit = n if first_exit == FF_NO_EXIT else first_exit
+    empty_frames = int(np.count_nonzero((cnt_np[:limit] < kb_min) & processed[:limit]))
+    rows = build_rows(video, pos_np, calibration, offset, config.use_absolute_time)
+    return VideoResult(scalars, pos_np, cnt_np, None if first_exit == FF_NO_EXIT else first_exit, rows,
+                       empty_frames)
+
+
+def eng_min_signal(params: DetectionParams, n_pixels: int) -> int:
+    from .engine import min_signal_count
+    return min_signal_count(n_pixels, params.min_signal_fraction)
+
+
+# --------------------------------------------------------------------------------------
+# output files
+# --------------------------------------------------------------------------------------
+def write_position_file(rows: Sequence[ResultRow], filepath) -> str:
+    """The README's 4-column result file (README.md:90-97): space separated, ``.9f`` floats."""
+    with open(filepath, "w") as fh:
+        fh.write("#Frame Time_s Position_px Position_m\n")
+        for frame_idx, t_s, px, p_m, _ in rows:
+            fh.write(f"{frame_idx} {t_s:.9f} {px} {p_m:.9f}\n")
+    return str(filepath)
+
+
+# --------------------------------------------------------------------------------------
+# driver (reference: scripts/process_videos.py:1277-1629, :1633-1703)
+# --------------------------------------------------------------------------------------
+def process_video_source(config: VideoSourceConfig, processor: Optional[MPIVideoProcessor] = None,
+                         engine=None, exchange=None, verbose: bool = True) -> Dict[str, VideoResult]:
+    """Process every ``*.cihx`` under ``config.video_path`` and write the result files."""
+    is_root = (processor is None or processor.is_root) and (exchange is None or exchange.rank == 0)
+    say = print if (verbose and is_root) else (lambda *a, **k: None)
+    say(f"\n{'=' * 60}\nProcessing: {config.name}\nVideo path: {config.video_path}")
+    say(f"Detection method: {config.detection_method}")
+    say(f"Default calibration: {config.calibration} m/pixel, offset: {config.position_offset} m")
+
+    cihx_files = sorted(Path(config.video_path).rglob("*.cihx"))
+    results: Dict[str, VideoResult] = {}
+    if not cihx_files:
+        say(f"No CIHX files found in {config.video_path}")
+        return results
+
+    for cihx_file in cihx_files:
+        cal, off = config.get_calibration_for_file(cihx_file.name)
+        say(f"\nLoading: {cihx_file.name}\n  Using calibration: {cal} m/pixel, offset: {off} m")
+        video = open_video(str(cihx_file), trigger_frame=config.trigger_frame,
+                           calibration=SpatialCalibration(scale=cal, units="m"))
+        try:
+            say(f"  Frames: {len(video)}  rate: {video.frame_rate} fps  shape: {video.frame_shape}")
+            res = process_video(video, config, cal, off, engine=engine, exchange=exchange)
+            sc = res.scalars
+            say(f"  Background scalar: {sc.background}")
+            say(f"  Centerline noise (from frame 0): mean={sc.centerline_mean:.1f}, "
+                f"std={sc.centerline_std:.1f}, max={sc.centerline_max:.1f}")
+            say(f"  Centerline flame threshold: {sc.flame_threshold:.1f}")
+            if res.first_exit is not None:
+                say(f"  Wave exited domain at frame {res.first_exit} (not recorded)")
+            say(f"  Skipped {res.empty_frames} empty/noise-only frames; {len(res.rows)} detections")
+            if is_root and res.rows and config.output_dir:
+                out_dir = Path(config.output_dir)
+                out_dir.mkdir(parents=True, exist_ok=True)
+                path = write_position_file(res.rows, out_dir / f"{cihx_file.stem}-flame-position.txt")
+                say(f"  All results: {path} ({len(res.rows)} points)")
+            results[cihx_file.name] = res
+        finally:
+            video.close()
+    return results
+
+
+def default_configs() -> List[VideoSourceConfig]:
+    """The two sources hard-coded in the reference's main() (:1646-1685) with the README's
+    method choice per camera (README.md:55,62)."""
+    nova = VideoSourceConfig(name="Nova")
+    nova.enabled = True
+    nova.detection_method = "half_maximum"
+    nova.video_path = "./Nova-Video-Files"
+    nova.output_dir = "./Processed-Photos/Nova-Output"
+    nova.file_calibrations = [
+        FileCalibration(calibration=0.000833333, position_offset=1.0159, files=["run-1-"]),
+        FileCalibration(calibration=0.000833333, position_offset=1.197565, files=["run-2-"]),
+        FileCalibration(calibration=0.000833333, position_offset=1.347567, files=["run-3-:run-10-"]),
+    ]
+    mini = VideoSourceConfig(name="Mini")
+    mini.enabled = True
+    mini.detection_method = "threshold"
+    mini.video_path = "./Mini-Video-Files"
+    mini.output_dir = "./Processed-Photos/Mini-Output"
+    mini.file_calibrations = [
+        FileCalibration(calibration=0.000869565, position_offset=0.050237, files=["run-1-:run-10-"]),
+    ]
+    return [nova, mini]
+
+
+def main() -> None:
+    """One process per GPU under torchrun (NCCL), or a single process on cuda:0."""
+    import torch
+    import torch.distributed as dist
+    from .sharding import RangeExchange
+
+    exchange = None
+    if "RANK" in os.environ and "WORLD_SIZE" in os.environ:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+        exchange = RangeExchange()
+        if exchange.rank == 0:
+            print(f"Running on {exchange.size} GPUs")
+    for cfg in default_configs():
+        if cfg.enabled and cfg.video_path and Path(cfg.video_path).exists():
+            process_video_source(cfg, None, exchange=exchange)
+    if exchange is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if exchange is None or exchange.rank == 0:
+        print("\nProcessing complete!")
+
+
+if __name__ == "__main__":
+    main()

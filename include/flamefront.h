@@ -1,0 +1,175 @@
+/*
+ * flamefront.h - C-ABI of libflamefront.so, the B200 (sm_100a) implementation of the
+ * per-frame flame-front path of Nadexterbrown/High-Speed-Image-Processing.
+ *
+ * The reference has no FFI: its seams are plain Python calls.
+ * Each entry point below names the reference interface it replaces (paths are relative
+ * to the reference repository root).  The ctypes binding a maintainer would add is in
+ * INTEGRATION.md; the binding this repo ships is
+ * high_speed_image_processing_b200/_cabi.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ / torch types cross this boundary;
+ *   - every function returns 0 (FF_OK) or a negative FF_ERR_* code, never throws;
+ *   - "dev" pointers are device memory owned by the caller (e.g. a torch tensor's
+ *     data_ptr()); "host" pointers are host memory owned by the caller;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all
+ *     device-resident calls are asynchronous on that stream;
+ *   - frames are stored exactly as in a Photron .mraw file: frame-major, row-major,
+ *     8-bit, little-endian 16-bit, or packed 12-bit (3 bytes = 2 pixels:
+ *     p0 = b0<<4 | b1>>4, p1 = (b1&15)<<8 | b2), `bits` selects which (the CIH "Color Bit");
+ *   - positions are int32: >= 0 detected column, FF_POS_NONE (-1) no detection / empty /
+ *     skipped frame, FF_POS_DROPPED (-2) removed by flame-exit truncation.
+ */
+#ifndef FLAMEFRONT_H_
+#define FLAMEFRONT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FF_ABI_VERSION 1
+
+/* status codes */
+#define FF_OK                 0
+#define FF_ERR_INVALID       -1   /* bad argument (NULL pointer, non-positive size, ...) */
+#define FF_ERR_UNSUPPORTED   -2   /* bit depth / shape / dtype this build cannot handle   */
+#define FF_ERR_CUDA          -3   /* a CUDA runtime call failed; see ff_last_cuda_error() */
+#define FF_ERR_NO_DEVICE     -4   /* no CUDA device / driver                              */
+#define FF_ERR_ALIGNMENT     -5   /* pointer not aligned as the entry point requires      */
+
+/* detection_method switch (README.md:55,62,132-141; VideoSourceConfig.detection_method) */
+#define FF_METHOD_THRESHOLD     0
+#define FF_METHOD_GRADIENT      1
+#define FF_METHOD_HALF_MAXIMUM  2
+
+/* dtype of the retained full-frame difference image */
+#define FF_DIFF_NONE  0
+#define FF_DIFF_U16   1   /* lossless when diff_thr >= 0: values are integers in [0,65535] */
+#define FF_DIFF_F32   2
+#define FF_DIFF_F64   3   /* the reference's own dtype (float64)                        */
+
+#define FF_POS_NONE     (-1)
+#define FF_POS_DROPPED  (-2)
+#define FF_NO_EXIT      2147483647   /* value of *first_exit when the flame never exits */
+
+/* ---- library ------------------------------------------------------------------- */
+int         ff_abi_version(void);
+const char* ff_strerror(int status);
+const char* ff_last_cuda_error(void);          /* thread-local text of the last CUDA failure */
+int         ff_device_count(int* count);
+int         ff_device_sm_count(int device, int* sm_count);
+
+/* ---- scratch sizing ---------------------------------------------------------------
+ * ff_stream_frames writes per-(frame,tile) counts of above-noise pixels into a caller-owned
+ * int32 scratch array; ff_detect sums them.  ff_partial_len returns its length in int32
+ * elements and the tile count per frame for a given frame shape.                       */
+int ff_partial_len(int64_t n_frames, int height, int width, int bits,
+                   int64_t* n_elems, int* tiles_per_frame);
+
+/* ---- stage 1: decode ------------------------------------------------------------------
+ * Replaces pyMRAW.load_video's 12-bit unpack (call site src/photron/video.py:332) and the
+ * per-frame copy in PhotonVideo.__getitem__ (src/photron/video.py:575-582).
+ * packed_dev: n_frames*H*W*bits/8 bytes; out_dev: uint16[n_frames*H*W] (uint8 for bits=8). */
+int ff_unpack(const void* packed_dev, void* out_dev, int64_t n_frames, int height, int width,
+              int bits, void* stream);
+
+/* ---- stage 2a: background-frame reduction ------------------------------------------------
+ * Replaces `background_scalar = float(np.max(video[0]))` (scripts/process_videos.py:1357-1358)
+ * and the centre-row extraction at :1361-1362.  The float64 mean/std/max and the flame
+ * threshold (:1363-1370) stay on the host, computed from centerline_dev's W values.
+ * bg_max_dev: int32[1]; centerline_dev: uint16[W] (row H/2 of the frame), nullable.       */
+int ff_background(const void* frame0_dev, int height, int width, int bits,
+                  int32_t* bg_max_dev, uint16_t* centerline_dev, void* stream);
+
+/* ---- stage 2b: fused front end ----------------------------------------------------------
+ * One HBM read per frame.  Replaces, per frame, subtract_scalar_background
+ * (scripts/process_videos.py:670-674, called at :1455 and :380), the pixel count inside
+ * is_empty_frame (:759, called at :1458-1459) and, when diff_dtype != FF_DIFF_NONE, the
+ * full-frame difference `d = sub_t - sub_{t-1}; d[d < thr] = 0` (:397-399, :677-701) with the
+ * prior-frame carry of :469/:1462.
+ *   frames_dev   n_frames frames, base 16-byte aligned
+ *   halo_dev     the frame preceding frames_dev[0] (same encoding) or NULL
+ *   bg_dev       int32[1] background scalar (output of ff_background)
+ *   empty_thr    pixel is "signal" iff max(x-bg,0) > empty_thr; pass < 0 to derive
+ *                floor(max(10, bg/2)) from *bg_dev on the device (:1458)
+ *   diff_thr     ceil(frame_diff_threshold); differences < diff_thr become 0
+ *   skip_dev     uint8[n_frames], nonzero = frame listed in skip_frames (:1443-1445), nullable
+ *   partial_dev  int32[ff_partial_len] scratch, fully overwritten
+ *   diff_out_dev [n_frames,H,W] of diff_dtype, nullable iff diff_dtype == FF_DIFF_NONE;
+ *                frames without a prior (first frame, skipped frames) are written as zeros
+ *   decoded_out_dev uint16[n_frames,H,W] decoded pixels (12-bit input only), nullable      */
+int ff_stream_frames(const void* frames_dev, const void* halo_dev, int64_t n_frames,
+                     int height, int width, int bits,
+                     const int32_t* bg_dev, int32_t empty_thr, int32_t diff_thr,
+                     const uint8_t* skip_dev, int32_t* partial_dev,
+                     void* diff_out_dev, int diff_dtype, uint16_t* decoded_out_dev,
+                     void* stream);
+
+/* ---- stage 3 + 4a: warp-per-profile detection and first-exit min ---------------------------
+ * Replaces the centre-row profile extraction (scripts/process_videos.py:375-376,417-418), the
+ * empty-frame decision (:761-763), the detection_method switch (README.md:132-141; gradient =
+ * HEAD Method A, :413,427-430) and the exit test (:1488-1494).
+ *   first_frame       clip-global index of frames_dev[0] (exit frames are reported globally)
+ *   min_signal_count  a frame is empty iff its above-noise count < min_signal_count
+ *   use_frame_diff    profile = centre row of the difference image (1) or of the
+ *                     background-subtracted image (0)   (VideoSourceConfig.use_frame_diff)
+ *   threshold_floor   threshold method: pixel is "high" iff p > threshold_floor
+ *                     ( = floor(centerline_flame_threshold), :1367-1370 )
+ *   grad2_bound       gradient method: valid iff 2*g_min < grad2_bound
+ *                     ( = ceil(-2*min_gradient_strength), :174,428 )
+ *   min_run_px        threshold method: minimum run length (>= 1)
+ *   exit_margin_px    exit iff pos >= W - exit_margin_px (README.md:146; HEAD :193 uses 15)
+ *   pos_out_dev       int32[n_frames]
+ *   count_out_dev     int32[n_frames] above-noise pixel count per frame, nullable
+ *   first_exit_dev    int32[1]; atomicMin'ed with the global index of every exit frame; the
+ *                     caller initialises it to FF_NO_EXIT (or a previous chunk's value)
+ *   profile_out_dev   int32[n_frames,W], nullable                                            */
+int ff_detect(const void* frames_dev, const void* halo_dev, int64_t n_frames, int64_t first_frame,
+              int height, int width, int bits,
+              const int32_t* bg_dev, const int32_t* partial_dev, int64_t min_signal_count,
+              int method, int use_frame_diff, int32_t diff_thr,
+              int32_t threshold_floor, int32_t grad2_bound, int32_t min_run_px,
+              int32_t exit_margin_px, const uint8_t* skip_dev,
+              int32_t* pos_out_dev, int32_t* count_out_dev, int32_t* first_exit_dev,
+              int32_t* profile_out_dev, void* stream);
+
+/* ---- stage 4b: truncation ----------------------------------------------------------------
+ * README.md:145-149: everything from the first exit frame on is dropped.  Frames whose
+ * global index (first_frame + i) >= *first_exit_dev get FF_POS_DROPPED.  In a multi-GPU
+ * run *first_exit_dev holds the all-reduced (min) value.                                   */
+int ff_truncate(int32_t* pos_dev, int64_t n_frames, int64_t first_frame,
+                const int32_t* first_exit_dev, void* stream);
+
+/* ---- host-resident clips: chunked H2D streaming -----------------------------------------------
+ * The end-to-end form of stages 2b-4 for a clip that lives in host memory (pinned, or the
+ * mmapped .mraw file): replaces the whole frame loop of process_video_source
+ * (scripts/process_videos.py:1441-1516) for one video / one contiguous frame range.
+ * Frames are copied in chunks on a copy stream, double-buffered against the kernels; once a
+ * finished chunk has reported an exit frame no further chunks are copied (the reference
+ * `break`s at :1494).  Blocking: returns when pos_out_host/count_out_host are complete.
+ *   ctx               from ff_host_ctx_create (owns staging buffers, streams, events)
+ *   frames_host       n_frames frames; halo_host the frame before them or NULL
+ *   bg                background scalar by value (host already synchronised on it)
+ *   frames_done_out   number of leading frames actually processed (== n_frames unless an
+ *                     exit stopped the copy early); frames beyond it hold FF_POS_DROPPED
+ *   first_exit_out    global index of the first exit frame or FF_NO_EXIT                     */
+typedef struct ff_host_ctx ff_host_ctx;
+int ff_host_ctx_create(int device, int64_t chunk_bytes, ff_host_ctx** ctx_out);
+int ff_host_ctx_destroy(ff_host_ctx* ctx);
+int ff_process_host(ff_host_ctx* ctx,
+                    const void* frames_host, const void* halo_host, int64_t n_frames,
+                    int64_t first_frame, int height, int width, int bits,
+                    int32_t bg, int32_t empty_thr, int64_t min_signal_count,
+                    int method, int use_frame_diff, int32_t diff_thr,
+                    int32_t threshold_floor, int32_t grad2_bound, int32_t min_run_px,
+                    int32_t exit_margin_px, const uint8_t* skip_host,
+                    int32_t* pos_out_host, int32_t* count_out_host,
+                    int64_t* frames_done_out, int32_t* first_exit_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLAMEFRONT_H_ */

@@ -1,0 +1,97 @@
+"""Multi-rank host logic on CPU: range partition, exit-min all-reduce, result all-gather,
+global truncation.  world_size 2 and 3 over gloo; the per-rank 'kernel output' is the oracle
+evaluated on the rank's contiguous range with its one-frame halo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from high_speed_image_processing_b200 import synthetic as syn
+from high_speed_image_processing_b200.sharding import RangeExchange, assign_videos, contiguous_range
+from high_speed_image_processing_b200._cabi import FF_NO_EXIT, FF_POS_DROPPED
+from oracle import flame_oracle as fo
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _torch_truncate(pos, first_frame, first_exit):
+    idx = torch.arange(first_frame, first_frame + pos.numel())
+    pos.masked_fill_(idx >= first_exit.to(torch.int64), FF_POS_DROPPED)
+
+
+def _worker(rank, size, port, n_frames, margin, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        spec = syn.SyntheticSpec(width=96, height=8, n_frames=n_frames, style="mini", t_enter=6.0, velocity=2.0,
+                                 curvature_px=1.0, seed=11)
+        frames = syn.render_frames(spec)
+        ex = RangeExchange()
+        a, b = ex.my_range(n_frames)
+        params = fo.ClipParams(method="threshold", exit_margin_px=margin)
+        part = fo.process_clip(frames[a:b], params, frame0=frames[0], first_index=a,
+                               prior_frame=frames[a - 1] if a > 0 else None)
+        pos_local = torch.from_numpy(part.pos_px.copy())
+        fe = FF_NO_EXIT if part.first_exit == b - a else a + part.first_exit
+        g = ex.finish(pos_local, torch.tensor([fe], dtype=torch.int32), n_frames, _torch_truncate,
+                      counts_local=torch.from_numpy(part.nonempty.astype(np.int32)))
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), pos=g.pos.numpy(), counts=g.counts.numpy(),
+                 first_exit=g.first_exit)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("size,n_frames", [(2, 61), (3, 64)])
+def test_range_sharded_run_equals_serial(tmp_path, size, n_frames):
+    margin = 10
+    mp.spawn(_worker, args=(size, _free_port(), n_frames, margin, str(tmp_path)), nprocs=size, join=True)
+    spec = syn.SyntheticSpec(width=96, height=8, n_frames=n_frames, style="mini", t_enter=6.0, velocity=2.0,
+                             curvature_px=1.0, seed=11)
+    serial = fo.process_clip(syn.render_frames(spec), fo.ClipParams(method="threshold", exit_margin_px=margin))
+    assert serial.first_exit < n_frames, "fixture must contain an exit"
+    want = serial.pos_px.copy()
+    want[serial.first_exit:] = FF_POS_DROPPED
+    for r in range(size):
+        z = np.load(tmp_path / f"r{r}.npz")
+        assert int(z["first_exit"]) == serial.first_exit
+        assert np.array_equal(z["pos"], want)
+        assert np.array_equal(z["counts"], serial.nonempty.astype(np.int32))
+
+
+def test_contiguous_range_is_the_reference_partition(golden):
+    for key, want in golden["distribute_indices"].items():
+        total, size, strategy = key.split("/")
+        if strategy != "contiguous":
+            continue
+        for r in range(int(size)):
+            a, b = contiguous_range(int(total), r, int(size))
+            assert list(range(a, b)) == want[r]
+    with pytest.raises(ValueError):
+        contiguous_range(5, 3, 3)
+
+
+def test_assign_videos():
+    assert [assign_videos(10, r, 4) for r in range(4)] == [[0, 4, 8], [1, 5, 9], [2, 6], [3, 7]]
+    w = [5, 1, 1, 1, 4, 4]
+    parts = [assign_videos(6, r, 2, weights=w) for r in range(2)]
+    assert sorted(parts[0] + parts[1]) == list(range(6))
+    assert abs(sum(w[i] for i in parts[0]) - sum(w[i] for i in parts[1])) <= 1
+    with pytest.raises(ValueError):
+        assign_videos(3, 0, 2, weights=[1])
+
+
+def test_single_process_exchange_is_identity():
+    ex = RangeExchange()
+    assert (ex.rank, ex.size) == (0, 1) and ex.my_range(9) == (0, 9)
+    pos = torch.tensor([1, 2, 90, 3], dtype=torch.int32)
+    g = ex.finish(pos, torch.tensor([2], dtype=torch.int32), 4, _torch_truncate)
+    assert g.first_exit == 2 and g.pos.tolist() == [1, 2, FF_POS_DROPPED, FF_POS_DROPPED]
