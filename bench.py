@@ -133,15 +133,17 @@ def cpu_baseline_serial(packed_blocks, frame0_packed, h, w, method: str) -> dict
     from oracle import flame_oracle as fo
     t0 = time.perf_counter()
     n_total = 0
+    checks = []
     frame0 = fo.frames_from_bytes(frame0_packed, 1, h, w, 12)[0]
     for first, blk in packed_blocks:           # blk holds [halo, frames...]
         n = blk.size // (h * w * 3 // 2)
         frames = fo.frames_from_bytes(blk, n, h, w, 12)
-        fo.process_clip(frames[1:], fo.ClipParams(method=method), frame0=frame0, first_index=first,
-                        prior_frame=frames[0])
+        r = fo.process_clip(frames[1:], fo.ClipParams(method=method), frame0=frame0, first_index=first,
+                            prior_frame=frames[0])
+        checks.append((first, r.pos_px, r.nonempty))
         n_total += n - 1
     dt = time.perf_counter() - t0
-    return {"frames": n_total, "seconds": dt, "value": n_total / dt}
+    return {"frames": n_total, "seconds": dt, "value": n_total / dt, "checks": checks}
 
 
 _POOL_STATE = {}
@@ -269,11 +271,11 @@ def own_arm(args) -> None:
                                 truncate=(world == 1))
         if world > 1:
             g = exchange.finish(res.pos, res.first_exit, total, eng.truncate, counts_local=res.counts)
-            return g.pos, g.first_exit_t
-        return res.pos, res.first_exit
+            return g.pos, g.first_exit_t, g.counts
+        return res.pos, res.first_exit, res.counts
 
     for _ in range(args.warmup):
-        pos_t, fe_t = step_device()
+        pos_t, fe_t, cnt_t = step_device()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -285,7 +287,7 @@ def own_arm(args) -> None:
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        pos_t, fe_t = step_device()
+        pos_t, fe_t, cnt_t = step_device()
     ev1.record()
     barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
@@ -298,6 +300,7 @@ def own_arm(args) -> None:
 
     # sanity on the result of the last step (not timed)
     pos = pos_t.cpu().numpy()
+    counts_np = cnt_t.cpu().numpy()
     first_exit = int(fe_t.cpu().item())
     det = np.nonzero(pos >= 0)[0]
     assert det.size > 200, "bench workload produced no detections"
@@ -351,6 +354,13 @@ def own_arm(args) -> None:
         (l0, l1), (f0_, f1) = baseline_sample_ranges(total, int(spec.t_enter), args.sample_frames)
         blocks = [(s, packed[(s - 1) * fb:e * fb].cpu().numpy()) for s, e in ((l0, l1), (f0_, f1))]
         r = cpu_baseline_serial(blocks, frame0.cpu().numpy(), h, w, "half_maximum")
+        # the baseline's own outputs double as a checker for the timed GPU result on those frames
+        # (untruncated positions: compare below the exit frame only)
+        for first, o_pos, o_cnt in r["checks"]:
+            hi = min(first + len(o_pos), first_exit)
+            assert np.array_equal(pos[first:hi], o_pos[:hi - first]), "GPU positions differ from the oracle"
+            assert np.array_equal(counts_np[first:first + len(o_cnt)], o_cnt.astype(np.int32)), \
+                "GPU above-noise counts differ from the oracle"
         cpu = {"value": r["value"], "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{r['frames']} frames ({l1 - l0} lead-in + {f1 - f0_} flame frames, the clip's "
                          f"proportions) in {r['seconds']:.1f} s: NumPy decode + per-frame path, serial"}

@@ -113,6 +113,35 @@ __device__ __forceinline__ void decode12x8(uint32_t w0, uint32_t w1, uint32_t w2
   v[7] = (int)(t3 & 0xFFFu);
 }
 
+// cnt += (x > k) for unsigned x, k, written as carry-out + add-with-carry (2 SASS instructions
+// instead of the compare / add / select triple the compiler emits for the C expression):
+// x > k  <=>  x + ~k carries out of 32 bits.  Callers pass nk = ~k.  (add.cc, not sub.cc: the
+// carry flag after a PTX subtraction is the hardware's NOT-borrow, which must not feed addc.)
+__device__ __forceinline__ void add_gt(int& cnt, uint32_t x, uint32_t nk) {
+  asm("{\n.reg .u32 d;\nadd.cc.u32 d, %1, %2;\naddc.u32 %0, %0, 0;\n}" : "+r"(cnt) : "r"(x), "r"(nk));
+}
+
+// Count how many of the 8 packed-12 pixels in 3 LE words exceed c (0 <= c <= 4095) WITHOUT
+// extracting them: each byte triple is permuted to the top 24 bits of a word, T = hi<<20 | lo<<8 | g
+// (g = don't-care low byte).  hi > c <=> T > (c<<20 | 0xFFFFF);  lo > c <=> (T & 0xFFFFF) > (c<<8 | 0xFF):
+// whatever sits below a field is dominated by the all-ones padding of the bound.
+// nk_hi / nk_lo are the complemented bounds (see add_gt).
+__device__ __forceinline__ void count12x8(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t nk_hi, uint32_t nk_lo,
+                                          int& cnt) {
+  const uint32_t t0 = __byte_perm(w0, 0u, 0x0124);  // b0 b1 b2 0
+  const uint32_t t1 = __byte_perm(w0, w1, 0x3455);  // b3 b4 b5 g
+  const uint32_t t2 = __byte_perm(w1, w2, 0x2344);  // b6 b7 b8 g
+  const uint32_t t3 = __byte_perm(w2, 0u, 0x1234);  // b9 b10 b11 0
+  add_gt(cnt, t0, nk_hi);
+  add_gt(cnt, t0 & 0xFFFFFu, nk_lo);
+  add_gt(cnt, t1, nk_hi);
+  add_gt(cnt, t1 & 0xFFFFFu, nk_lo);
+  add_gt(cnt, t2, nk_hi);
+  add_gt(cnt, t2 & 0xFFFFFu, nk_lo);
+  add_gt(cnt, t3, nk_hi);
+  add_gt(cnt, t3 & 0xFFFFFu, nk_lo);
+}
+
 // One pixel out of a packed buffer whose first byte holds flat pixel 0 (any bit depth).
 template <int BITS>
 __device__ __forceinline__ int load_px_generic(const uint8_t* __restrict__ base, int64_t q) {

@@ -71,6 +71,40 @@ __device__ __forceinline__ void store_diff(void* base, int64_t px, const int (&d
   }
 }
 
+// Pixel-pair access for the float difference outputs: lane l of a warp takes pair l of 32
+// consecutive pairs, so one store instruction covers a contiguous 512-byte (f64) / 256-byte
+// (f32) line instead of 32 scattered 16-byte pieces.
+template <int BITS>
+__device__ __forceinline__ void load_pair(const uint8_t* stage, int j, int (&v)[2]) {
+  if (BITS == 12) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(stage);
+    const int byte = 3 * j;
+    const uint32_t lo = w[byte >> 2];
+    const uint32_t hi = w[(byte >> 2) + 1];            // may read past the tile: stays inside smem
+    const uint32_t le = __funnelshift_r(lo, hi, (byte & 3) * 8);   // b0 | b1<<8 | b2<<16 | ..
+    const uint32_t t = __byte_perm(le, 0u, 0x4012);                // b0<<16 | b1<<8 | b2
+    v[0] = (int)(t >> 12);
+    v[1] = (int)(t & 0xFFFu);
+  } else if (BITS == 16) {
+    const uint32_t q = reinterpret_cast<const uint32_t*>(stage)[j];
+    v[0] = q & 0xFFFF;
+    v[1] = q >> 16;
+  } else {
+    const uint32_t q = reinterpret_cast<const uint16_t*>(stage)[j];
+    v[0] = q & 0xFF;
+    v[1] = q >> 8;
+  }
+}
+
+template <int DIFF>
+__device__ __forceinline__ void store_diff_pair(void* base, int64_t px, int d0, int d1) {
+  if (DIFF == FF_DIFF_F32) {
+    __stcs(reinterpret_cast<float2*>(static_cast<float*>(base) + px), make_float2((float)d0, (float)d1));
+  } else if (DIFF == FF_DIFF_F64) {
+    __stcs(reinterpret_cast<double2*>(static_cast<double*>(base) + px), make_double2((double)d0, (double)d1));
+  }
+}
+
 // COUNT: emit per-(frame,tile) above-noise counts.  DIFF: retained difference dtype.
 // DECODED: also write decoded uint16 pixels.  K: groups per thread per tile.
 template <int BITS, bool COUNT, int DIFF, bool DECODED, int K>
@@ -132,12 +166,23 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const StreamParams p) 
     const int ethr = p.empty_thr >= 0 ? p.empty_thr : max(10, bg >> 1);
     cthr = bg + ethr;  // max(x-bg,0) > ethr  <=>  x > bg + ethr   (ethr >= 0)
   }
+  const uint32_t c12 = (uint32_t)min(cthr, 4095);      // 12-bit pixels never exceed 4095
+  const uint32_t nk_hi = ~((c12 << 20) | 0xFFFFFu);   // complemented bounds for add_gt
+  const uint32_t nk_lo = ~((c12 << 8) | 0xFFu);
+  const uint32_t ncthr = ~(uint32_t)cthr;
 
-  uint32_t prev[K][4];  // background-subtracted previous frame, two uint16 per register
+  // Work item = 8-pixel group (16-byte vector stores) or, for float difference outputs, one
+  // pixel pair per lane (see load_pair).  prev[] holds the background-subtracted previous frame
+  // of this thread's pixels, two uint16 per register.
+  constexpr bool kPair = (DIFF == FF_DIFF_F32 || DIFF == FF_DIFF_F64);
+  constexpr int kItemPx = kPair ? 2 : kGroupPx;
+  constexpr int kItems = K * kGroupPx / kItemPx;        // items per thread per tile
+  const int tile_items = tile_groups * (kGroupPx / kItemPx);
+  uint32_t prev[kItems][kItemPx / 2];
 #pragma unroll
-  for (int k = 0; k < K; ++k)
+  for (int k = 0; k < kItems; ++k)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) prev[k][j] = 0;
+    for (int j = 0; j < kItemPx / 2; ++j) prev[k][j] = 0;
   bool have_prev = false;
 
   for (int it = 0; it < n_items; ++it) {
@@ -162,29 +207,48 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const StreamParams p) 
     int cnt = 0;
 
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < kItems; ++k) {
       const int g = tid + k * kThreads;
-      if (g < tile_groups) {
-        int v[8];
-        load_group<BITS>(stage, g, v);
-        const int64_t px = (int64_t)f * p.px_per_frame + tile_px0 + (int64_t)g * kGroupPx;
+      if (g < tile_items) {
+        if (BITS == 12 && COUNT && DIFF == FF_DIFF_NONE && !DECODED) {   // count in place, no extraction
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(stage) + 3 * g;
+          count12x8(w[0], w[1], w[2], nk_hi, nk_lo, cnt);
+          continue;
+        }
+        int v[kItemPx];
+        if (kPair) {
+          int v2[2];
+          load_pair<BITS>(stage, g, v2);
+          v[0] = v2[0];
+          v[1] = v2[1];
+        } else {
+          int v8[8];
+          load_group<BITS>(stage, g, v8);
+#pragma unroll
+          for (int j = 0; j < kItemPx; ++j) v[j] = v8[j];
+        }
+        const int64_t px = (int64_t)f * p.px_per_frame + tile_px0 + (int64_t)g * kItemPx;
         if (COUNT) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) cnt += (v[j] > cthr) ? 1 : 0;
+          for (int j = 0; j < kItemPx; ++j) add_gt(cnt, (uint32_t)v[j], ncthr);
         }
         if (DECODED && !is_halo) {
-          uint4 q;
-          q.x = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
-          q.y = (uint32_t)v[2] | ((uint32_t)v[3] << 16);
-          q.z = (uint32_t)v[4] | ((uint32_t)v[5] << 16);
-          q.w = (uint32_t)v[6] | ((uint32_t)v[7] << 16);
-          __stcs(reinterpret_cast<uint4*>(p.decoded_out + px), q);
+          if (kPair) {
+            __stcs(reinterpret_cast<uint32_t*>(p.decoded_out + px), (uint32_t)v[0] | ((uint32_t)v[1] << 16));
+          } else {
+            uint4 q;
+            q.x = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
+            q.y = (uint32_t)v[2 % kItemPx] | ((uint32_t)v[3 % kItemPx] << 16);
+            q.z = (uint32_t)v[4 % kItemPx] | ((uint32_t)v[5 % kItemPx] << 16);
+            q.w = (uint32_t)v[6 % kItemPx] | ((uint32_t)v[7 % kItemPx] << 16);
+            __stcs(reinterpret_cast<uint4*>(p.decoded_out + px), q);
+          }
         }
         if (DIFF != FF_DIFF_NONE) {
-          int d[8];
-          uint32_t cur[4];
+          int d[kItemPx];
+          uint32_t cur[kItemPx / 2];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < kItemPx / 2; ++j) {
             const int s0 = max(v[2 * j] - bg, 0);
             const int s1 = max(v[2 * j + 1] - bg, 0);
             int d0 = s0 - (int)(prev[k][j] & 0xFFFFu);
@@ -193,10 +257,19 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const StreamParams p) 
             d[2 * j + 1] = (diff_valid && d1 >= p.diff_thr) ? d1 : 0;
             cur[j] = (uint32_t)s0 | ((uint32_t)s1 << 16);
           }
-          if (emit_diff) store_diff<DIFF>(p.diff_out, px, d);
+          if (emit_diff) {
+            if (kPair) {
+              store_diff_pair<DIFF>(p.diff_out, px, d[0], d[1]);
+            } else {
+              int d8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) d8[j] = d[j % kItemPx];
+              store_diff<DIFF>(p.diff_out, px, d8);
+            }
+          }
           if (!skipped) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) prev[k][j] = cur[j];
+            for (int j = 0; j < kItemPx / 2; ++j) prev[k][j] = cur[j];
           }
         }
       }

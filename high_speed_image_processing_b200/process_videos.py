@@ -291,6 +291,45 @@ def process_video_source(config: VideoSourceConfig, processor: Optional[MPIVideo
     return results
 
 
+def process_collection(collection, configs, engine=None, exchange=None, balance: bool = True,
+                       per_video=None) -> Dict[int, "VideoResult"]:
+    """BASELINE config 5: a ``VideoCollection`` sharded by WHOLE VIDEOS across ranks
+    (the GPU analogue of ``MPIVideoProcessor.process_videos``, src/photron/parallel.py:173-208).
+
+    ``configs`` is one ``VideoSourceConfig`` for all videos or a sequence with one per video
+    (mixed methods / calibrations).  Each rank processes its videos end to end on its own GPU
+    (no data-path collective); the per-video results (a few KB each) are all-gathered so every
+    rank returns the full ``{video_index: VideoResult}`` map, ordered by index like the
+    reference's gather + sort.  ``per_video(video, cfg, cal, off)`` overrides the per-video
+    function (tests of the host logic pass a stub)."""
+    import torch.distributed as dist
+    from .sharding import assign_videos
+
+    n = len(collection)
+    cfgs = list(configs) if isinstance(configs, (list, tuple)) else [configs] * n
+    if len(cfgs) != n:
+        raise ValueError("configs must be a single VideoSourceConfig or one per video")
+    rank = 0 if exchange is None else exchange.rank
+    size = 1 if exchange is None else exchange.size
+    weights = [len(v) * v.frame_shape[0] * v.frame_shape[1] for v in collection] if balance else None
+    mine = assign_videos(n, rank, size, weights)
+    run = per_video if per_video is not None else (
+        lambda video, cfg, cal, off: process_video(video, cfg, cal, off, engine=engine, exchange=None))
+    local = {}
+    for vi in mine:
+        video, cfg = collection[vi], cfgs[vi]
+        cal, off = cfg.get_calibration_for_file(video.filepath.name)
+        local[vi] = run(video, cfg, cal, off)
+    if size == 1:
+        return dict(sorted(local.items()))
+    parts = [None] * size
+    dist.all_gather_object(parts, local, group=exchange.group)
+    merged = {}
+    for part in parts:
+        merged.update(part)
+    return dict(sorted(merged.items()))
+
+
 def default_configs() -> List[VideoSourceConfig]:
     """The two sources hard-coded in the reference's main() (:1646-1685) with the README's
     method choice per camera (README.md:55,62)."""

@@ -95,3 +95,55 @@ def test_single_process_exchange_is_identity():
     pos = torch.tensor([1, 2, 90, 3], dtype=torch.int32)
     g = ex.finish(pos, torch.tensor([2], dtype=torch.int32), 4, _torch_truncate)
     assert g.first_exit == 2 and g.pos.tolist() == [1, 2, FF_POS_DROPPED, FF_POS_DROPPED]
+
+
+# ---- config 5: whole videos sharded across ranks -------------------------------------------
+def _collection_worker(rank, size, port, vdir, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        from high_speed_image_processing_b200.photron import open_collection
+        from high_speed_image_processing_b200.process_videos import (FileCalibration, VideoSourceConfig,
+                                                                     process_collection)
+        coll = open_collection(vdir)
+        cfgs = []
+        for i in range(len(coll)):
+            c = VideoSourceConfig(name=f"v{i}")
+            c.detection_method = ("half_maximum", "threshold", "gradient")[i % 3]
+            c.file_calibrations = [FileCalibration(calibration=0.5, position_offset=float(i), files=[f"run-{i}-"])]
+            cfgs.append(c)
+        seen = []
+
+        def stub(video, cfg, cal, off):            # stands in for the GPU path: host logic only
+            seen.append(video.filepath.name)
+            return (video.filepath.name, cfg.detection_method, cal, off, len(video), rank)
+
+        res = process_collection(coll, cfgs, exchange=RangeExchange(), per_video=stub)
+        import json
+        with open(os.path.join(out_dir, f"c{rank}.json"), "w") as fh:
+            json.dump({"res": {str(k): list(v) for k, v in res.items()}, "seen": seen}, fh)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_collection_sharded_by_video(tmp_path):
+    import json
+    vdir = tmp_path / "videos"
+    lengths = [4, 9, 3, 7, 5]
+    for i, n in enumerate(lengths):
+        syn.write_clip(vdir, f"run-{i}-", syn.SyntheticSpec(width=64, height=8, n_frames=n, bits=16, seed=i))
+    out = tmp_path / "out"
+    out.mkdir()
+    mp.spawn(_collection_worker, args=(2, _free_port(), str(vdir), str(out)), nprocs=2, join=True)
+    r0 = json.load(open(out / "c0.json"))
+    r1 = json.load(open(out / "c1.json"))
+    assert r0["res"] == r1["res"]                                   # every rank gets the full map
+    assert sorted(r0["seen"] + r1["seen"]) == sorted(f"run-{i}-.cihx" for i in range(5))
+    assert not set(r0["seen"]) & set(r1["seen"])                    # each video processed exactly once
+    for i, n in enumerate(lengths):
+        name, method, cal, off, length, _ = r0["res"][str(i)]
+        assert (name, method, cal, off, length) == (f"run-{i}-.cihx", ("half_maximum", "threshold", "gradient")[i % 3],
+                                                    0.5, float(i), n)
+    load = [sum(lengths[int(k)] for k, v in r0["res"].items() if v[5] == r) for r in (0, 1)]
+    assert abs(load[0] - load[1]) <= max(lengths)                   # size-balanced

@@ -1,0 +1,106 @@
+#!/usr/bin/env python
+"""Per-kernel timings of the other BASELINE configurations (C1, C3, C4) and of every
+streaming-kernel variant - these are parity-test cases, not bench.py's headline, but
+DESIGN.md quotes their roofline fractions.  Prints one JSON object per line.
+
+    python tools/bench_variants.py [--frames-scale 1.0] [--reps 5]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
+
+import torch  # noqa: E402
+
+from high_speed_image_processing_b200 import synthetic as syn  # noqa: E402
+from high_speed_image_processing_b200.engine import DetectionParams, FlameFrontEngine  # noqa: E402
+
+
+def time_call(fn, reps: int) -> float:
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    best = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best.append(e0.elapsed_time(e1))
+    best.sort()
+    return best[len(best) // 2]
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames-scale", type=float, default=1.0)
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+    eng = FlameFrontEngine(0)
+    peak = 6547.5
+    pk = REPO / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peak = float(json.loads(pk.read_text())["hbm_gbs"])
+
+    cases = [
+        ("C1", "half_maximum", None, False),
+        ("C2", "half_maximum", None, False),
+        ("C3", "threshold", None, False),
+        ("C4", "gradient", "uint16", False),
+        ("C4", "gradient", "float32", False),
+        ("C4", "gradient", "float64", False),
+        ("C2", "half_maximum", None, True),       # also materialise decoded uint16 frames
+    ]
+    cache = {}
+    for name, method, diff, decoded in cases:
+        base = syn.config_spec(name)
+        n = max(8, int(base.n_frames * args.frames_scale))
+        if diff == "float64":
+            n = min(n, 2500)                       # 8 B/px x 1 Mpx x 2500 = 21 GB retained
+        spec = syn.config_spec(name, n_frames=n) if n != base.n_frames else base
+        key = (name, n)
+        if key not in cache:
+            cache.clear()
+            cache[key] = syn.render_packed_torch(spec, eng.device)
+        packed = cache[key]
+        h, w, fb = spec.height, spec.width, spec.frame_bytes
+        params = DetectionParams(method=method)
+        scalars, bg_dev = eng.clip_scalars(packed[:fb], h, w, 12)
+
+        eng._stream_events = []
+        out = {}
+
+        def run():
+            out["res"] = eng.process_range(packed, n, h, w, 12, params, scalars, bg_dev, diff_dtype=diff,
+                                           keep_decoded=decoded)
+        whole_ms = time_call(run, args.reps)
+        ev = eng._stream_events
+        torch.cuda.synchronize()
+        stream_ms = sorted(e0.elapsed_time(e1) for e0, e1 in ev[2:])
+        stream_ms = stream_ms[len(stream_ms) // 2]
+        eng._stream_events = None
+        px = h * w
+        out_bytes = {None: 0, "uint16": 2, "float32": 4, "float64": 8}[diff] * px + (2 * px if decoded else 0)
+        alg = n * (fb + out_bytes + 8)
+        res = out.pop("res")
+        fe = int(res.first_exit.cpu().item())
+        ndet = int((res.pos >= 0).sum().item())
+        del res
+        print(json.dumps({
+            "config": name, "frames": n, "shape": [h, w], "method": method, "diff_dtype": diff, "decoded_out": decoded,
+            "algorithmic_bytes_per_frame": fb + out_bytes + 8,
+            "stream_kernel_ms": stream_ms, "stream_kernel_gbs": alg / stream_ms / 1e6,
+            "stream_kernel_frac_of_measured_peak": alg / stream_ms / 1e6 / peak,
+            "whole_path_ms": whole_ms, "whole_path_frames_per_s": n / whole_ms * 1e3,
+            "whole_path_gbs": alg / whole_ms / 1e6, "first_exit": fe, "detections": ndet}), flush=True)
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
