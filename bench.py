@@ -345,6 +345,17 @@ def own_arm(args) -> None:
     clocks = sampler.stop() if rank == 0 else {}
     assert fe_h == first_exit and np.array_equal(pos_h, pos), "host-streamed result differs from device-resident"
     e2e_value = total / e2e_sec
+    # PCIe roofline for the end-to-end path: plain pinned-host -> device copy of the same buffer
+    h2d_peak = 0.0
+    scratch = torch.empty_like(packed)
+    for _ in range(3):
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        scratch.copy_(host, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_peak = max(h2d_peak, host.numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9)
+    del scratch
     h2d = fpr * fb + fb + (fb if halo is not None else 0)
     d2h = 2 * 4 * fpr + 4 + 4 + 2 * w
 
@@ -389,7 +400,9 @@ def own_arm(args) -> None:
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": e2e_sec * 1e3,
-                    "h2d_gbs_per_gpu": h2d / e2e_sec / 1e9, "launches_per_step": launches_e2e},
+                    "h2d_gbs_per_gpu": h2d / e2e_sec / 1e9, "h2d_peak_gbs_measured": h2d_peak,
+                    "frac_of_h2d_peak": (h2d / e2e_sec / 1e9) / h2d_peak if h2d_peak else None,
+                    "launches_per_step": launches_e2e},
             "gpu_launches": launches,
             "clocks": clocks,
             "result": {"first_exit_frame": first_exit, "detections": int(det.size)},

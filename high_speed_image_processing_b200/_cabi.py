@@ -57,6 +57,10 @@ SIGNATURES = {
     "ff_detect": (_int, [_vp, _vp, _i64, _i64, _int, _int, _int, _vp, _vp, _i64, _int, _int, _i32, _i32, _i32,
                          _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ff_truncate": (_int, [_vp, _i64, _i64, _vp, _vp]),
+    "ff_head_lines": (_int, [_vp, _vp, _i64, _int, _int, _int, _vp, _vp, _i64, _i32, C.POINTER(C.c_double), _int, _vp,
+                             _vp, _vp, _vp]),
+    "ff_head_track": (_int, [_vp, _vp, _i64, _i64, _int, _i32, _i32, _i32, C.c_double, C.c_double, _i32, _i32, _i32,
+                             _vp, _vp, _vp]),
     "ff_host_ctx_create": (_int, [_int, _i64, C.POINTER(_vp)]),
     "ff_host_ctx_destroy": (_int, [_vp]),
     "ff_process_host": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _int, _int, _i32, _i32, _i64, _int, _int, _i32,

@@ -22,6 +22,10 @@ int detect_impl(const void*, const void*, int64_t, int64_t, int, int, int, const
                 int32_t*, cudaStream_t);
 int background_impl(const void*, int, int, int, int32_t*, uint16_t*, cudaStream_t);
 int truncate_impl(int32_t*, int64_t, int64_t, const int32_t*, cudaStream_t);
+int head_lines_impl(const void*, const void*, int64_t, int, int, int, const int32_t*, const int32_t*, int64_t, int32_t,
+                    const double*, int, const uint8_t*, double*, uint8_t*, cudaStream_t);
+int head_track_impl(const double*, const uint8_t*, int64_t, int64_t, int, int32_t, int32_t, int32_t, double, double,
+                    int32_t, int32_t, int32_t, int32_t*, int32_t*, cudaStream_t);
 
 }  // namespace ff
 
@@ -184,6 +188,24 @@ int ff_detect(const void* frames_dev, const void* halo_dev, int64_t n_frames, in
 int ff_truncate(int32_t* pos_dev, int64_t n_frames, int64_t first_frame, const int32_t* first_exit_dev,
                 void* stream) {
   return truncate_impl(pos_dev, n_frames, first_frame, first_exit_dev, static_cast<cudaStream_t>(stream));
+}
+
+int ff_head_lines(const void* frames_dev, const void* halo_dev, int64_t n_frames, int height, int width, int bits,
+                  const int32_t* bg_dev, const int32_t* partial_dev, int64_t min_signal_count, int32_t diff_thr,
+                  const double* gauss_weights_host, int radius, const uint8_t* skip_dev, double* lines_out_dev,
+                  uint8_t* flags_out_dev, void* stream) {
+  return head_lines_impl(frames_dev, halo_dev, n_frames, height, width, bits, bg_dev, partial_dev, min_signal_count,
+                         diff_thr, gauss_weights_host, radius, skip_dev, lines_out_dev, flags_out_dev,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int ff_head_track(const double* lines_dev, const uint8_t* flags_dev, int64_t n_frames, int64_t first_frame, int width,
+                  int32_t edge_margin_px, int32_t max_displacement_px, int32_t search_window_px,
+                  double min_gradient_strength, double sobel_threshold_fraction, int32_t exit_margin_px,
+                  int32_t last_frame_in, int32_t last_pos_in, int32_t* out_dev, int32_t* stop_dev, void* stream) {
+  return head_track_impl(lines_dev, flags_dev, n_frames, first_frame, width, edge_margin_px, max_displacement_px,
+                         search_window_px, min_gradient_strength, sobel_threshold_fraction, exit_margin_px,
+                         last_frame_in, last_pos_in, out_dev, stop_dev, static_cast<cudaStream_t>(stream));
 }
 
 int ff_host_ctx_create(int device, int64_t chunk_bytes, ff_host_ctx** ctx_out) {

@@ -1,0 +1,381 @@
+// the reference's HEAD detector (scripts/process_videos.py:350-465) on the GPU.
+//
+// head_band_kernel  - per non-empty frame, on the (2*(R+3)+1)-row band around the centre row:
+//     thresholded frame difference (:397-399) -> 3x3 grey opening (:404) -> Gaussian sigma
+//     (:407, scipy radius R = int(4*sigma+0.5)) -> Sobel(axis=1) and np.gradient(axis=1)
+//     (:410-413); only the centre row of the last two is ever read (:417-418).
+//     The morphology is exact integer work; the Gaussian/Sobel/gradient are float64 in SciPy,
+//     so they are evaluated here in float64 with explicit round-to-nearest mul/add (no FMA) in
+//     the exact operation order of scipy.ndimage's NI_Correlate1D (centre tap first, then
+//     symmetric pairs outermost -> innermost) - positions come out bit-identical.
+//     Boundaries: scipy mode 'reflect'.  Every stage is symmetric, so evaluating the stages on
+//     the reflect-EXTENDED band equals reflecting each stage's output.
+// head_track_kernel - the sequential part (:317-348, :420-465): velocity-constrained search
+//     window from the last detected position, arg-min gradient / rightmost Sobel, max of the
+//     candidates, stop at the exit frame (:1488-1494).  One CTA walks the frames in order.
+#include <climits>
+
+#include "ff_common.cuh"
+
+namespace ff {
+namespace {
+
+constexpr int kMaxRadius = 8;
+constexpr int kHeadThreads = 256;
+constexpr int kHeadTileW = 256;
+
+struct HeadBandParams {
+  const uint8_t* frames;
+  const uint8_t* halo;
+  int64_t frame_bytes;
+  int n_frames;
+  int height, width;
+  const int32_t* bg_dev;
+  const int32_t* partial;
+  int tiles_per_frame;
+  int64_t min_signal_count;
+  int diff_thr;
+  const uint8_t* skip;
+  double w[2 * kMaxRadius + 1];
+  int radius;
+  double* lines;   // [n][2][W]  (sobel row, gradient row)
+  uint8_t* flags;  // [n]  0 = not processed (skipped / empty), 1 = lines valid, 2 = processed, no prior frame
+};
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  const int period = 2 * n;
+  i %= period;
+  if (i < 0) i += period;
+  return i < n ? i : period - 1 - i;
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(kHeadThreads) head_band_kernel(const HeadBandParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int f = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int W = p.width, H = p.height;
+  const int R = p.radius;
+  const int HALO = R + 3;
+  const int NB = 2 * HALO + 1;            // band rows
+  const int x_begin = blockIdx.x * kHeadTileW;
+  const int tw = min(kHeadTileW, W - x_begin);
+  const int LW = tw + 2 * HALO;           // band columns held by this CTA
+  const int c = H / 2;
+
+  // ---- frame state (uniform across the CTA) ------------------------------------------------
+  const bool skipped = p.skip != nullptr && p.skip[f] != 0;
+  __shared__ int s_cnt;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  if (!skipped) {
+    int cnt = 0;
+    for (int t = tid; t < p.tiles_per_frame; t += kHeadThreads) cnt += __ldg(p.partial + (int64_t)f * p.tiles_per_frame + t);
+    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if ((tid & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+  }
+  __syncthreads();
+  const bool empty = (int64_t)s_cnt < p.min_signal_count;
+  const uint8_t* prior = nullptr;
+  if (!skipped && !empty) {
+    int hf = f - 1;
+    if (p.skip != nullptr)
+      while (hf >= 0 && p.skip[hf]) --hf;
+    prior = hf >= 0 ? p.frames + (int64_t)hf * p.frame_bytes : p.halo;
+  }
+  const int flag = (skipped || empty) ? 0 : (prior != nullptr ? 1 : 2);
+  if (blockIdx.x == 0 && tid == 0) p.flags[f] = (uint8_t)flag;
+  if (flag != 1) return;
+
+  // ---- shared-memory carve-up -----------------------------------------------------------------
+  uint16_t* bufA = reinterpret_cast<uint16_t*>(smem);                    // [NB][LW]
+  uint16_t* bufB = bufA + NB * LW;                                        // [NB][LW]
+  const size_t u16_bytes = ((size_t)2 * NB * LW * sizeof(uint16_t) + 15) & ~(size_t)15;
+  double* g0 = reinterpret_cast<double*>(smem + u16_bytes);               // [3][LW]
+  double* bl = g0 + 3 * LW;                                               // [3][LW]
+
+  const int bg = __ldg(p.bg_dev);
+  const uint8_t* cur = p.frames + (int64_t)f * p.frame_bytes;
+
+  // ---- D: thresholded difference on the reflect-extended band ----------------------------------
+  for (int e = tid; e < NB * LW; e += kHeadThreads) {
+    const int i = e / LW, j = e - i * LW;
+    const int r = reflect_idx(c - HALO + i, H);
+    const int x = reflect_idx(x_begin - HALO + j, W);
+    const int64_t q = (int64_t)r * W + x;
+    int d = max(load_px_generic<BITS>(cur, q) - bg, 0) - max(load_px_generic<BITS>(prior, q) - bg, 0);
+    if (d < p.diff_thr) d = 0;
+    bufA[e] = (uint16_t)d;              // diff_thr >= 0 is enforced by the launcher: 0 <= d <= 65535
+  }
+  __syncthreads();
+  // ---- E = 3x3 minimum (valid rows [1,NB-1), cols [1,LW-1)) --------------------------------------
+  for (int e = tid; e < NB * LW; e += kHeadThreads) {
+    const int i = e / LW, j = e - i * LW;
+    unsigned m = 0;
+    if (i >= 1 && i < NB - 1 && j >= 1 && j < LW - 1) {
+      m = 0xFFFFu;
+#pragma unroll
+      for (int di = -1; di <= 1; ++di)
+#pragma unroll
+        for (int dj = -1; dj <= 1; ++dj) m = min(m, (unsigned)bufA[(i + di) * LW + j + dj]);
+    }
+    bufB[e] = (uint16_t)m;
+  }
+  __syncthreads();
+  // ---- NR = 3x3 maximum of E (valid rows [2,NB-2), cols [2,LW-2)) ---------------------------------
+  for (int e = tid; e < NB * LW; e += kHeadThreads) {
+    const int i = e / LW, j = e - i * LW;
+    unsigned m = 0;
+    if (i >= 2 && i < NB - 2 && j >= 2 && j < LW - 2) {
+#pragma unroll
+      for (int di = -1; di <= 1; ++di)
+#pragma unroll
+        for (int dj = -1; dj <= 1; ++dj) m = max(m, (unsigned)bufB[(i + di) * LW + j + dj]);
+    }
+    bufA[e] = (uint16_t)m;
+  }
+  __syncthreads();
+  // ---- G0 = Gaussian along rows (axis 0) for band rows HALO-1, HALO, HALO+1 ------------------------
+  for (int e = tid; e < 3 * LW; e += kHeadThreads) {
+    const int b = e / LW, j = e - b * LW;
+    double tmp = 0.0;
+    if (j >= 2 && j < LW - 2) {
+      const int row = HALO - 1 + b;
+      tmp = __dmul_rn((double)bufA[row * LW + j], p.w[R]);
+      for (int jj = -R; jj < 0; ++jj) {
+        const double pair = __dadd_rn((double)bufA[(row + jj) * LW + j], (double)bufA[(row - jj) * LW + j]);
+        tmp = __dadd_rn(tmp, __dmul_rn(pair, p.w[R + jj]));
+      }
+    }
+    g0[e] = tmp;
+  }
+  __syncthreads();
+  // ---- BL = Gaussian along columns (axis 1), valid cols [HALO-1, LW-HALO+1) -----------------------
+  for (int e = tid; e < 3 * LW; e += kHeadThreads) {
+    const int b = e / LW, j = e - b * LW;
+    double tmp = 0.0;
+    if (j >= HALO - 1 && j < LW - HALO + 1) {
+      const double* g = g0 + b * LW;
+      tmp = __dmul_rn(g[j], p.w[R]);
+      for (int jj = -R; jj < 0; ++jj) tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(g[j + jj], g[j - jj]), p.w[R + jj]));
+    }
+    bl[e] = tmp;
+  }
+  __syncthreads();
+  // ---- Sobel(axis=1) and np.gradient(axis=1) on the centre row --------------------------------------
+  double* out_s = p.lines + ((int64_t)f * 2 + 0) * W;
+  double* out_g = p.lines + ((int64_t)f * 2 + 1) * W;
+  for (int t = tid; t < tw; t += kHeadThreads) {
+    const int j = HALO + t;
+    const int x = x_begin + t;
+    double s3[3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const double* v = bl + b * LW;
+      // correlate1d([-1,0,1]): tmp = in[0]*0; tmp += (in[-1] - in[+1]) * (-1)
+      const double t0 = __dmul_rn(v[j], 0.0);
+      s3[b] = __dadd_rn(t0, __dmul_rn(__dsub_rn(v[j - 1], v[j + 1]), -1.0));
+    }
+    // correlate1d([1,2,1]) along rows: tmp = in[0]*2; tmp += (in[-1] + in[+1]) * 1
+    out_s[x] = __dadd_rn(__dmul_rn(s3[1], 2.0), __dmul_rn(__dadd_rn(s3[0], s3[2]), 1.0));
+    const double* v = bl + 1 * LW;
+    double g;
+    if (x == 0) g = __ddiv_rn(__dsub_rn(v[j + 1], v[j]), 1.0);
+    else if (x == W - 1) g = __ddiv_rn(__dsub_rn(v[j], v[j - 1]), 1.0);
+    else g = __ddiv_rn(__dsub_rn(v[j + 1], v[j - 1]), 2.0);
+    out_g[x] = g;
+  }
+}
+
+struct HeadTrackParams {
+  const double* lines;
+  const uint8_t* flags;
+  int n_frames;
+  int64_t first_frame;
+  int width;
+  int edge_margin, max_disp, window, exit_margin;
+  double min_strength, sobel_frac;
+  int last_frame_in, last_pos_in;  // tracker state carried in from an earlier range (-1 = none)
+  int32_t* out;                    // [n][5]: final, min_gradient, rightmost_sobel, search_start, search_end
+  int32_t* stop;                   // [3]: exit frame (global) or FF_NO_EXIT, last frame, last pos
+};
+
+__global__ void __launch_bounds__(kHeadThreads) head_track_kernel(const HeadTrackParams p) {
+  __shared__ double s_min[kHeadThreads / 32];
+  __shared__ int s_arg[kHeadThreads / 32];
+  __shared__ double s_amax[kHeadThreads / 32];
+  __shared__ int s_right[kHeadThreads / 32];
+  __shared__ int s_last_f, s_last_p, s_stop;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W = p.width;
+  if (tid == 0) {
+    s_last_f = p.last_frame_in;
+    s_last_p = p.last_pos_in;
+    s_stop = 0;
+    p.stop[0] = FF_NO_EXIT;
+  }
+  __syncthreads();
+  for (int f = 0; f < p.n_frames; ++f) {
+    const int fl = p.flags[f];
+    if (fl == 0) continue;
+    const int gf = (int)(p.first_frame + f);
+    int s0, s1;
+    if (s_last_p < 0) {
+      s0 = p.edge_margin;
+      s1 = W - p.edge_margin;
+    } else {
+      s0 = s_last_p;
+      s1 = min(W - p.edge_margin, s_last_p + p.max_disp * max(1, gf - s_last_f) + p.window);
+    }
+    int pos_a = -1, pos_b = -1;
+    if (fl == 1 && s1 > s0 && s0 >= 0) {     // non-empty search slice (:424)
+      s1 = min(s1, W);
+      const double* sob = p.lines + ((int64_t)f * 2 + 0) * W;
+      const double* grd = p.lines + ((int64_t)f * 2 + 1) * W;
+      double mn = 1.0 / 0.0, amax = -1.0;
+      int arg = INT_MAX;
+      for (int x = s0 + tid; x < s1; x += kHeadThreads) {
+        const double g = grd[x];
+        if (g < mn) { mn = g; arg = x; }
+        amax = fmax(amax, fabs(sob[x]));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double om = __shfl_xor_sync(0xFFFFFFFFu, mn, o);
+        const int oa = __shfl_xor_sync(0xFFFFFFFFu, arg, o);
+        if (om < mn || (om == mn && oa < arg)) { mn = om; arg = oa; }
+        amax = fmax(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, o));
+      }
+      if (lane == 0) { s_min[warp] = mn; s_arg[warp] = arg; s_amax[warp] = amax; }
+      __syncthreads();
+      mn = s_min[0]; arg = s_arg[0]; amax = s_amax[0];
+#pragma unroll
+      for (int k = 1; k < kHeadThreads / 32; ++k) {
+        if (s_min[k] < mn || (s_min[k] == mn && s_arg[k] < arg)) { mn = s_min[k]; arg = s_arg[k]; }
+        amax = fmax(amax, s_amax[k]);
+      }
+      if (mn < -p.min_strength) pos_a = arg;                                  // :427-430
+      int right = -1;
+      if (amax > p.min_strength) {                                            // :434-440
+        const double thr = __dmul_rn(amax, p.sobel_frac);
+        for (int x = s0 + tid; x < s1; x += kHeadThreads)
+          if (fabs(sob[x]) > thr) right = x;
+      }
+      right = __reduce_max_sync(0xFFFFFFFFu, right);
+      if (lane == 0) s_right[warp] = right;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < kHeadThreads / 32; ++k) pos_b = max(pos_b, s_right[k]);
+    }
+    const int final_pos = max(pos_a, pos_b);                                  // :452-465
+    __syncthreads();   // everyone has read s_last_* / reduction scratch
+    if (tid == 0) {
+      int32_t* o = p.out + (int64_t)f * 5;
+      o[0] = final_pos; o[1] = pos_a; o[2] = pos_b; o[3] = s0; o[4] = s1;
+      if (final_pos >= 0) { s_last_f = gf; s_last_p = final_pos; }
+      if (final_pos >= 0 && final_pos >= W - p.exit_margin) {                 // :1488-1494
+        p.stop[0] = gf;
+        s_stop = 1;
+      }
+    }
+    __syncthreads();
+    if (s_stop) break;
+  }
+  if (tid == 0) {
+    p.stop[1] = s_last_f;
+    p.stop[2] = s_last_p;
+  }
+}
+
+}  // namespace
+
+int head_lines_impl(const void* frames, const void* halo, int64_t n_frames, int height, int width, int bits,
+                    const int32_t* bg_dev, const int32_t* partial, int64_t min_signal_count, int32_t diff_thr,
+                    const double* gauss_weights_host, int radius, const uint8_t* skip, double* lines_out,
+                    uint8_t* flags_out, cudaStream_t st) {
+  if (frames == nullptr || bg_dev == nullptr || partial == nullptr || gauss_weights_host == nullptr ||
+      lines_out == nullptr || flags_out == nullptr)
+    return FF_ERR_INVALID;
+  if (n_frames <= 0 || height <= 0 || width < 2 || n_frames > 65535 * 64) return FF_ERR_INVALID;
+  if (bits != 8 && bits != 12 && bits != 16) return FF_ERR_UNSUPPORTED;
+  if (radius < 0 || radius > kMaxRadius) return FF_ERR_UNSUPPORTED;
+  if (diff_thr < 0) return FF_ERR_UNSUPPORTED;       // band is held as uint16
+  const int64_t px = (int64_t)height * width;
+  if (bits == 12 && (px & 1)) return FF_ERR_UNSUPPORTED;
+
+  HeadBandParams p{};
+  p.frames = static_cast<const uint8_t*>(frames);
+  p.halo = static_cast<const uint8_t*>(halo);
+  p.frame_bytes = frame_bytes_of(px, bits);
+  p.height = height;
+  p.width = width;
+  p.bg_dev = bg_dev;
+  p.partial = partial;
+  p.tiles_per_frame = choose_tiling(px).tiles_per_frame;
+  p.min_signal_count = min_signal_count;
+  p.diff_thr = diff_thr;
+  p.skip = skip;
+  p.radius = radius;
+  for (int i = 0; i < 2 * radius + 1; ++i) p.w[i] = gauss_weights_host[i];
+  p.lines = lines_out;
+  p.flags = flags_out;
+
+  const int halo_px = radius + 3;
+  const int nb = 2 * halo_px + 1;
+  const int lw = kHeadTileW + 2 * halo_px;
+  const size_t smem = (((size_t)2 * nb * lw * sizeof(uint16_t) + 15) & ~(size_t)15) + (size_t)6 * lw * sizeof(double);
+  const int tiles_x = (width + kHeadTileW - 1) / kHeadTileW;
+  auto launch = [&](auto kern) -> int {
+    if (smem > 48 * 1024) FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // gridDim.y is limited to 65535: walk the frames in slabs
+    for (int64_t f0 = 0; f0 < n_frames; f0 += 65535) {
+      HeadBandParams q = p;
+      const int nf = (int)((n_frames - f0 < 65535) ? n_frames - f0 : 65535);
+      q.n_frames = nf;
+      q.frames = p.frames + f0 * p.frame_bytes;
+      q.halo = f0 == 0 ? p.halo : p.frames + (f0 - 1) * p.frame_bytes;
+      q.partial = p.partial + f0 * p.tiles_per_frame;
+      q.skip = p.skip ? p.skip + f0 : nullptr;
+      q.lines = p.lines + f0 * 2 * width;
+      q.flags = p.flags + f0;
+      kern<<<dim3((unsigned)tiles_x, (unsigned)nf), kHeadThreads, smem, st>>>(q);
+      FF_CUDA_TRY(cudaGetLastError());
+    }
+    return FF_OK;
+  };
+  switch (bits) {
+    case 8: return launch(head_band_kernel<8>);
+    case 12: return launch(head_band_kernel<12>);
+    default: return launch(head_band_kernel<16>);
+  }
+}
+
+int head_track_impl(const double* lines, const uint8_t* flags, int64_t n_frames, int64_t first_frame, int width,
+                    int32_t edge_margin_px, int32_t max_displacement_px, int32_t search_window_px,
+                    double min_gradient_strength, double sobel_threshold_fraction, int32_t exit_margin_px,
+                    int32_t last_frame_in, int32_t last_pos_in, int32_t* out, int32_t* stop, cudaStream_t st) {
+  if (lines == nullptr || flags == nullptr || out == nullptr || stop == nullptr) return FF_ERR_INVALID;
+  if (n_frames <= 0 || width < 2 || n_frames > 0x7FFFFFFF || first_frame < 0) return FF_ERR_INVALID;
+  FF_CUDA_TRY(cudaMemsetAsync(out, 0xFF, sizeof(int32_t) * 5 * (size_t)n_frames, st));
+  HeadTrackParams p{};
+  p.lines = lines;
+  p.flags = flags;
+  p.n_frames = (int)n_frames;
+  p.first_frame = first_frame;
+  p.width = width;
+  p.edge_margin = edge_margin_px;
+  p.max_disp = max_displacement_px;
+  p.window = search_window_px;
+  p.exit_margin = exit_margin_px;
+  p.min_strength = min_gradient_strength;
+  p.sobel_frac = sobel_threshold_fraction;
+  p.last_frame_in = last_frame_in;
+  p.last_pos_in = last_pos_in;
+  p.out = out;
+  p.stop = stop;
+  head_track_kernel<<<1, kHeadThreads, 0, st>>>(p);
+  FF_CUDA_TRY(cudaGetLastError());
+  return FF_OK;
+}
+
+}  // namespace ff

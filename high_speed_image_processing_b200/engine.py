@@ -133,6 +133,17 @@ class RangeResult:
 
 
 @dataclass
+class HeadRangeResult:
+    """Device-resident outputs of the HEAD-parity detector on one frame range."""
+    first_frame: int
+    track: torch.Tensor               # int32[n,5]: final, min_gradient, rightmost_sobel, search_start, search_end
+    flags: torch.Tensor               # uint8[n]: 0 not processed, 1 detected on a difference image, 2 no prior
+    stop: torch.Tensor                # int32[3]: exit frame or FF_NO_EXIT, last detection frame, last position
+    lines: Optional[torch.Tensor]     # float64[n,2,W] (Sobel / gradient centre rows) when kept
+    scalars: Optional[ClipScalars] = None
+
+
+@dataclass
 class HostResult:
     first_frame: int
     pos: np.ndarray
@@ -347,6 +358,70 @@ class FlameFrontEngine:
             if truncate:
                 self.truncate(pos, first_frame, first_exit)
         return RangeResult(first_frame, pos, counts, first_exit, diff, profiles, decoded, scalars)
+
+    # ------------------------------------------------------------------ HEAD-parity detector
+    def process_head(self, frames: torch.Tensor, n_frames: int, height: int, width: int, bits: int,
+                     params, frame_rate: float, calibration: float, *, frame0: Optional[torch.Tensor] = None,
+                     first_frame: int = 0, halo: Optional[torch.Tensor] = None,
+                     skip: Optional[torch.Tensor] = None, keep_lines: bool = False,
+                     tracker_state=(-1, -1)) -> "HeadRangeResult":
+        """The detector the reference runs at HEAD (scripts/process_videos.py:350-465) on a
+        device-resident frame range: streaming kernel (above-noise counts) -> ``ff_head_lines``
+        (difference, 3x3 opening, Gaussian, Sobel / gradient on the centre band, float64 in
+        SciPy's operation order) -> ``ff_head_track`` (velocity-constrained search window,
+        candidate selection, exit stop).  ``params`` is a ``head.HeadParams``."""
+        from .head import gaussian_weights, max_displacement_px
+        self._check_dev(frames, "frames")
+        fb = frame_nbytes(height, width, bits)
+        if frames.dtype != torch.uint8 or frames.numel() < n_frames * fb:
+            raise ValueError(f"frames must be uint8 with at least {n_frames * fb} bytes")
+        if width < 2:
+            raise ValueError("Shape of array too small to calculate a numerical gradient, "
+                             "at least 2 elements are required.")
+        if halo is not None:
+            self._check_dev(halo, "halo")
+        if skip is not None:
+            self._check_dev(skip, "skip")
+            if skip.dtype != torch.uint8 or skip.numel() != n_frames:
+                raise ValueError("skip must be uint8[n_frames]")
+        if frame0 is None:
+            if first_frame != 0:
+                raise ValueError("frame0 (the clip's first frame) is required for a sub-range")
+            frame0 = frames[:fb]
+        bg_dev, line_dev = self.background(frame0, height, width, bits)
+        fetch = self._fetch_frame0_stats_async(bg_dev, line_dev)
+        diff_thr = _clamp_i32(math.ceil(params.frame_diff_threshold))
+        n_elems, tiles = C.c_int64(0), C.c_int(0)
+        _cabi.check(self._lib.ff_partial_len(n_frames, height, width, bits, C.byref(n_elems), C.byref(tiles)),
+                    "ff_partial_len")
+        partial = torch.empty(max(1, n_elems.value), dtype=torch.int32, device=self.device)
+        lines = torch.empty((n_frames, 2, width), dtype=torch.float64, device=self.device)
+        flags = torch.empty(n_frames, dtype=torch.uint8, device=self.device)
+        track = torch.empty((n_frames, 5), dtype=torch.int32, device=self.device)
+        stop = torch.empty(3, dtype=torch.int32, device=self.device)
+        weights = np.ascontiguousarray(gaussian_weights(params.gaussian_sigma), dtype=np.float64)
+        radius = (weights.size - 1) // 2
+        st = self._stream()
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.ff_stream_frames(
+                frames.data_ptr(), _ptr(halo), n_frames, height, width, bits, bg_dev.data_ptr(), -1, diff_thr,
+                _ptr(skip), partial.data_ptr(), None, FF_DIFF_NONE, None, st), "ff_stream_frames")
+            _cabi.check(self._lib.ff_head_lines(
+                frames.data_ptr(), _ptr(halo), n_frames, height, width, bits, bg_dev.data_ptr(),
+                partial.data_ptr(), min_signal_count(height * width, params.min_signal_fraction), diff_thr,
+                weights.ctypes.data_as(C.POINTER(C.c_double)), radius, _ptr(skip), lines.data_ptr(),
+                flags.data_ptr(), st), "ff_head_lines")
+            _cabi.check(self._lib.ff_head_track(
+                lines.data_ptr(), flags.data_ptr(), n_frames, first_frame, width, params.edge_margin_px,
+                max_displacement_px(frame_rate, calibration, params), params.search_window_px,
+                float(params.min_gradient_strength), float(params.sobel_threshold_fraction),
+                params.exit_margin_px, int(tracker_state[0]), int(tracker_state[1]), track.data_ptr(),
+                stop.data_ptr(), st), "ff_head_track")
+        self.launches += 3
+        done, bg_host, line_host = fetch
+        done.synchronize()
+        scalars = ClipScalars.from_frame0_stats(int(bg_host.item()), line_host.numpy())
+        return HeadRangeResult(first_frame, track, flags, stop, lines if keep_lines else None, scalars)
 
     def truncate(self, pos: torch.Tensor, first_frame: int, first_exit: torch.Tensor) -> None:
         """Mark frames at/after the (global) first exit frame as dropped (README.md:145-149)."""

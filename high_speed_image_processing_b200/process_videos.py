@@ -24,6 +24,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from .engine import ClipScalars, DetectionParams, DETECTION_METHODS
+from .head import HeadParams, finish_head_track
 from .photron import MPIVideoProcessor, PhotonVideo, SpatialCalibration, open_video
 
 _REPO_ROOT = Path(__file__).resolve().parent.parent
@@ -76,6 +77,9 @@ class VideoSourceConfig:
     frame_diff_threshold: float = 5.0        # FlameDetectorConfig.frame_diff_threshold (:169)
     min_gradient_strength: float = 10.0      # FlameDetectorConfig.min_gradient_strength (:174)
     min_run_px: int = 1
+    # detection_method = "head": the detector the reference executes at HEAD (FlameDetector,
+    # :220-663) with its own FlameDetectorConfig defaults (exit margin 15, :193)
+    head_params: HeadParams = field(default_factory=HeadParams)
 
     _video_path: Optional[str] = field(default=None, init=False, repr=False)
     _output_dir: Optional[str] = field(default=None, init=False, repr=False)
@@ -110,7 +114,7 @@ class VideoSourceConfig:
     def detection_params(self) -> DetectionParams:
         if self.detection_method not in DETECTION_METHODS:
             raise ValueError(f"unknown detection_method {self.detection_method!r}; "
-                             f"options: {', '.join(DETECTION_METHODS)}")
+                             f"options: {', '.join(DETECTION_METHODS + ('head',))}")
         return DetectionParams(method=self.detection_method, use_frame_diff=self.use_frame_diff,
                                frame_diff_threshold=self.frame_diff_threshold,
                                min_gradient_strength=self.min_gradient_strength,
@@ -131,6 +135,9 @@ class VideoResult:
     first_exit: Optional[int]     # first exit frame (not recorded), None if the flame never exits
     rows: List[ResultRow]
     empty_frames: int
+    velocity_history: List[list] = field(default_factory=list)   # [frame, v_backward1, v_backward2, v_central]
+    ddt_frame: Optional[int] = None
+    stop: Optional[Tuple[str, int]] = None                       # HEAD mode: ("exit"|"velocity_drop", frame)
 
     @property
     def frames(self) -> List[int]:
@@ -165,10 +172,15 @@ def process_video(video: PhotonVideo, config: VideoSourceConfig, calibration: fl
     from ._cabi import FF_NO_EXIT
 
     eng = engine if engine is not None else get_engine()
-    params = config.detection_params()
     n, (h, w), bits = len(video), video.frame_shape, video.storage_bits
     if n == 0:
         raise ValueError("video has no frames")
+    if config.detection_method == "head":
+        if exchange is not None and exchange.size > 1:
+            raise ValueError("detection_method='head' tracks sequentially over the clip: shard by whole "
+                             "videos (process_collection), not by frame range")
+        return _process_video_head(video, config, calibration, offset, eng)
+    params = config.detection_params()
 
     # per-clip scalars from frame 0 (every rank reads frame 0 itself: 1 frame of H2D)
     frame0 = torch.from_numpy(np.ascontiguousarray(video.raw_frames(0, 1))).to(eng.device)
@@ -229,6 +241,39 @@ def process_video(video: PhotonVideo, config: VideoSourceConfig, calibration: fl
                        empty_frames)
 
 
+def _process_video_head(video: PhotonVideo, config: VideoSourceConfig, calibration: float, offset: float,
+                        eng) -> VideoResult:
+    """HEAD-parity mode: the reference loop :1441-1516 with ``FlameDetector.detect`` on the GPU."""
+    import torch
+    from ._cabi import FF_NO_EXIT
+    from .engine import min_signal_count
+
+    hp = config.head_params
+    n, (h, w), bits = len(video), video.frame_shape, video.storage_bits
+    frames_dev = torch.from_numpy(np.ascontiguousarray(video.raw_frames(0, n))).to(eng.device)
+    skip_dev = skip_np = None
+    if config.skip_frames:
+        skip_np = np.zeros(n, dtype=np.uint8)
+        for s in config.skip_frames:
+            if 0 <= s < n:
+                skip_np[s] = 1
+        skip_dev = torch.from_numpy(skip_np).to(eng.device)
+    res = eng.process_head(frames_dev, n, h, w, bits, hp, video.frame_rate, calibration, skip=skip_dev)
+    track, flags = res.track.cpu().numpy(), res.flags.cpu().numpy()
+    time_of = video.get_absolute_time if config.use_absolute_time else video.get_time
+    summary = finish_head_track(track, flags, 0, w, video.frame_rate, calibration, offset, time_of, hp)
+    pos = np.full(n, -1, dtype=np.int32)
+    for frame_idx, _, px, _, _ in summary.rows:
+        pos[frame_idx] = px
+    stop_frame = summary.stop[1] if summary.stop else n
+    pos[stop_frame:] = -2
+    processed = np.ones(n, dtype=bool) if skip_np is None else skip_np == 0
+    empty_frames = int(np.count_nonzero((flags[:stop_frame] == 0) & processed[:stop_frame]))
+    first_exit = summary.stop[1] if summary.stop and summary.stop[0] == "exit" else None
+    return VideoResult(res.scalars, pos, np.zeros(n, dtype=np.int32), first_exit, list(summary.rows), empty_frames,
+                       summary.velocity_history, summary.ddt_frame, summary.stop)
+
+
 def eng_min_signal(params: DetectionParams, n_pixels: int) -> int:
     from .engine import min_signal_count
     return min_signal_count(n_pixels, params.min_signal_fraction)
@@ -244,6 +289,63 @@ def write_position_file(rows: Sequence[ResultRow], filepath) -> str:
         for frame_idx, t_s, px, p_m, _ in rows:
             fh.write(f"{frame_idx} {t_s:.9f} {px} {p_m:.9f}\n")
     return str(filepath)
+
+
+_VELOCITY_HEADER = [
+    "# Flame Position and Velocity Data",
+    "#",
+    "# Velocity Extraction Methods:",
+    "#   Vel_Backward1: First-order backward difference",
+    "#                  v_n = (x_n - x_{n-1}) / dt",
+    "#                  Evaluates velocity at current time step",
+    "#",
+    "#   Vel_Backward2: Second-order backward difference",
+    "#                  v_n = (3*x_n - 4*x_{n-1} + x_{n-2}) / (2*dt)",
+    "#                  Higher accuracy at current time, requires 3 points",
+    "#",
+    "#   Vel_Central:   Second-order central difference",
+    "#                  v_{n-1} = (x_n - x_{n-2}) / (2*dt)",
+    "#                  Most accurate, but evaluates at PRIOR time step",
+    "#",
+]
+
+
+def merge_velocities(rows: Sequence[ResultRow], velocity_history: Sequence[Sequence]) -> List[tuple]:
+    """(frame, t, px, m, v1, v2, vc, is_post_ddt) - the merge at :1548-1555."""
+    vel = {e[0]: (e[1], e[2], e[3]) for e in velocity_history}
+    return [(f, t, px, m, *vel.get(f, (None, None, None)), post) for f, t, px, m, post in rows]
+
+
+def write_velocity_file(data: Sequence[tuple], filepath) -> str:
+    """The 7-column file of the reference's HEAD writer (:1561-1604), byte for byte: 15 comment
+    lines, a column line, then space-separated rows with ``.9f`` time/position and ``.3f``
+    velocities (empty field when a velocity is undefined)."""
+    with open(filepath, "w") as fh:
+        for line in _VELOCITY_HEADER:
+            fh.write(line + "\n")
+        fh.write(" ".join(["#Frame", "Time_s", "Position_px", "Position_m", "Vel_Backward1", "Vel_Backward2",
+                           "Vel_Central"]) + "\n")
+        for f_idx, t_s, px, p_m, v1, v2, vc in data:
+            fields = [str(f_idx), f"{t_s:.9f}", str(px), f"{p_m:.9f}",
+                      f"{v1:.3f}" if v1 is not None else "", f"{v2:.3f}" if v2 is not None else "",
+                      f"{vc:.3f}" if vc is not None else ""]
+            fh.write(" ".join(fields) + "\n")
+    return str(filepath)
+
+
+def write_head_outputs(res: "VideoResult", out_dir, stem: str) -> List[str]:
+    """All / pre-DDT / post-DDT files exactly as :1606-1619."""
+    merged = merge_velocities(res.rows, res.velocity_history)
+    out_dir = Path(out_dir)
+    out_dir.mkdir(parents=True, exist_ok=True)
+    written = [write_velocity_file([m[:7] for m in merged], out_dir / f"{stem}-flame-position.txt")]
+    pre = [m[:7] for m in merged if not m[7]]
+    post = [m[:7] for m in merged if m[7]]
+    if pre:
+        written.append(write_velocity_file(pre, out_dir / f"{stem}-flame-position-pre-DDT.txt"))
+    if post:
+        written.append(write_velocity_file(post, out_dir / f"{stem}-flame-position-post-DDT.txt"))
+    return written
 
 
 # --------------------------------------------------------------------------------------
@@ -283,8 +385,14 @@ def process_video_source(config: VideoSourceConfig, processor: Optional[MPIVideo
             if is_root and res.rows and config.output_dir:
                 out_dir = Path(config.output_dir)
                 out_dir.mkdir(parents=True, exist_ok=True)
-                path = write_position_file(res.rows, out_dir / f"{cihx_file.stem}-flame-position.txt")
-                say(f"  All results: {path} ({len(res.rows)} points)")
+                if config.detection_method == "head":
+                    for path in write_head_outputs(res, out_dir, cihx_file.stem):
+                        say(f"  Results: {path}")
+                    if res.ddt_frame is not None:
+                        say(f"  DDT detected at frame {res.ddt_frame}")
+                else:
+                    path = write_position_file(res.rows, out_dir / f"{cihx_file.stem}-flame-position.txt")
+                    say(f"  All results: {path} ({len(res.rows)} points)")
             results[cihx_file.name] = res
         finally:
             video.close()

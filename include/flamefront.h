@@ -143,6 +143,30 @@ int ff_detect(const void* frames_dev, const void* halo_dev, int64_t n_frames, in
 int ff_truncate(int32_t* pos_dev, int64_t n_frames, int64_t first_frame,
                 const int32_t* first_exit_dev, void* stream);
 
+/* ---- HEAD-parity detector (the code the reference executes at HEAD) ------------------------------
+ * ff_head_lines replaces, per non-empty frame, the image pipeline of FlameDetector.detect
+ * (scripts/process_videos.py:397-418): thresholded frame difference -> grey_opening 3x3 ->
+ * gaussian_filter(sigma) -> sobel(axis=1) and np.gradient(axis=1), evaluated only on the band of
+ * rows that reaches the centre row, in float64 with SciPy's operation order (bit-identical).
+ *   gauss_weights_host  2*radius+1 float64 taps (scipy _gaussian_kernel1d), HOST pointer
+ *   lines_out_dev       float64[n_frames,2,W]: [.,0,:] Sobel centre row, [.,1,:] gradient centre row
+ *   flags_out_dev       uint8[n_frames]: 0 not processed (skipped/empty), 1 lines valid,
+ *                       2 processed but no prior frame (detect() ran without a difference image)
+ * ff_head_track replaces the sequential part (:317-348 search bounds, :420-465 candidate
+ * selection) and the exit stop (:1488-1494).
+ *   last_frame_in/last_pos_in  tracker state carried in (-1/-1 = no detection yet)
+ *   out_dev   int32[n_frames,5]: final, pos_min_gradient, pos_rightmost_sobel, search_start,
+ *             search_end; all -1 for frames that were not processed or lie after the exit frame
+ *   stop_dev  int32[3]: exit frame (global index) or FF_NO_EXIT, last detection frame, last position */
+int ff_head_lines(const void* frames_dev, const void* halo_dev, int64_t n_frames, int height, int width,
+                  int bits, const int32_t* bg_dev, const int32_t* partial_dev, int64_t min_signal_count,
+                  int32_t diff_thr, const double* gauss_weights_host, int radius, const uint8_t* skip_dev,
+                  double* lines_out_dev, uint8_t* flags_out_dev, void* stream);
+int ff_head_track(const double* lines_dev, const uint8_t* flags_dev, int64_t n_frames, int64_t first_frame,
+                  int width, int32_t edge_margin_px, int32_t max_displacement_px, int32_t search_window_px,
+                  double min_gradient_strength, double sobel_threshold_fraction, int32_t exit_margin_px,
+                  int32_t last_frame_in, int32_t last_pos_in, int32_t* out_dev, int32_t* stop_dev, void* stream);
+
 /* ---- host-resident clips: chunked H2D streaming -----------------------------------------------
  * The end-to-end form of stages 2b-4 for a clip that lives in host memory (pinned, or the
  * mmapped .mraw file): replaces the whole frame loop of process_video_source

@@ -218,6 +218,33 @@ def main() -> None:
     # ---- HEAD detector replay (f1/f2 rows of SURVEY 8f) ----------------------------------------
     gold["head_replay"] = replay_head_loop(pv, video, 0.000833333, 1.347567)
 
+    # ---- the reference's own driver, end to end (f1 + f2 + f3) -----------------------------------
+    # process_video_source (:1277-1629) with only the matplotlib renderers replaced by no-ops;
+    # the text files it writes are the golden outputs of the HEAD path.
+    pv.save_frame_image = lambda *a, **k: None
+    pv.generate_stacked_sequence = lambda *a, **k: None
+    pv.generate_stacked_sequence_single_column = lambda *a, **k: None
+    ddir = work / "driver" / "Nova-Video-Files"
+    syn.write_clip(ddir, "run-3-", spec, frames=frames)                       # matches "run-3-:run-10-"
+    syn.write_clip(ddir, "run-5-_C001H001S0001", spec, frames=frames)         # the last-integer bug: default cal
+    dcfg = pv.VideoSourceConfig(name="Nova")
+    dcfg.enabled = True
+    dcfg.calibration = 0.001
+    dcfg.position_offset = 0.25
+    dcfg.video_path = str(ddir)
+    dcfg.output_dir = str(work / "driver" / "out")
+    dcfg.file_calibrations = [pv.FileCalibration(calibration=0.000833333, position_offset=1.347567,
+                                                 files=["run-3-:run-10-"])]
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        pv.process_video_source(dcfg, None)
+    outs = {}
+    for path in sorted((work / "driver" / "out").glob("*.txt")):
+        outs[path.name] = path.read_text()
+    assert "run-3--flame-position.txt" in outs and "run-5-_C001H001S0001-flame-position.txt" in outs
+    gold["driver_outputs"] = outs
+    gold["driver_config"] = {"calibration": 0.001, "position_offset": 0.25}
+
     # ---- FileCalibration / VideoSourceConfig ----------------------------------------------------
     rules = [
         pv.FileCalibration(calibration=0.000833333, position_offset=1.0159, files=["run-1-"]),

@@ -1,0 +1,148 @@
+"""HEAD-parity detector on the GPU (ff_head_lines / ff_head_track) against SciPy, the oracle
+loop and the files written by the reference's own driver."""
+import numpy as np
+import pytest
+import torch
+
+from high_speed_image_processing_b200 import synthetic as syn
+from high_speed_image_processing_b200.head import HeadParams, finish_head_track
+from high_speed_image_processing_b200.process_videos import FileCalibration, VideoSourceConfig, process_video_source
+from oracle import flame_oracle as fo
+from oracle import head_oracle as ho
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, engine):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(engine.device)
+
+
+def run_head_gpu(engine, frames, bits, hp, frame_rate=160000, cal=0.000833333, **kw):
+    n, h, w = frames.shape
+    return engine.process_head(dev(syn.pack_frames(frames, bits), engine), n, h, w, bits, hp, frame_rate, cal,
+                               keep_lines=True, **kw)
+
+
+def oracle_lines(frames, hp):
+    """Per-frame (flag, sobel row, gradient row) via the reference's SciPy calls."""
+    bg = fo.background_scalar(frames[0])
+    noise = fo.empty_noise_threshold(bg)
+    out, prior = [], None
+    for i in range(len(frames)):
+        sub = fo.subtract_scalar_background(frames[i], bg)
+        if fo.is_empty_frame(sub, noise, hp.min_signal_fraction):
+            out.append((0, None, None))
+        elif prior is None:
+            out.append((2, None, None))
+        else:
+            s, g = ho.detect_lines_scipy(fo.frame_difference(sub, prior, hp.frame_diff_threshold),
+                                         sigma=hp.gaussian_sigma)
+            out.append((1, s, g))
+        prior = sub
+    return out
+
+
+@pytest.mark.parametrize("h,w,bits", [(16, 128, 12), (64, 512, 12), (6, 40, 12), (3, 34, 16), (19, 70, 8),
+                                       (1, 64, 16), (2, 300, 12), (128, 1024, 12), (24, 257, 12)])
+def test_band_lines_bit_exact_vs_scipy(engine, h, w, bits):
+    spec = syn.SyntheticSpec(width=w, height=h, n_frames=36, bits=bits, style="mini", t_enter=4.0,
+                             velocity=max(1.0, w / 40.0), curvature_px=1.0, seed=h * w)
+    frames = syn.render_frames(spec)
+    hp = HeadParams()
+    res = run_head_gpu(engine, frames, bits, hp)
+    flags = res.flags.cpu().numpy()
+    lines = res.lines.cpu().numpy()
+    want = oracle_lines(frames, hp)
+    assert sum(1 for f, _, _ in want if f == 1) > 5, "fixture must exercise the detector"
+    for i, (flag, s, g) in enumerate(want):
+        assert flags[i] == flag, i
+        if flag == 1:
+            assert np.array_equal(lines[i, 0], s), (i, np.abs(lines[i, 0] - s).max())
+            assert np.array_equal(lines[i, 1], g), (i, np.abs(lines[i, 1] - g).max())
+
+
+@pytest.mark.parametrize("sigma", [1.0, 1.5, 2.0])
+def test_other_sigmas(engine, sigma):
+    frames = syn.render_frames(syn.SyntheticSpec(width=200, height=32, n_frames=24, style="nova", t_enter=3.0,
+                                                 velocity=6.0, seed=9))
+    hp = HeadParams(gaussian_sigma=sigma)
+    res = run_head_gpu(engine, frames, 12, hp)
+    lines = res.lines.cpu().numpy()
+    for i, (flag, s, g) in enumerate(oracle_lines(frames, hp)):
+        if flag == 1:
+            assert np.array_equal(lines[i, 0], s) and np.array_equal(lines[i, 1], g)
+
+
+@pytest.mark.parametrize("style,w,h,vel", [("nova", 128, 16, 2.0), ("mini", 512, 64, 5.0), ("mini", 300, 10, 3.0)])
+def test_tracker_matches_oracle_loop(engine, style, w, h, vel):
+    spec = syn.SyntheticSpec(width=w, height=h, n_frames=int(w / vel) + 30, style=style, t_enter=6.0, velocity=vel,
+                             tail_length=40.0, curvature_px=2.0, seed=w + h)
+    frames = syn.render_frames(spec)
+    hp = HeadParams()
+    cal, off, rate = 0.000833333, 1.347567, 160000
+    time_of = lambda i: fo.frame_time_absolute(i, 500, 1, rate)
+    res = run_head_gpu(engine, frames, 12, hp, frame_rate=rate, cal=cal)
+    got = finish_head_track(res.track.cpu().numpy(), res.flags.cpu().numpy(), 0, w, rate, cal, off, time_of, hp)
+    want = ho.run_head(frames, rate, cal, off, time_of)
+    assert got.per_frame == want.per_frame
+    assert [list(r) for r in got.rows] == want.rows
+    assert got.velocity_history == want.velocity_history
+    assert got.ddt_frame == want.ddt_frame and got.stop == want.stop
+    stop = res.stop.cpu().numpy()
+    if want.stop and want.stop[0] == "exit":
+        assert stop[0] == want.stop[1]
+
+
+def test_reference_golden_replay(engine, clip_small, golden):
+    c = golden["clip_small"]
+    hr = golden["head_replay"]
+    n, h, w = c["n_frames"], c["height"], c["width"]
+    res = engine.process_head(dev(clip_small["packed"], engine), n, h, w, 12, HeadParams(), 160000, 0.000833333)
+    got = finish_head_track(res.track.cpu().numpy(), res.flags.cpu().numpy(), 0, w, 160000, 0.000833333, 1.347567,
+                            lambda i: fo.frame_time_absolute(i, 500, 1, 160000), HeadParams())
+    assert got.per_frame == [{k: v for k, v in p.items() if k != "diff_sha1"} for p in hr["per_frame"]]
+    assert [list(r) for r in got.rows] == hr["results"]
+    assert got.velocity_history == hr["velocity_history"] and list(got.stop) == hr["stop"]
+
+
+def test_driver_writes_the_reference_files_byte_for_byte(tmp_path, clip_small, golden):
+    """process_video_source(detection_method='head') on the same recordings the reference's own
+    driver processed (oracle/make_golden.py): every output file must be identical."""
+    vdir = tmp_path / "Nova-Video-Files"
+    vdir.mkdir()
+    for stem in ("run-3-", "run-5-_C001H001S0001"):
+        (vdir / f"{stem}.cihx").write_bytes(clip_small["cihx"])
+        (vdir / f"{stem}.mraw").write_bytes(clip_small["packed"].tobytes())
+    cfg = VideoSourceConfig(name="Nova")
+    cfg.enabled = True
+    cfg.detection_method = "head"
+    cfg.calibration = golden["driver_config"]["calibration"]
+    cfg.position_offset = golden["driver_config"]["position_offset"]
+    cfg.video_path = str(vdir)
+    cfg.output_dir = str(tmp_path / "out")
+    cfg.file_calibrations = [FileCalibration(calibration=0.000833333, position_offset=1.347567,
+                                             files=["run-3-:run-10-"])]
+    process_video_source(cfg, None, verbose=False)
+    produced = {p.name: p.read_text() for p in (tmp_path / "out").glob("*.txt")}
+    assert produced == golden["driver_outputs"]
+
+
+def test_head_with_skip_frames_and_no_detection(engine):
+    frames = syn.render_frames(syn.SyntheticSpec(width=128, height=16, n_frames=40, style="mini", t_enter=5.0,
+                                                 velocity=3.0, seed=4))
+    dark = np.full((12, 16, 128), 40, dtype=np.uint16)
+    res = run_head_gpu(engine, dark, 12, HeadParams())
+    assert res.flags.cpu().numpy().tolist() == [0] * 12
+    assert (res.track.cpu().numpy() == -1).all()
+    mask = np.zeros(len(frames), dtype=np.uint8)
+    mask[[10, 11, 20]] = 1
+    res = run_head_gpu(engine, frames, 12, HeadParams(), skip=dev(mask, engine))
+    flags = res.flags.cpu().numpy()
+    assert flags[10] == 0 and flags[11] == 0 and flags[20] == 0
+    # frame 12's prior is frame 9 (the latest non-skipped frame)
+    bg = fo.background_scalar(frames[0])
+    d = fo.frame_difference(fo.subtract_scalar_background(frames[12], bg),
+                            fo.subtract_scalar_background(frames[9], bg), 5.0)
+    s, g = ho.detect_lines_scipy(d)
+    lines = res.lines.cpu().numpy()
+    assert np.array_equal(lines[12, 0], s) and np.array_equal(lines[12, 1], g)
