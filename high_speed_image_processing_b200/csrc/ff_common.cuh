@@ -113,6 +113,21 @@ __device__ __forceinline__ void decode12x8(uint32_t w0, uint32_t w1, uint32_t w2
   v[7] = (int)(t3 & 0xFFFu);
 }
 
+// 12 bytes -> four 16x2 words, pixel 2j in the LOW half and pixel 2j+1 in the HIGH half of x[j]
+// (the byte order of a little-endian uint16 pair, so x[j] can be stored as is).  Each triple is
+// permuted to (b1 b2 | b0 b1): the high half then holds lo-pixel | junk nibble, the low half
+// hi-pixel << 4, and one shift + mask pair cleans both lanes at once.
+__device__ __forceinline__ void decode12x8_16x2(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t (&x)[4]) {
+  const uint32_t p0 = __byte_perm(w0, 0u, 0x1201);
+  const uint32_t p1 = __byte_perm(w0, w1, 0x4534);
+  const uint32_t p2 = __byte_perm(w1, w2, 0x3423);
+  const uint32_t p3 = __byte_perm(w2, 0u, 0x2312);
+  x[0] = ((p0 >> 4) & 0x00000FFFu) | (p0 & 0x0FFF0000u);
+  x[1] = ((p1 >> 4) & 0x00000FFFu) | (p1 & 0x0FFF0000u);
+  x[2] = ((p2 >> 4) & 0x00000FFFu) | (p2 & 0x0FFF0000u);
+  x[3] = ((p3 >> 4) & 0x00000FFFu) | (p3 & 0x0FFF0000u);
+}
+
 // cnt += (x > k) for unsigned x, k, written as carry-out + add-with-carry (2 SASS instructions
 // instead of the compare / add / select triple the compiler emits for the C expression):
 // x > k  <=>  x + ~k carries out of 32 bits.  Callers pass nk = ~k.  (add.cc, not sub.cc: the

@@ -25,7 +25,7 @@ struct StreamParams {
   int64_t px_per_frame;
   int n_frames;
   int tiles_per_frame;
-  int frames_per_chunk;
+  int64_t items_per_cta;   // (tile, frame) work items per CTA, tile-major order
   const int32_t* bg_dev;
   int empty_thr;
   int diff_thr;
@@ -117,17 +117,63 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const StreamParams p) 
   int* warp_cnt = reinterpret_cast<int*>(full + kStages);  // [2][8]
 
   const int tid = threadIdx.x;
-  const int tile = blockIdx.x % p.tiles_per_frame;
-  const int chunk = blockIdx.x / p.tiles_per_frame;
-  const int f_begin = chunk * p.frames_per_chunk;
-  const int f_end = min(f_begin + p.frames_per_chunk, p.n_frames);
+
+  uint64_t policy = 0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+    policy = policy_evict_first();
+  }
+  __syncthreads();
+
+  int bg = 0, cthr = 0;
+  if (COUNT || DIFF != FF_DIFF_NONE) {
+    bg = __ldg(p.bg_dev);
+    const int ethr = p.empty_thr >= 0 ? p.empty_thr : max(10, bg >> 1);
+    cthr = bg + ethr;  // max(x-bg,0) > ethr  <=>  x > bg + ethr   (ethr >= 0)
+  }
+  const uint32_t c12 = (uint32_t)min(cthr, 4095);      // 12-bit pixels never exceed 4095
+  const uint32_t nk_hi = ~((c12 << 20) | 0xFFFFFu);   // complemented bounds for add_gt
+  const uint32_t nk_lo = ~((c12 << 8) | 0xFFu);
+  const uint32_t ncthr = ~(uint32_t)cthr;
+  // 16x2 SIMD (DPX) constants for the packed-12 / uint16-difference variant: every value on that
+  // path fits a signed 16-bit lane (pixels and bg <= 4095, |differences| <= 4095).
+  constexpr bool kSimd = (BITS == 12 && DIFF == FF_DIFF_U16);
+  const uint32_t dup = 0x00010001u;
+  const uint32_t s_ncthr = (uint32_t)(-(int)c12 & 0xFFFF) * dup;          // -cthr per lane
+  const uint32_t s_nbg = (uint32_t)(-min(bg, 4095) & 0xFFFF) * dup;       // -bg per lane
+  const int tm1 = min(max(p.diff_thr, 0) - 1, 8190);                      // thr-1 (thr > 4095 keeps nothing)
+  const uint32_t s_k = (uint32_t)((1 - tm1) & 0xFFFF) * dup;              // relu(d - tm1) = relu((d-1) + (1-tm1))
+
+  // Work item = 8-pixel group (16-byte vector stores) or, for float difference outputs, one
+  // pixel pair per lane (see load_pair).  prev[] holds the background-subtracted previous frame
+  // of this thread's pixels, two uint16 per register.
+  constexpr bool kPair = (DIFF == FF_DIFF_F32 || DIFF == FF_DIFF_F64);
+  constexpr int kItemPx = kPair ? 2 : kGroupPx;
+  constexpr int kItems = K * kGroupPx / kItemPx;        // items per thread per tile
+  uint32_t prev[kItems][kItemPx / 2];
+
+  // The (tile, frame) grid is cut tile-major into equal runs, one per CTA, so the launch is
+  // exactly one resident wave whatever the tile count; a run that crosses a tile boundary is
+  // processed as two segments.  `git` numbers the stage-ring slots across segments.
+  const int64_t total_work = (int64_t)p.tiles_per_frame * p.n_frames;
+  int64_t work = (int64_t)blockIdx.x * p.items_per_cta;
+  const int64_t work_end = min(work + p.items_per_cta, total_work);
+  uint32_t git = 0;
+  while (work < work_end) {
+  const int tile = (int)(work / p.n_frames);
+  const int f_begin = (int)(work - (int64_t)tile * p.n_frames);
+  const int f_end = (int)min((int64_t)p.n_frames, (int64_t)f_begin + (work_end - work));
+  work += f_end - f_begin;
 
   const int64_t tile_px0 = (int64_t)tile * (kGroups * kGroupPx);
   const int tile_groups = (int)min((int64_t)kGroups, (p.px_per_frame - tile_px0) / kGroupPx);
   const uint32_t tile_bytes = (uint32_t)tile_groups * BITS;
   const int64_t tile_off = (int64_t)tile * kStageBytes;
+  const int tile_items = tile_groups * (kGroupPx / kItemPx);
 
-  // Frame feeding prev[] before the first frame of this chunk (difference modes only).
+  // Frame feeding prev[] before the first frame of this segment (difference modes only).
   const uint8_t* halo_ptr = nullptr;
   if (DIFF != FF_DIFF_NONE) {
     int hf = f_begin - 1;
@@ -144,54 +190,28 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const StreamParams p) 
     return fr + tile_off;
   };
 
-  uint64_t policy = 0;
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
-    fence_mbar_init();
-    policy = policy_evict_first();
-  }
-  __syncthreads();
-  if (tid == 0) {
+  if (tid == 0) {   // every stage is free here: the previous segment drained the ring
     const int pre = min(kStages - 1, n_items);
     for (int i = 0; i < pre; ++i) {
-      mbar_arrive_expect_tx(&full[i], tile_bytes);
-      bulk_g2s(smem + i * kStageBytes, src_of(i), tile_bytes, &full[i], policy);
+      const uint32_t ps = (git + i) % kStages;
+      mbar_arrive_expect_tx(&full[ps], tile_bytes);
+      bulk_g2s(smem + ps * kStageBytes, src_of(i), tile_bytes, &full[ps], policy);
     }
   }
 
-  int bg = 0, cthr = 0;
-  if (COUNT || DIFF != FF_DIFF_NONE) {
-    bg = __ldg(p.bg_dev);
-    const int ethr = p.empty_thr >= 0 ? p.empty_thr : max(10, bg >> 1);
-    cthr = bg + ethr;  // max(x-bg,0) > ethr  <=>  x > bg + ethr   (ethr >= 0)
-  }
-  const uint32_t c12 = (uint32_t)min(cthr, 4095);      // 12-bit pixels never exceed 4095
-  const uint32_t nk_hi = ~((c12 << 20) | 0xFFFFFu);   // complemented bounds for add_gt
-  const uint32_t nk_lo = ~((c12 << 8) | 0xFFu);
-  const uint32_t ncthr = ~(uint32_t)cthr;
-
-  // Work item = 8-pixel group (16-byte vector stores) or, for float difference outputs, one
-  // pixel pair per lane (see load_pair).  prev[] holds the background-subtracted previous frame
-  // of this thread's pixels, two uint16 per register.
-  constexpr bool kPair = (DIFF == FF_DIFF_F32 || DIFF == FF_DIFF_F64);
-  constexpr int kItemPx = kPair ? 2 : kGroupPx;
-  constexpr int kItems = K * kGroupPx / kItemPx;        // items per thread per tile
-  const int tile_items = tile_groups * (kGroupPx / kItemPx);
-  uint32_t prev[kItems][kItemPx / 2];
 #pragma unroll
   for (int k = 0; k < kItems; ++k)
 #pragma unroll
-    for (int j = 0; j < kItemPx / 2; ++j) prev[k][j] = 0;
+    for (int j = 0; j < kItemPx / 2; ++j) prev[k][j] = kSimd ? 0xFFFFFFFFu : 0u;   // SIMD path keeps ~sub
   bool have_prev = false;
 
-  for (int it = 0; it < n_items; ++it) {
-    const int s = it % kStages;
-    const uint32_t parity = (uint32_t)(it / kStages) & 1u;
+  for (int it = 0; it < n_items; ++it, ++git) {
+    const int s = git % kStages;
+    const uint32_t parity = (git / kStages) & 1u;
     if (tid == 0) {
-      const int nx = it + kStages - 1;  // its stage was drained in iteration it-1
+      const int nx = it + kStages - 1;  // its stage was drained in the previous iteration
       if (nx < n_items) {
-        const int ns = nx % kStages;
+        const uint32_t ns = (git + kStages - 1) % kStages;
         mbar_arrive_expect_tx(&full[ns], tile_bytes);
         bulk_g2s(smem + ns * kStageBytes, src_of(nx), tile_bytes, &full[ns], policy);
       }
@@ -205,6 +225,7 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const StreamParams p) 
     const bool emit_diff = (DIFF != FF_DIFF_NONE) && !is_halo;
     const bool diff_valid = have_prev && !skipped;
     int cnt = 0;
+    uint32_t acc2 = 0;   // SIMD path: two 16-bit counters
 
 #pragma unroll
     for (int k = 0; k < kItems; ++k) {
@@ -213,6 +234,27 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const StreamParams p) 
         if (BITS == 12 && COUNT && DIFF == FF_DIFF_NONE && !DECODED) {   // count in place, no extraction
           const uint32_t* w = reinterpret_cast<const uint32_t*>(stage) + 3 * g;
           count12x8(w[0], w[1], w[2], nk_hi, nk_lo, cnt);
+          continue;
+        }
+        if (kSimd) {
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(stage) + 3 * g;
+          uint32_t x[4], o[4];
+          decode12x8_16x2(w[0], w[1], w[2], x);
+          const int64_t px = (int64_t)f * p.px_per_frame + tile_px0 + (int64_t)g * kGroupPx;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (COUNT) acc2 += __viaddmin_s16x2_relu(x[j], s_ncthr, dup);           // [x > cthr] per lane
+            const uint32_t sub2 = __viaddmax_s16x2(x[j], s_nbg, 0u);                // max(x - bg, 0)
+            const uint32_t e2 = __viaddmax_s16x2(sub2, prev[k][j], 0x80008000u);    // sub + ~prev = d - 1
+            const uint32_t r2 = __viaddmax_s16x2_relu(e2, s_k, 0u);                 // relu(d - (thr-1))
+            const uint32_t m2 = __vimin_s16x2_relu(r2, dup);                         // [d >= thr]
+            o[j] = diff_valid ? r2 + m2 * (uint32_t)tm1 : 0u;                       // d where d >= thr, else 0
+            if (!skipped) prev[k][j] = ~sub2;
+          }
+          if (DECODED && !is_halo)
+            __stcs(reinterpret_cast<uint4*>(p.decoded_out + px), make_uint4(x[0], x[1], x[2], x[3]));
+          if (emit_diff)
+            __stcs(reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.diff_out) + px), make_uint4(o[0], o[1], o[2], o[3]));
           continue;
         }
         int v[kItemPx];
@@ -274,21 +316,23 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const StreamParams p) 
         }
       }
     }
+    if (kSimd) cnt += (int)(acc2 & 0xFFFFu) + (int)(acc2 >> 16);
     if (DIFF != FF_DIFF_NONE && !skipped) have_prev = true;
 
     if (COUNT && !is_halo) {
       cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-      if ((tid & 31) == 0) warp_cnt[(it & 1) * 8 + (tid >> 5)] = cnt;
+      if ((tid & 31) == 0) warp_cnt[(git & 1) * 8 + (tid >> 5)] = cnt;
     }
     __syncthreads();  // stage s drained by every thread; warp_cnt visible
     if (COUNT && !is_halo && tid == 0) {
-      const int* wc = warp_cnt + (it & 1) * 8;
+      const int* wc = warp_cnt + (git & 1) * 8;
       int tot = 0;
 #pragma unroll
       for (int w = 0; w < kThreads / 32; ++w) tot += wc[w];
       p.partial[(int64_t)f * p.tiles_per_frame + tile] = tot;
     }
   }
+  }  // segments
 }
 
 // Shapes the TMA path cannot take (P % 32 != 0): one thread per pixel pair, plain loads,
@@ -380,14 +424,12 @@ int launch_stream(StreamParams p, cudaStream_t st) {
     ctas_per_sm[dev] = occ > 0 ? occ : 1;
     configured[dev] = true;
   }
-  // One resident wave: every CTA is long-lived and marches over its own frame chunk.
+  // One resident wave: the (tile, frame) items are split evenly over SMs x CTAs/SM long-lived CTAs.
   const int64_t wave = (int64_t)sm_count_cached() * ctas_per_sm[dev];
-  int64_t chunks = wave / p.tiles_per_frame;
-  if (chunks < 1) chunks = 1;
-  if (chunks > p.n_frames) chunks = p.n_frames;
-  p.frames_per_chunk = (int)((p.n_frames + chunks - 1) / chunks);
-  chunks = (p.n_frames + p.frames_per_chunk - 1) / p.frames_per_chunk;
-  const int64_t grid = chunks * p.tiles_per_frame;
+  const int64_t total_work = (int64_t)p.tiles_per_frame * p.n_frames;
+  p.items_per_cta = (total_work + wave - 1) / wave;
+  if (p.items_per_cta < 1) p.items_per_cta = 1;
+  const int64_t grid = (total_work + p.items_per_cta - 1) / p.items_per_cta;
   if (grid > 0x7FFFFFFF) return FF_ERR_UNSUPPORTED;
   kern<<<(unsigned)grid, kThreads, kSmem, st>>>(p);
   FF_CUDA_TRY(cudaGetLastError());
@@ -465,7 +507,7 @@ int stream_frames_impl(const void* frames, const void* halo, int64_t n_frames, i
   p.px_per_frame = px;
   p.n_frames = (int)n_frames;
   p.tiles_per_frame = t.tiles_per_frame;
-  p.frames_per_chunk = 1;
+  p.items_per_cta = 1;
   p.bg_dev = bg_dev;
   p.empty_thr = empty_thr;
   p.diff_thr = diff_thr;
