@@ -41,6 +41,7 @@ def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames-scale", type=float, default=1.0)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--only", default="", help="comma list of config:diff pairs, e.g. C4:uint16,C2:None")
     args = ap.parse_args()
     eng = FlameFrontEngine(0)
     peak = 6547.5
@@ -57,6 +58,9 @@ def main() -> None:
         ("C4", "gradient", "float64", False),
         ("C2", "half_maximum", None, True),       # also materialise decoded uint16 frames
     ]
+    if args.only:
+        want = {tuple(x.split(":")) for x in args.only.split(",")}
+        cases = [c for c in cases if (c[0], str(c[2])) in want and not c[3]]
     cache = {}
     for name, method, diff, decoded in cases:
         base = syn.config_spec(name)
