@@ -45,14 +45,16 @@ def workload_spec(total_frames: int):
                                 "t_enter": float(max(2, total_frames - FLAME_FRAMES))})
 
 
-def config_dict(world: int, frames_per_gpu: int, chunk_mb: int) -> dict:
+def config_dict(world: int, frames_per_gpu: int, chunk_mb: int, transport: str = "") -> dict:
+    extra = {"exchange_transport": transport} if transport else {}
     return {
+        **extra,
         "workload": "C2: Nova-style synthetic 1024x128, packed 12-bit MRAW, half_maximum on the "
                     "frame-difference centre-row profile, per-file calibration",
         "frames_per_gpu": frames_per_gpu, "total_frames": frames_per_gpu * world,
         "width": 1024, "height": 128, "bits": 12, "detection_method": "half_maximum",
         "sharding": "single GPU" if world == 1 else f"contiguous frame ranges + 1-frame halo over {world} GPUs; "
-                    "NCCL all-reduce(min) of the exit frame + all-gather of positions per step",
+                    "one exchange kernel per rank and step (exit-frame min + truncation + position gather)",
         "l2": "inputs larger than L2 (3.93 GB per GPU per step >> 126 MB); no flush needed",
         "e2e_chunk_mb": chunk_mb,
     }
@@ -238,8 +240,10 @@ def own_arm(args) -> None:
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    from high_speed_image_processing_b200.sharding import bind_to_gpu_numa_node
+    numa_cpus = bind_to_gpu_numa_node(local_rank)      # before any pinned allocation
     eng = FlameFrontEngine(local_rank, host_chunk_bytes=args.chunk_mb << 20)
-    exchange = RangeExchange()
+    exchange = RangeExchange(engine=eng, transport=args.exchange)
 
     fpr = args.frames
     total = fpr * world
@@ -267,11 +271,13 @@ def own_arm(args) -> None:
 
     # ---------------- device-resident: `value` ------------------------------------------------
     def step_device():
-        res = eng.process_range(packed, fpr, h, w, 12, params, frame0=frame0, first_frame=a, halo=halo,
-                                truncate=(world == 1))
-        if world > 1:
-            g = exchange.finish(res.pos, res.first_exit, total, eng.truncate, counts_local=res.counts)
+        if world > 1:       # ff_detect writes straight into this rank's range block; one kernel finishes
+            blk = exchange.begin(total)
+            eng.process_range(packed, fpr, h, w, 12, params, frame0=frame0, first_frame=a, halo=halo,
+                              truncate=False, pos_out=blk.pos, counts_out=blk.counts, first_exit=blk.first_exit)
+            g = exchange.finish(blk)
             return g.pos, g.first_exit_t, g.counts
+        res = eng.process_range(packed, fpr, h, w, 12, params, frame0=frame0, first_frame=a, halo=halo)
         return res.pos, res.first_exit, res.counts
 
     for _ in range(args.warmup):
@@ -290,6 +296,7 @@ def own_arm(args) -> None:
         pos_t, fe_t, cnt_t = step_device()
     ev1.record()
     barrier()
+    exchange.check()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = eng.launches - launches0
     stream_ms = [e0.elapsed_time(e1) for e0, e1 in eng._stream_events]
@@ -324,9 +331,8 @@ def own_arm(args) -> None:
         scalars, _ = eng.clip_scalars(f0, h, w, 12)
         hres = eng.process_host(host, fpr, h, w, 12, params, scalars, first_frame=a, halo=halo_host)
         if world > 1:
-            g = exchange.finish(torch.from_numpy(hres.pos).to(device),
-                                torch.tensor([hres.first_exit], dtype=torch.int32, device=device), total,
-                                eng.truncate)
+            g = exchange.finish_arrays(torch.from_numpy(hres.pos).to(device),
+                                       torch.tensor([hres.first_exit], dtype=torch.int32, device=device), total)
             return g.pos.cpu().numpy(), g.first_exit
         return hres.pos, hres.first_exit
 
@@ -391,7 +397,7 @@ def own_arm(args) -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": config_dict(world, fpr, args.chunk_mb),
+            "config": config_dict(world, fpr, args.chunk_mb, exchange.transport if world > 1 else ""),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "kernel": "ff::stream_kernel<12,count,K=4>",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": fpr * alg_bytes_per_frame,
@@ -408,6 +414,7 @@ def own_arm(args) -> None:
             "result": {"first_exit_frame": first_exit, "detections": int(det.size)},
         }
         print(json.dumps(line), flush=True)
+    exchange.close()
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -424,6 +431,8 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--sample-frames", type=int, default=4000, help="CPU baseline sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", choices=["auto", "peer", "gathered"], default="auto",
+                    help="multi-GPU block transport: peer memory over NVLink (CUDA IPC) or one NCCL all-gather")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3                      # timing rule: at least 3 warm-up steps

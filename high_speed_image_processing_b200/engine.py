@@ -269,7 +269,8 @@ class FlameFrontEngine:
                       skip: Optional[torch.Tensor] = None, diff_dtype: Optional[str] = None,
                       keep_profiles: bool = False, keep_decoded: bool = False,
                       first_exit: Optional[torch.Tensor] = None, truncate: bool = True,
-                      partial: Optional[torch.Tensor] = None) -> RangeResult:
+                      partial: Optional[torch.Tensor] = None, pos_out: Optional[torch.Tensor] = None,
+                      counts_out: Optional[torch.Tensor] = None) -> RangeResult:
         """Fused front end + detection + exit min (+ local truncation) on a device-resident
         contiguous frame range.  Nothing but two tiny scalars ever goes to the host.
 
@@ -277,8 +278,18 @@ class FlameFrontEngine:
         clip's first frame, packed, on the device; defaults to ``frames[0]`` when
         ``first_frame == 0``): then the background reduction is launched first, the streaming
         kernel starts right behind it with device-side thresholds, and the host computes the
-        float64 centre-row statistics while that kernel runs - the GPU never waits for the host."""
+        float64 centre-row statistics while that kernel runs - the GPU never waits for the host.
+
+        ``pos_out`` / ``counts_out`` / ``first_exit`` let the caller supply the int32 output
+        arrays - e.g. views into a range block of ``sharding.RangeExchange`` so that the
+        multi-GPU exchange needs no packing copy (``first_exit`` must then be pre-set to
+        FF_NO_EXIT by the block's owner)."""
         self._check_dev(frames, "frames")
+        for name, t in (("pos_out", pos_out), ("counts_out", counts_out)):
+            if t is not None:
+                self._check_dev(t, name)
+                if t.dtype != torch.int32 or t.numel() < n_frames:
+                    raise ValueError(f"{name} must be int32 with at least {n_frames} elements")
         fb = frame_nbytes(height, width, bits)
         if frames.dtype != torch.uint8 or frames.numel() < n_frames * fb:
             raise ValueError(f"frames must be uint8 with at least {n_frames * fb} bytes")
@@ -320,8 +331,10 @@ class FlameFrontEngine:
                     "ff_partial_len")
         if partial is None or partial.numel() < n_elems.value:
             partial = torch.empty(max(1, n_elems.value), dtype=torch.int32, device=self.device)
-        pos = torch.empty(n_frames, dtype=torch.int32, device=self.device)
-        counts = torch.empty(n_frames, dtype=torch.int32, device=self.device)
+        pos = pos_out[:n_frames] if pos_out is not None else torch.empty(n_frames, dtype=torch.int32,
+                                                                         device=self.device)
+        counts = counts_out[:n_frames] if counts_out is not None else torch.empty(n_frames, dtype=torch.int32,
+                                                                                  device=self.device)
         if first_exit is None:
             first_exit = torch.full((1,), FF_NO_EXIT, dtype=torch.int32, device=self.device)
         diff = None if diff_torch is None else torch.empty((n_frames, height, width), dtype=diff_torch,
@@ -430,6 +443,26 @@ class FlameFrontEngine:
         with torch.cuda.device(self.device):
             _cabi.check(self._lib.ff_truncate(pos.data_ptr(), pos.numel(), first_frame, first_exit.data_ptr(),
                                               self._stream()), "ff_truncate")
+        self.launches += 1
+
+    def merge_ranges(self, gathered: torch.Tensor, world: int, cap_frames: int, total: int,
+                     pos_out: torch.Tensor, counts_out: Optional[torch.Tensor],
+                     first_exit_out: torch.Tensor) -> None:
+        """Finish a range-sharded clip from the all-gathered range blocks (``ff_merge_ranges``):
+        global exit frame = min of the block headers, truncation against it, de-padding."""
+        self._check_dev(gathered, "gathered")
+        self._check_dev(pos_out, "pos_out")
+        self._check_dev(first_exit_out, "first_exit_out")
+        if gathered.dtype != torch.int32 or gathered.numel() < world * (4 + 2 * cap_frames):
+            raise ValueError("gathered must hold world range blocks of int32")
+        if pos_out.dtype != torch.int32 or pos_out.numel() < total:
+            raise ValueError("pos_out must be int32[total]")
+        if counts_out is not None:
+            self._check_dev(counts_out, "counts_out")
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.ff_merge_ranges(gathered.data_ptr(), world, cap_frames, total, pos_out.data_ptr(),
+                                                  _ptr(counts_out), first_exit_out.data_ptr(), self._stream()),
+                        "ff_merge_ranges")
         self.launches += 1
 
     # ------------------------------------------------------------------ host-resident clips

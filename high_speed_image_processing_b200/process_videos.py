@@ -207,30 +207,31 @@ def process_video(video: PhotonVideo, config: VideoSourceConfig, calibration: fl
     if residency not in ("device", "host"):
         raise ValueError("residency must be 'auto', 'device' or 'host'")
 
-    if b - a == 0:
-        pos_local = torch.empty(0, dtype=torch.int32, device=eng.device)
-        cnt_local = torch.empty(0, dtype=torch.int32, device=eng.device)
-        fe_local = torch.full((1,), FF_NO_EXIT, dtype=torch.int32, device=eng.device)
-    elif residency == "device" or multi:
+    if multi:
+        # every rank fills its range block in place; one exchange kernel per rank finishes the clip
+        if exchange.engine is None:
+            exchange.engine = eng
+        blk = exchange.begin(n, eng.device)
+        if b - a > 0:
+            frames_dev = torch.from_numpy(np.ascontiguousarray(video.raw_frames(a, b))).to(eng.device)
+            halo_dev = None if halo_np is None else torch.from_numpy(np.ascontiguousarray(halo_np)).to(eng.device)
+            skip_dev = None if skip_np is None else torch.from_numpy(skip_np[a:b].copy()).to(eng.device)
+            eng.process_range(frames_dev, b - a, h, w, bits, params, scalars, bg_dev, first_frame=a,
+                              halo=halo_dev, skip=skip_dev, truncate=False, pos_out=blk.pos,
+                              counts_out=blk.counts, first_exit=blk.first_exit)
+        g = exchange.finish(blk)
+        pos_np, cnt_np, first_exit = g.pos.cpu().numpy(), g.counts.cpu().numpy(), g.first_exit
+        exchange.check()
+    elif residency == "device":
         frames_dev = torch.from_numpy(np.ascontiguousarray(video.raw_frames(a, b))).to(eng.device)
-        halo_dev = None if halo_np is None else torch.from_numpy(np.ascontiguousarray(halo_np)).to(eng.device)
-        skip_dev = None if skip_np is None else torch.from_numpy(skip_np[a:b].copy()).to(eng.device)
-        res = eng.process_range(frames_dev, b - a, h, w, bits, params, scalars, bg_dev, first_frame=a,
-                                halo=halo_dev, skip=skip_dev, truncate=not multi)
-        pos_local, cnt_local, fe_local = res.pos, res.counts, res.first_exit
+        skip_dev = None if skip_np is None else torch.from_numpy(skip_np).to(eng.device)
+        res = eng.process_range(frames_dev, n, h, w, bits, params, scalars, bg_dev, skip=skip_dev)
+        pos_np, cnt_np = res.pos.cpu().numpy(), res.counts.cpu().numpy()
+        first_exit = int(res.first_exit.cpu().item())
     else:
         hres = eng.process_host(video.raw_frames(a, b), b - a, h, w, bits, params, scalars, first_frame=a,
                                 halo=halo_np, skip=None if skip_np is None else skip_np[a:b])
         pos_np, cnt_np, first_exit = hres.pos, hres.counts, hres.first_exit
-        pos_local = cnt_local = fe_local = None
-
-    if pos_local is not None:
-        if multi:
-            g = exchange.finish(pos_local, fe_local, n, eng.truncate, counts_local=cnt_local)
-            pos_np, cnt_np, first_exit = g.pos.cpu().numpy(), g.counts.cpu().numpy(), g.first_exit
-        else:
-            pos_np, cnt_np = pos_local.cpu().numpy(), cnt_local.cpu().numpy()
-            first_exit = int(fe_local.cpu().item())
 
     kb_min = eng_min_signal(params, h * w)
     processed = np.ones(n, dtype=bool) if skip_np is None else skip_np == 0
@@ -472,13 +473,15 @@ def main() -> None:
     if "RANK" in os.environ and "WORLD_SIZE" in os.environ:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl")
-        exchange = RangeExchange()
+        from .engine import get_engine
+        exchange = RangeExchange(engine=get_engine())
         if exchange.rank == 0:
             print(f"Running on {exchange.size} GPUs")
     for cfg in default_configs():
         if cfg.enabled and cfg.video_path and Path(cfg.video_path).exists():
             process_video_source(cfg, None, exchange=exchange)
     if exchange is not None:
+        exchange.close()
         dist.barrier()
         dist.destroy_process_group()
     if exchange is None or exchange.rank == 0:

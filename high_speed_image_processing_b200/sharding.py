@@ -8,20 +8,35 @@ Frames shard naturally:
   look-back of the frame difference (scripts/process_videos.py:397-399,469);
 * across clips: whole videos round-robin over ranks (src/photron/parallel.py:173-208).
 
-The single real exchange is tiny: an all-reduce(min) of the first exit frame (one int32)
-followed by an all-gather of the per-rank position arrays.  It replaces the reference's
-pickled ``comm.gather`` (scripts/process_videos.py:1533-1541) and turns the per-rank ``break``
-(:1494) into a global truncation (README.md:145-149).  NCCL on GPUs, gloo in CPU tests.
+The single real exchange is tiny - the first exit frame (one int32, min over ranks) and the
+per-rank position / count arrays - and it is ONE step: every rank's ``ff_detect`` writes into
+a *range block* ``{first_exit,0,0,0 | pos[cap] | counts[cap]}`` and one kernel per rank turns
+the blocks of all ranks into the truncated whole-clip arrays (csrc/ff_exchange.cu).  It
+replaces the reference's pickled ``comm.gather`` (scripts/process_videos.py:1533-1541) and
+turns the per-rank ``break`` (:1494) into a global truncation (README.md:145-149).
+
+Transports for the blocks:
+
+``peer``      (GPUs of one box) blocks stay in place; peers map them over NVLink through CUDA
+              IPC and the finishing kernel pulls them itself, synchronising on epoch flags in
+              peer memory - no collective on the data path (``ff_exchange_*``).
+``gathered``  one ``all_gather_into_tensor`` of the blocks (NCCL; gloo in the CPU tests), then
+              ``ff_merge_ranges``.
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
+import socket
 from dataclasses import dataclass
-from typing import List, Optional, Sequence, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
 
 from ._cabi import FF_NO_EXIT, FF_POS_DROPPED
+
+BLOCK_HEADER = 4        # int32 words in front of a range block's arrays (csrc/ff_exchange.cu: kHdr)
 
 
 def contiguous_range(total: int, rank: int, size: int) -> Tuple[int, int]:
@@ -50,62 +65,265 @@ def assign_videos(n_videos: int, rank: int, size: int, weights: Optional[Sequenc
     return [v for v in range(n_videos) if owner[v] == rank]
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[List[int]]:
+    """Pin this process to the CPUs local to its GPU (``/sys/bus/pci/devices/<bdf>/local_cpulist``)
+    so that the pinned staging memory it allocates afterwards is first-touched on the GPU's own
+    NUMA node: with 8 ranks streaming ~55 GB/s each, host memory placed on the wrong socket
+    becomes the bottleneck.  Returns the CPU list, or None when the topology is not exposed."""
+    bdf = None
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+    except Exception:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            raw = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
+            raw = (raw.decode() if isinstance(raw, bytes) else str(raw)).lower()
+            bdf = raw[4:] if len(raw.split(":")[0]) == 8 else raw      # 00000000:1b:00.0 -> 0000:1b:00.0
+        except Exception:
+            return None
+    path = f"/sys/bus/pci/devices/{bdf}/local_cpulist"
+    try:
+        text = open(path).read().strip()
+        cpus: List[int] = []
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.extend(range(int(a), int(b) + 1))
+            elif part:
+                cpus.append(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
+@dataclass
+class RangeBlock:
+    """This rank's outputs for one step, laid out for the exchange."""
+    total: int                      # frames in the whole clip
+    cap: int                        # capacity of pos / counts (ceil(total / world) or larger)
+    pos: torch.Tensor               # int32[cap] view  - ff_detect's pos_out
+    counts: torch.Tensor            # int32[cap] view  - ff_detect's count_out
+    first_exit: torch.Tensor        # int32[1] view    - ff_detect's first_exit (pre-set to FF_NO_EXIT)
+    send: Optional[torch.Tensor] = None     # gathered transport: the whole block
+
+
 @dataclass
 class GatheredRange:
     first_exit_t: torch.Tensor      # int32[1] global index of the first exit frame, or FF_NO_EXIT
     pos: torch.Tensor               # int32[total] positions of the whole clip, truncated
-    counts: Optional[torch.Tensor]  # int32[total] above-noise counts (if provided)
+    counts: Optional[torch.Tensor]  # int32[total] above-noise counts
 
     @property
     def first_exit(self) -> int:    # synchronises on the device scalar
         return int(self.first_exit_t.item())
 
 
-class RangeExchange:
-    """The exit-min + result-gather step over a process group."""
+class _DevicePointerView:
+    """Expose raw device memory (owned by libflamefront) to torch through the CUDA array interface."""
 
-    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, ptr: int, n_int32: int):
+        self.__cuda_array_interface__ = {"shape": (n_int32,), "typestr": "<i4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+MergeFn = Callable[[torch.Tensor, int, int, int, torch.Tensor, Optional[torch.Tensor], torch.Tensor], None]
+
+
+class RangeExchange:
+    """The exit-min + truncation + result-gather step over a process group.
+
+    ``engine``: the rank's ``FlameFrontEngine`` (supplies ``ff_merge_ranges`` and, for the peer
+    transport, the C-ABI handle).  ``transport``: "auto" (peer memory when every rank is a GPU of
+    this host and the IPC mapping succeeds, else gathered), "peer" or "gathered".  Without an
+    engine (CPU tests of the host logic) the transport is "gathered" and ``finish`` needs a
+    ``merge`` callable."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, engine=None, transport: str = "auto"):
+        if transport not in ("auto", "peer", "gathered"):
+            raise ValueError("transport must be 'auto', 'peer' or 'gathered'")
         self.group = group
+        self.engine = engine
         self.active = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if self.active else 0
         self.size = dist.get_world_size(group) if self.active else 1
+        self._want = transport
+        self.transport = "gathered"
+        self._xchg = None               # ff_exchange* (peer transport)
+        self._xchg_cap = 0
+        self._xchg_buf = None           # torch view of the exchange's local allocation
+        self._bufs = {}                 # gathered transport: (cap, device) -> (send, recv, init)
+        self._peer_failed = False
 
+    # ------------------------------------------------------------------ partition
     def my_range(self, total: int) -> Tuple[int, int]:
         return contiguous_range(total, self.rank, self.size)
 
-    def exit_min(self, first_exit: torch.Tensor) -> torch.Tensor:
-        """In-place all-reduce(min) of the int32[1] first-exit scalar."""
-        if self.active and self.size > 1:
-            dist.all_reduce(first_exit, op=dist.ReduceOp.MIN, group=self.group)
-        return first_exit
+    def block_cap(self, total: int) -> int:
+        return max(1, -(-total // self.size))
 
-    def gather_ranges(self, local: torch.Tensor, total: int, fill: int = FF_POS_DROPPED) -> torch.Tensor:
-        """All-gather per-rank int32 blocks (contiguous_range layout) into int32[total]."""
+    # ------------------------------------------------------------------ peer transport set-up
+    def _peer_possible(self) -> bool:
+        if self._want == "gathered" or self._peer_failed or self.engine is None:
+            return False
         if not (self.active and self.size > 1):
-            return local
-        base, extra = divmod(total, self.size)
-        width = base + (1 if extra else 0)
-        padded = torch.full((width,), fill, dtype=local.dtype, device=local.device)
-        padded[: local.numel()] = local
-        out = torch.empty(self.size * width, dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(out, padded, group=self.group)
-        if extra == 0:
-            return out
-        parts = []
-        for r in range(self.size):
-            a, b = contiguous_range(total, r, self.size)
-            parts.append(out[r * width: r * width + (b - a)])
-        return torch.cat(parts)
+            return False
+        if dist.get_backend(self.group) != "nccl":
+            return False
+        return True
 
-    def finish(self, pos_local: torch.Tensor, first_exit_local: torch.Tensor, total: int,
-               truncate, counts_local: Optional[torch.Tensor] = None) -> GatheredRange:
-        """exit-min, local truncation against the GLOBAL exit frame, then the gathers.
+    def _setup_peer(self, cap: int) -> bool:
+        """Create the exchange context and map the peers' blocks.  Collective: every rank calls
+        it with the same ``cap``; the outcome is agreed on by all ranks."""
+        eng = self.engine
+        lib = eng._lib
+        dev = eng.device
+        ok = 1
+        ctx = C.c_void_p()
+        hb = lib.ff_exchange_handle_bytes()
+        handle = (C.c_ubyte * hb)()
+        try:
+            # all ranks must be GPUs of one host
+            names = [None] * self.size
+            dist.all_gather_object(names, socket.gethostname(), group=self.group)
+            if len(set(names)) != 1:
+                ok = 0
+            if ok:
+                with torch.cuda.device(dev):
+                    st = lib.ff_exchange_create(dev.index, self.rank, self.size, cap, C.byref(ctx))
+                    if st == 0:
+                        st = lib.ff_exchange_get_handle(ctx, handle)
+                    if st != 0:
+                        ok = 0
+        except Exception:
+            ok = 0
+        mine = torch.tensor(list(bytes(handle)) + [ok], dtype=torch.uint8, device=dev)
+        allh = torch.empty(self.size * (hb + 1), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        allh_np = allh.cpu().numpy().reshape(self.size, hb + 1)
+        if not bool(allh_np[:, hb].all()):
+            ok = 0
+        if ok:
+            packed = allh_np[:, :hb].copy().tobytes()
+            with torch.cuda.device(dev):
+                if lib.ff_exchange_open_peers(ctx, packed) != 0:
+                    ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) != 1:
+            if ctx.value:
+                lib.ff_exchange_destroy(ctx)
+            if self._want == "peer":
+                raise RuntimeError("peer-memory exchange requested but CUDA IPC mapping of the peers failed")
+            self._peer_failed = True
+            return False
+        self._xchg, self._xchg_cap = ctx, cap
+        self.transport = "peer"
+        return True
 
-        ``truncate(pos_local, first_frame, first_exit)`` applies the truncation in place; on
-        GPUs it is ``FlameFrontEngine.truncate`` (the ff_truncate kernel)."""
-        start, _ = self.my_range(total)
-        fe = self.exit_min(first_exit_local)
-        truncate(pos_local, start, fe)
-        pos = self.gather_ranges(pos_local, total)
-        counts = None if counts_local is None else self.gather_ranges(counts_local, total, fill=0)
+    def close(self) -> None:
+        if self._xchg is not None:
+            if self.active:
+                torch.cuda.synchronize(self.engine.device)
+                dist.barrier(group=self.group)       # no peer may still be reading my blocks
+            self.engine._lib.ff_exchange_destroy(self._xchg)
+            self._xchg = None
+            self._xchg_buf = None
+
+    # ------------------------------------------------------------------ one step
+    def begin(self, total: int, device: Optional[torch.device] = None) -> RangeBlock:
+        """Start a step: returns the block whose views ``ff_detect`` fills
+        (``engine.process_range(..., pos_out=blk.pos, counts_out=blk.counts,
+        first_exit=blk.first_exit, truncate=False)``)."""
+        cap = self.block_cap(total)
+        if device is None:
+            device = self.engine.device if self.engine is not None else torch.device("cpu")
+        if self._peer_possible() and (self._xchg is None or cap > self._xchg_cap):
+            if self._xchg is not None:
+                self.close()
+            self._setup_peer(cap)
+        if self._xchg is not None:
+            eng = self.engine
+            pos_p, cnt_p, fe_p = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            with torch.cuda.device(eng.device):
+                st = eng._lib.ff_exchange_begin(self._xchg, C.byref(pos_p), C.byref(cnt_p), C.byref(fe_p),
+                                                torch.cuda.current_stream(eng.device).cuda_stream)
+            if st != 0:
+                raise RuntimeError(f"ff_exchange_begin failed ({st})")
+            xc = self._xchg_cap
+
+            def view(ptr, n):
+                return torch.as_tensor(_DevicePointerView(ptr.value, n), device=eng.device)
+            return RangeBlock(total, xc, view(pos_p, xc), view(cnt_p, xc), view(fe_p, 1))
+        key = (cap, str(device))
+        if key not in self._bufs:
+            n = BLOCK_HEADER + 2 * cap
+            send = torch.zeros(n, dtype=torch.int32, device=device)
+            recv = torch.zeros(self.size * n, dtype=torch.int32, device=device)
+            init = torch.tensor([FF_NO_EXIT, 0, 0, 0], dtype=torch.int32, device=device)
+            self._bufs[key] = (send, recv, init)
+        send, _, init = self._bufs[key]
+        send[:BLOCK_HEADER].copy_(init)
+        return RangeBlock(total, cap, send[BLOCK_HEADER:BLOCK_HEADER + cap],
+                          send[BLOCK_HEADER + cap:BLOCK_HEADER + 2 * cap], send[0:1], send)
+
+    def finish(self, blk: RangeBlock, merge: Optional[MergeFn] = None, want_counts: bool = True) -> GatheredRange:
+        """Exchange + merge: every rank returns the whole clip's truncated positions, counts and
+        the global first exit frame.  ``merge`` defaults to the engine's ``ff_merge_ranges``."""
+        device = blk.pos.device
+        pos = torch.empty(blk.total, dtype=torch.int32, device=device)
+        counts = torch.empty(blk.total, dtype=torch.int32, device=device) if want_counts else None
+        fe = torch.empty(1, dtype=torch.int32, device=device)
+        if blk.send is None:            # peer transport
+            eng = self.engine
+            with torch.cuda.device(eng.device):
+                st = eng._lib.ff_exchange_finish(self._xchg, blk.total, pos.data_ptr(),
+                                                 None if counts is None else counts.data_ptr(), fe.data_ptr(),
+                                                 torch.cuda.current_stream(eng.device).cuda_stream)
+            if st != 0:
+                raise RuntimeError(f"ff_exchange_finish failed ({st})")
+            eng.launches += 1
+            return GatheredRange(fe, pos, counts)
+        key = (blk.cap, str(device))
+        send, recv, _ = self._bufs[key]
+        if self.active and self.size > 1:
+            dist.all_gather_into_tensor(recv, send, group=self.group)
+        else:
+            recv = send
+        if merge is None:
+            if self.engine is None:
+                raise ValueError("finish needs an engine or a merge callable")
+            merge = self.engine.merge_ranges
+        merge(recv, self.size, blk.cap, blk.total, pos, counts, fe)
         return GatheredRange(fe, pos, counts)
+
+    def finish_arrays(self, pos_local: torch.Tensor, first_exit_local: torch.Tensor, total: int,
+                      merge: Optional[MergeFn] = None, counts_local: Optional[torch.Tensor] = None) -> GatheredRange:
+        """Same step for results that were not written in place (e.g. they came back from the
+        host-streamed path): copies them into a block first."""
+        blk = self.begin(total, pos_local.device)
+        n = pos_local.numel()
+        blk.pos[:n].copy_(pos_local)
+        if counts_local is not None:
+            blk.counts[:n].copy_(counts_local)
+        blk.first_exit.copy_(first_exit_local.reshape(1))
+        return self.finish(blk, merge, want_counts=counts_local is not None)
+
+    def check(self) -> None:
+        """Peer transport: raise if a peer failed to arrive in the last steps (synchronises)."""
+        if self._xchg is None:
+            return
+        eng = self.engine
+        status = C.c_int32(0)
+        with torch.cuda.device(eng.device):
+            st = eng._lib.ff_exchange_status(self._xchg, C.byref(status),
+                                             torch.cuda.current_stream(eng.device).cuda_stream)
+        if st != 0 or status.value != 0:
+            raise RuntimeError(f"peer-memory exchange: rank {status.value - 1} never published its block "
+                               f"(status {st})")

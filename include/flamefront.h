@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FF_ABI_VERSION 1
+#define FF_ABI_VERSION 2
 
 /* status codes */
 #define FF_OK                 0
@@ -142,6 +142,45 @@ int ff_detect(const void* frames_dev, const void* halo_dev, int64_t n_frames, in
  * run *first_exit_dev holds the all-reduced (min) value.                                   */
 int ff_truncate(int32_t* pos_dev, int64_t n_frames, int64_t first_frame,
                 const int32_t* first_exit_dev, void* stream);
+
+/* ---- stage 4 across GPUs: the one exchange step of a range-sharded clip -----------------------------
+ * Replaces the pickled `comm.gather` + sort of per-rank result lists (scripts/process_videos.py:
+ * 1533-1541) and turns the per-rank `break` (:1494) into the global truncation of README.md:145-149.
+ * Every rank owns contiguous_range(total, rank, world) (the contiguous variant of
+ * MPIVideoProcessor.distribute_indices, src/photron/parallel.py:101-113) and lets ff_detect write
+ * into a RANGE BLOCK of int32:  { first_exit, 0, 0, 0 | pos[cap] | counts[cap] }  (ff_range_block_len).
+ *
+ * Transport 1 - gathered: the caller all-gathers the blocks (one all_gather_into_tensor) and
+ * ff_merge_ranges finishes: global exit = min of the headers, truncation, de-padding into
+ * pos_out_dev[total] / count_out_dev[total] (nullable) / first_exit_out_dev[1].
+ *
+ * Transport 2 - peer memory (one box, NVLink): ff_exchange_* keeps the blocks where ff_detect wrote
+ * them; peers map them through CUDA IPC and ONE kernel per rank publishes an epoch flag to every
+ * peer, waits for theirs, pulls their blocks over NVLink and merges - no collective call on the
+ * data path.  Blocks are double-buffered by epoch parity, so a step needs no second barrier.
+ *   ff_exchange_create      allocates the local blocks + flag row (cap_frames per block)
+ *   ff_exchange_get_handle  writes ff_exchange_handle_bytes() bytes to exchange with the peers
+ *   ff_exchange_open_peers  handles = world * handle_bytes, rank-major (own slot ignored)
+ *   ff_exchange_begin       next epoch: returns this epoch's pos/count/first_exit device pointers
+ *                           (first_exit reset to FF_NO_EXIT on `stream`) for ff_detect to fill
+ *   ff_exchange_finish      the fused publish/wait/pull/merge kernel; every rank must call it once
+ *                           per ff_exchange_begin
+ *   ff_exchange_status      synchronises `stream`; *status_out != 0 means a peer (value-1) never
+ *                           published within ~2 s and the outputs are invalid                          */
+int ff_range_block_len(int64_t cap_frames, int64_t* n_elems);
+int ff_merge_ranges(const int32_t* gathered_dev, int world, int64_t block_cap_frames, int64_t total_frames,
+                    int32_t* pos_out_dev, int32_t* count_out_dev, int32_t* first_exit_out_dev, void* stream);
+typedef struct ff_exchange ff_exchange;
+int ff_exchange_create(int device, int rank, int world, int64_t cap_frames, ff_exchange** out);
+int ff_exchange_handle_bytes(void);
+int ff_exchange_get_handle(ff_exchange* x, void* handle_out);
+int ff_exchange_open_peers(ff_exchange* x, const void* handles);
+int ff_exchange_begin(ff_exchange* x, int32_t** pos_dev, int32_t** count_dev, int32_t** first_exit_dev,
+                      void* stream);
+int ff_exchange_finish(ff_exchange* x, int64_t total_frames, int32_t* pos_out_dev, int32_t* count_out_dev,
+                       int32_t* first_exit_out_dev, void* stream);
+int ff_exchange_status(ff_exchange* x, int32_t* status_out, void* stream);
+int ff_exchange_destroy(ff_exchange* x);
 
 /* ---- HEAD-parity detector (the code the reference executes at HEAD) ------------------------------
  * ff_head_lines replaces, per non-empty frame, the image pipeline of FlameDetector.detect

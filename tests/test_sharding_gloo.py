@@ -11,7 +11,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from high_speed_image_processing_b200 import synthetic as syn
-from high_speed_image_processing_b200.sharding import RangeExchange, assign_videos, contiguous_range
+from high_speed_image_processing_b200.sharding import (BLOCK_HEADER, RangeExchange, assign_videos,
+                                                       bind_to_gpu_numa_node, contiguous_range)
 from high_speed_image_processing_b200._cabi import FF_NO_EXIT, FF_POS_DROPPED
 from oracle import flame_oracle as fo
 
@@ -22,9 +23,17 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _torch_truncate(pos, first_frame, first_exit):
-    idx = torch.arange(first_frame, first_frame + pos.numel())
-    pos.masked_fill_(idx >= first_exit.to(torch.int64), FF_POS_DROPPED)
+def _torch_merge(gathered, world, cap, total, pos_out, counts_out, first_exit_out):
+    """CPU stand-in for the ff_merge_ranges kernel (csrc/ff_exchange.cu) - same block layout."""
+    blocks = gathered.view(world, BLOCK_HEADER + 2 * cap)
+    fe = int(blocks[:, 0].min())
+    first_exit_out[0] = fe
+    for r in range(world):
+        a, b = contiguous_range(total, r, world)
+        pos_out[a:b] = blocks[r, BLOCK_HEADER:BLOCK_HEADER + (b - a)]
+        if counts_out is not None:
+            counts_out[a:b] = blocks[r, BLOCK_HEADER + cap:BLOCK_HEADER + cap + (b - a)]
+    pos_out[min(fe, total):] = FF_POS_DROPPED
 
 
 def _worker(rank, size, port, n_frames, margin, out_dir):
@@ -40,10 +49,17 @@ def _worker(rank, size, port, n_frames, margin, out_dir):
         params = fo.ClipParams(method="threshold", exit_margin_px=margin)
         part = fo.process_clip(frames[a:b], params, frame0=frames[0], first_index=a,
                                prior_frame=frames[a - 1] if a > 0 else None)
-        pos_local = torch.from_numpy(part.pos_px.copy())
         fe = FF_NO_EXIT if part.first_exit == b - a else a + part.first_exit
-        g = ex.finish(pos_local, torch.tensor([fe], dtype=torch.int32), n_frames, _torch_truncate,
-                      counts_local=torch.from_numpy(part.nonempty.astype(np.int32)))
+        if rank % 2 == 0:      # in place, the way ff_detect fills a block
+            blk = ex.begin(n_frames, torch.device("cpu"))
+            assert int(blk.first_exit[0]) == FF_NO_EXIT and blk.pos.numel() == ex.block_cap(n_frames)
+            blk.pos[:b - a] = torch.from_numpy(part.pos_px.copy())
+            blk.counts[:b - a] = torch.from_numpy(part.nonempty.astype(np.int32))
+            blk.first_exit[0] = fe
+            g = ex.finish(blk, _torch_merge)
+        else:                  # results that came from elsewhere (the host-streamed path)
+            g = ex.finish_arrays(torch.from_numpy(part.pos_px.copy()), torch.tensor([fe], dtype=torch.int32),
+                                 n_frames, _torch_merge, counts_local=torch.from_numpy(part.nonempty.astype(np.int32)))
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), pos=g.pos.numpy(), counts=g.counts.numpy(),
                  first_exit=g.first_exit)
     finally:
@@ -93,8 +109,35 @@ def test_single_process_exchange_is_identity():
     ex = RangeExchange()
     assert (ex.rank, ex.size) == (0, 1) and ex.my_range(9) == (0, 9)
     pos = torch.tensor([1, 2, 90, 3], dtype=torch.int32)
-    g = ex.finish(pos, torch.tensor([2], dtype=torch.int32), 4, _torch_truncate)
-    assert g.first_exit == 2 and g.pos.tolist() == [1, 2, FF_POS_DROPPED, FF_POS_DROPPED]
+    g = ex.finish_arrays(pos, torch.tensor([2], dtype=torch.int32), 4, _torch_merge)
+    assert g.first_exit == 2 and g.pos.tolist() == [1, 2, FF_POS_DROPPED, FF_POS_DROPPED] and g.counts is None
+    assert ex.transport == "gathered"
+    with pytest.raises(ValueError):
+        ex.finish(ex.begin(4, torch.device("cpu")))          # no engine and no merge callable
+    with pytest.raises(ValueError):
+        RangeExchange(transport="carrier-pigeon")
+
+
+def test_steps_reuse_the_block_and_reset_the_header():
+    ex = RangeExchange()
+    for step, fe in enumerate((3, FF_NO_EXIT, 1)):
+        blk = ex.begin(5, torch.device("cpu"))
+        assert int(blk.first_exit[0]) == FF_NO_EXIT          # reset every step
+        blk.pos[:5] = torch.arange(5, dtype=torch.int32) + 10 * step
+        blk.counts[:5] = 7
+        blk.first_exit[0] = fe
+        g = ex.finish(blk, _torch_merge)
+        want = [(10 * step + i) if i < fe else FF_POS_DROPPED for i in range(5)]
+        assert g.pos.tolist() == want and g.counts.tolist() == [7] * 5 and g.first_exit == fe
+
+
+def test_numa_binding_is_harmless_without_a_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import os
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before
 
 
 # ---- config 5: whole videos sharded across ranks -------------------------------------------

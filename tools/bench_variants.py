@@ -37,6 +37,29 @@ def time_call(fn, reps: int) -> float:
     return best[len(best) // 2]
 
 
+def bench_head(eng, name, spec, packed, n, reps) -> None:
+    """HEAD-parity detector: streaming kernel (counts) + band kernel (difference -> 3x3 opening
+    -> Gaussian -> Sobel/gradient centre rows, float64) + sequential tracker."""
+    from high_speed_image_processing_b200.head import HeadParams
+    h, w = spec.height, spec.width
+    hp = HeadParams()
+    out = {}
+
+    def run():
+        out["res"] = eng.process_head(packed, n, h, w, 12, hp, float(spec.record_rate), 0.000833333)
+    ms = time_call(run, reps)
+    res = out.pop("res")
+    flags = res.flags.cpu().numpy()
+    track = res.track.cpu().numpy()
+    stop = res.stop.cpu().numpy()
+    print(json.dumps({
+        "config": name, "frames": n, "shape": [h, w], "method": "head (FlameDetector parity)",
+        "whole_path_ms": ms, "whole_path_frames_per_s": n / ms * 1e3,
+        "whole_path_gbs": n * (spec.frame_bytes + 8) / ms / 1e6,
+        "frames_through_band_kernel": int((flags == 1).sum()), "detections": int((track[:, 0] >= 0).sum()),
+        "exit_frame": int(stop[0])}), flush=True)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames-scale", type=float, default=1.0)
@@ -57,10 +80,12 @@ def main() -> None:
         ("C4", "gradient", "float32", False),
         ("C4", "gradient", "float64", False),
         ("C2", "half_maximum", None, True),       # also materialise decoded uint16 frames
+        ("C2", "head", None, False),              # the detector the reference runs at HEAD
+        ("C4", "head", None, False),
     ]
     if args.only:
         want = {tuple(x.split(":")) for x in args.only.split(",")}
-        cases = [c for c in cases if (c[0], str(c[2])) in want and not c[3]]
+        cases = [c for c in cases if ((c[0], str(c[2])) in want or (c[0], c[1]) in want) and not c[3]]
     cache = {}
     for name, method, diff, decoded in cases:
         base = syn.config_spec(name)
@@ -74,8 +99,13 @@ def main() -> None:
             cache[key] = syn.render_packed_torch(spec, eng.device)
         packed = cache[key]
         h, w, fb = spec.height, spec.width, spec.frame_bytes
-        params = DetectionParams(method=method)
+        params = DetectionParams(method=method if method != "head" else "gradient")
         scalars, bg_dev = eng.clip_scalars(packed[:fb], h, w, 12)
+
+        if method == "head":
+            bench_head(eng, name, spec, packed, n, args.reps)
+            torch.cuda.empty_cache()
+            continue
 
         eng._stream_events = []
         out = {}

@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Range-sharded run under torchrun: both block transports of the exchange step against the
+oracle's serial answer, plus the latency of the step itself.
+
+    torchrun --nproc-per-node N tools/check_exchange.py [--out report.json] [--steps 20]
+
+Rank 0 writes a JSON report; every rank exits non-zero on a mismatch.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from high_speed_image_processing_b200 import synthetic as syn  # noqa: E402
+from high_speed_image_processing_b200._cabi import FF_NO_EXIT, FF_POS_DROPPED  # noqa: E402
+from high_speed_image_processing_b200.engine import DetectionParams, FlameFrontEngine  # noqa: E402
+from high_speed_image_processing_b200.sharding import RangeExchange  # noqa: E402
+from oracle import flame_oracle as fo  # noqa: E402
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="")
+    ap.add_argument("--steps", type=int, default=20)
+    args = ap.parse_args()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=device)
+    eng = FlameFrontEngine(local)
+    report = {"world": world, "transports": {}, "ok": True}
+
+    cases = [("threshold", 403, 9.0), ("half_maximum", 400, 12.0), ("gradient", 397, 300.0)]   # last: no exit
+    for transport in ("peer", "gathered"):
+        ex = RangeExchange(engine=eng, transport=transport)
+        lat = []
+        for method, n_frames, t_enter in cases:
+            spec = syn.SyntheticSpec(width=256, height=32, n_frames=n_frames, style="mini" if method != "half_maximum"
+                                     else "nova", t_enter=t_enter, velocity=1.5, seed=77)
+            frames = syn.render_frames(spec)
+            want = fo.process_clip(frames, fo.ClipParams(method=method))
+            exp = want.pos_px.copy()
+            exp[want.first_exit:] = FF_POS_DROPPED
+            exp_fe = want.first_exit if want.first_exit < n_frames else FF_NO_EXIT
+            packed = torch.from_numpy(syn.pack_frames(frames, 12)).to(device)
+            fb = spec.frame_bytes
+            a, b = ex.my_range(n_frames)
+            mine = packed[a * fb:b * fb].clone()
+            halo = packed[(a - 1) * fb:a * fb].clone() if a > 0 else None
+            frame0 = packed[:fb].clone()
+            params = DetectionParams(method=method)
+            for step in range(args.steps):
+                blk = ex.begin(n_frames)
+                eng.process_range(mine, b - a, spec.height, spec.width, 12, params, frame0=frame0, first_frame=a,
+                                  halo=halo, truncate=False, pos_out=blk.pos, counts_out=blk.counts,
+                                  first_exit=blk.first_exit)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g = ex.finish(blk)
+                e1.record()
+                torch.cuda.synchronize()
+                if step >= 3:
+                    lat.append(e0.elapsed_time(e1) * 1e3)
+                ok = (np.array_equal(g.pos.cpu().numpy(), exp) and g.first_exit == exp_fe and
+                      np.array_equal(g.counts.cpu().numpy(), want.nonempty.astype(np.int32)))
+                if not ok:
+                    report["ok"] = False
+                    print(f"[rank {rank}] MISMATCH transport={transport} method={method} step={step}", flush=True)
+            ex.check()
+        assert ex.transport == transport, f"asked for {transport}, got {ex.transport}"
+        lat.sort()
+        report["transports"][transport] = {"finish_us_median": lat[len(lat) // 2] if lat else None,
+                                           "finish_us_min": lat[0] if lat else None, "samples": len(lat)}
+        ex.close()
+
+    flag = torch.tensor([1 if report["ok"] else 0], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    report["ok"] = bool(flag.item())
+    if rank == 0:
+        text = json.dumps(report)
+        print(text, flush=True)
+        if args.out:
+            Path(args.out).write_text(text)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if report["ok"] else 1)
+
+
+if __name__ == "__main__":
+    main()
