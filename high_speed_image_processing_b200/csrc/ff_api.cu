@@ -145,12 +145,12 @@ int ff_device_sm_count(int device, int* sm_count) {
   return FF_OK;
 }
 
-int ff_partial_len(int64_t n_frames, int height, int width, int bits, int64_t* n_elems, int* tiles_per_frame) {
+int ff_partial_len(int64_t n_frames, int height, int width, int bits, int64_t* n_elems, int* partials_per_frame) {
   if (n_frames < 0 || height <= 0 || width <= 0) return FF_ERR_INVALID;
   if (bits != 8 && bits != 12 && bits != 16) return FF_ERR_UNSUPPORTED;
   const Tiling t = choose_tiling((int64_t)height * width);
-  if (n_elems) *n_elems = n_frames * t.tiles_per_frame;
-  if (tiles_per_frame) *tiles_per_frame = t.tiles_per_frame;
+  if (n_elems) *n_elems = n_frames * t.partials_per_frame;
+  if (partials_per_frame) *partials_per_frame = t.partials_per_frame;
   return FF_OK;
 }
 
@@ -264,7 +264,7 @@ int ff_process_host(ff_host_ctx* c, const void* frames_host, const void* halo_ho
   if (chunk_frames < 1) chunk_frames = 1;
   if (chunk_frames > n_frames) chunk_frames = n_frames;
   const Tiling tl = choose_tiling(px);
-  int rc = ctx_reserve(c, halo_slot + chunk_frames * fb, chunk_frames * tl.tiles_per_frame, n_frames);
+  int rc = ctx_reserve(c, halo_slot + chunk_frames * fb, chunk_frames * tl.partials_per_frame, n_frames);
   if (rc != FF_OK) return rc;
 
   cudaStream_t cs = c->copy_stream, ks = c->compute_stream;

@@ -24,11 +24,15 @@ void set_cuda_error(cudaError_t e, const char* where);
 constexpr int kThreads = 256;
 constexpr int kGroupPx = 8;
 
+constexpr int kWarpsPerCta = kThreads / 32;
+
 struct Tiling {
-  int k;                // groups per thread per tile (1 or 4)
-  int tile_px;          // kThreads * k * 8
-  int tiles_per_frame;  // ceil(P / tile_px)
-  bool fast;            // TMA-staged path usable (P % 32 == 0)
+  int k;                   // groups per thread per tile (1 or 4)
+  int tile_px;             // kThreads * k * 8
+  int tiles_per_frame;     // ceil(P / tile_px)
+  int partials_per_frame;  // int32 above-noise counts the streaming kernel emits per frame:
+                           // one per (tile, warp) on the TMA path, one per frame otherwise
+  bool fast;               // TMA-staged path usable (P % 32 == 0)
 };
 
 inline Tiling choose_tiling(int64_t px_per_frame) {
@@ -40,9 +44,11 @@ inline Tiling choose_tiling(int64_t px_per_frame) {
     t.k = 0;
     t.tile_px = 0;
     t.tiles_per_frame = 1;
+    t.partials_per_frame = 1;
     return t;
   }
   t.tiles_per_frame = (int)((px_per_frame + t.tile_px - 1) / t.tile_px);
+  t.partials_per_frame = t.tiles_per_frame * kWarpsPerCta;
   return t;
 }
 
@@ -62,6 +68,9 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

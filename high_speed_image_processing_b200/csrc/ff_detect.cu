@@ -27,7 +27,7 @@ struct DetectParams {
   int height, width;
   const int32_t* bg_dev;
   const int32_t* partial;
-  int tiles_per_frame;
+  int partials_per_frame;
   int64_t min_signal_count;
   int method;
   int use_diff;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kDetectWarps * 32) detect_kernel(const DetectP
 
     // above-noise pixel count (is_empty_frame, scripts/process_videos.py:759-763)
     int cnt = 0;
-    for (int t = lane; t < p.tiles_per_frame; t += 32) cnt += __ldg(p.partial + (int64_t)f * p.tiles_per_frame + t);
+    for (int t = lane; t < p.partials_per_frame; t += 32) cnt += __ldg(p.partial + (int64_t)f * p.partials_per_frame + t);
     cnt = __reduce_add_sync(full, cnt);
     if (lane == 0 && p.count_out != nullptr) p.count_out[f] = cnt;
     const bool empty = (int64_t)cnt < p.min_signal_count;
@@ -261,7 +261,7 @@ int detect_impl(const void* frames, const void* halo, int64_t n_frames, int64_t 
   p.width = width;
   p.bg_dev = bg_dev;
   p.partial = partial;
-  p.tiles_per_frame = choose_tiling(px).tiles_per_frame;
+  p.partials_per_frame = choose_tiling(px).partials_per_frame;
   p.min_signal_count = min_signal_count;
   p.method = method;
   p.use_diff = use_frame_diff ? 1 : 0;

@@ -32,7 +32,7 @@ struct HeadBandParams {
   int height, width;
   const int32_t* bg_dev;
   const int32_t* partial;
-  int tiles_per_frame;
+  int partials_per_frame;
   int64_t min_signal_count;
   int diff_thr;
   const uint8_t* skip;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_band_kernel(const HeadBandP
   __syncthreads();
   if (!skipped) {
     int cnt = 0;
-    for (int t = tid; t < p.tiles_per_frame; t += kHeadThreads) cnt += __ldg(p.partial + (int64_t)f * p.tiles_per_frame + t);
+    for (int t = tid; t < p.partials_per_frame; t += kHeadThreads) cnt += __ldg(p.partial + (int64_t)f * p.partials_per_frame + t);
     cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
     if ((tid & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
   }
@@ -200,7 +200,158 @@ struct HeadTrackParams {
   int32_t* stop;                   // [3]: exit frame (global) or FF_NO_EXIT, last frame, last pos
 };
 
-__global__ void __launch_bounds__(kHeadThreads) head_track_kernel(const HeadTrackParams p) {
+// The sequential walk is latency-bound: every frame's search window depends on the previous
+// frame's answer, so the work per frame is a dependent chain of ~100-element scans.  This kernel
+// takes the memory latency out of the chain: a producer warp finds the frames that reached the
+// detector (flags != 0) and streams their two float64 lines (16*W bytes, contiguous) into a
+// shared-memory ring with TMA bulk copies, several frames ahead; a single consumer warp walks
+// the ring in frame order and scans its window out of shared memory with warp shuffles.
+// Same comparisons, same tie-breaks as the generic kernel below (first minimum of the gradient,
+// rightmost |Sobel| above the fraction of the window's peak).
+constexpr int kTrackThreads = 64;          // warp 0: tracker, warp 1: producer
+constexpr int kTrackMaxStages = 8;
+
+struct TrackMeta { int f; int fl; };
+
+__global__ void __launch_bounds__(kTrackThreads) head_track_kernel(const HeadTrackParams p, int n_stages) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int W = p.width;
+  const size_t stage_bytes = (size_t)16 * W;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)n_stages * stage_bytes);
+  uint64_t* empty = full + kTrackMaxStages;
+  TrackMeta* meta = reinterpret_cast<TrackMeta*>(empty + kTrackMaxStages);
+  volatile int* s_stop = reinterpret_cast<volatile int*>(meta + kTrackMaxStages);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned fullmask = 0xFFFFFFFFu;
+
+  if (tid == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    *s_stop = 0;
+    p.stop[0] = FF_NO_EXIT;
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == 1) {
+    // ---- producer: scan the flags 512 frames at a time, push active frames in order -------------
+    int it = 0;
+    auto push = [&](int f, int fl) {      // lane 0 only
+      const int s = it % n_stages;
+      mbar_wait(&empty[s], ((it / n_stages) & 1) ^ 1);
+      meta[s].f = f;
+      meta[s].fl = fl;
+      if (fl == 1) {
+        mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
+        bulk_g2s(smem + (size_t)s * stage_bytes, p.lines + (int64_t)f * 2 * W, (uint32_t)stage_bytes, &full[s],
+                 policy_evict_first());
+      } else {
+        mbar_arrive(&full[s]);
+      }
+      ++it;
+    };
+    bool stopped = false;
+    for (int base = 0; base < p.n_frames && !stopped; base += 32 * 16) {
+      // lane l inspects frames [base + 16 l, base + 16 l + 16): bit j = flag != 0, bit 16+j = flag == 1
+      uint32_t bits = 0;
+      const int f0 = base + lane * 16;
+      for (int j = 0; j < 16; ++j) {
+        const int f = f0 + j;
+        const int fl = f < p.n_frames ? (int)p.flags[f] : 0;
+        if (fl != 0) bits |= 1u << j;
+        if (fl == 1) bits |= 1u << (16 + j);
+      }
+      for (int l = 0; l < 32 && !stopped; ++l) {
+        uint32_t b = __shfl_sync(fullmask, bits, l);
+        if (lane == 0) {
+          while (b & 0xFFFFu) {
+            const int j = __ffs((int)(b & 0xFFFFu)) - 1;
+            b &= ~(1u << j);
+            if (*s_stop) { stopped = true; break; }
+            push(base + l * 16 + j, ((b >> (16 + j)) & 1u) ? 1 : 2);
+          }
+        }
+        stopped = __shfl_sync(fullmask, (int)stopped, 0) != 0;
+      }
+    }
+    if (lane == 0) push(-1, 0);           // sentinel: no more frames
+    return;
+  }
+
+  // ---- consumer: the reference's sequential search (:317-348, :420-465, :1488-1494) -----------------
+  int last_f = p.last_frame_in, last_p = p.last_pos_in;
+  bool stopped = false;
+  for (int it = 0;; ++it) {
+    const int s = it % n_stages;
+    mbar_wait(&full[s], (it / n_stages) & 1);
+    const int f = meta[s].f;
+    const int fl = meta[s].fl;
+    if (f < 0) break;
+    if (!stopped) {
+      const int gf = (int)(p.first_frame + f);
+      int s0, s1;
+      if (last_p < 0) {
+        s0 = p.edge_margin;
+        s1 = W - p.edge_margin;
+      } else {
+        s0 = last_p;
+        s1 = min(W - p.edge_margin, last_p + p.max_disp * max(1, gf - last_f) + p.window);
+      }
+      int pos_a = -1, pos_b = -1;
+      if (fl == 1 && s1 > s0 && s0 >= 0) {     // non-empty search slice (:424)
+        s1 = min(s1, W);
+        const double* sob = reinterpret_cast<const double*>(smem + (size_t)s * stage_bytes);
+        const double* grd = sob + W;
+        double mn = 1.0 / 0.0, amax = -1.0;
+        int arg = INT_MAX;
+        for (int x = s0 + lane; x < s1; x += 32) {
+          const double g = grd[x];
+          if (g < mn) { mn = g; arg = x; }
+          amax = fmax(amax, fabs(sob[x]));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double om = __shfl_xor_sync(fullmask, mn, o);
+          const int oa = __shfl_xor_sync(fullmask, arg, o);
+          if (om < mn || (om == mn && oa < arg)) { mn = om; arg = oa; }
+          amax = fmax(amax, __shfl_xor_sync(fullmask, amax, o));
+        }
+        if (mn < -p.min_strength) pos_a = arg;                                  // :427-430
+        if (amax > p.min_strength) {                                            // :434-440
+          const double thr = __dmul_rn(amax, p.sobel_frac);
+          int right = -1;
+          for (int x = s0 + lane; x < s1; x += 32)
+            if (fabs(sob[x]) > thr) right = x;
+          pos_b = __reduce_max_sync(fullmask, right);
+        }
+      }
+      const int final_pos = max(pos_a, pos_b);                                  // :452-465
+      if (lane == 0) {
+        int32_t* o = p.out + (int64_t)f * 5;
+        o[0] = final_pos; o[1] = pos_a; o[2] = pos_b; o[3] = s0; o[4] = s1;
+      }
+      if (final_pos >= 0) { last_f = gf; last_p = final_pos; }
+      if (final_pos >= 0 && final_pos >= W - p.exit_margin) {                   // :1488-1494
+        if (lane == 0) {
+          p.stop[0] = gf;
+          *s_stop = 1;
+        }
+        stopped = true;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+  if (lane == 0) {
+    p.stop[1] = last_f;
+    p.stop[2] = last_p;
+  }
+}
+
+// Any width (rows too long for a useful shared-memory ring): the lines are read from global memory.
+__global__ void __launch_bounds__(kHeadThreads) head_track_generic_kernel(const HeadTrackParams p) {
   __shared__ double s_min[kHeadThreads / 32];
   __shared__ int s_arg[kHeadThreads / 32];
   __shared__ double s_amax[kHeadThreads / 32];
@@ -311,7 +462,7 @@ int head_lines_impl(const void* frames, const void* halo, int64_t n_frames, int 
   p.width = width;
   p.bg_dev = bg_dev;
   p.partial = partial;
-  p.tiles_per_frame = choose_tiling(px).tiles_per_frame;
+  p.partials_per_frame = choose_tiling(px).partials_per_frame;
   p.min_signal_count = min_signal_count;
   p.diff_thr = diff_thr;
   p.skip = skip;
@@ -334,7 +485,7 @@ int head_lines_impl(const void* frames, const void* halo, int64_t n_frames, int 
       q.n_frames = nf;
       q.frames = p.frames + f0 * p.frame_bytes;
       q.halo = f0 == 0 ? p.halo : p.frames + (f0 - 1) * p.frame_bytes;
-      q.partial = p.partial + f0 * p.tiles_per_frame;
+      q.partial = p.partial + f0 * p.partials_per_frame;
       q.skip = p.skip ? p.skip + f0 : nullptr;
       q.lines = p.lines + f0 * 2 * width;
       q.flags = p.flags + f0;
@@ -373,7 +524,23 @@ int head_track_impl(const double* lines, const uint8_t* flags, int64_t n_frames,
   p.last_pos_in = last_pos_in;
   p.out = out;
   p.stop = stop;
-  head_track_kernel<<<1, kHeadThreads, 0, st>>>(p);
+  // ring of 16*W-byte stages: as many as fit (2..8); very wide rows take the generic kernel
+  const size_t stage_bytes = (size_t)16 * width;
+  const size_t fixed = (size_t)kTrackMaxStages * (8 + 8 + sizeof(TrackMeta)) + 16;
+  int stages = (int)((200 * 1024 - fixed) / stage_bytes);
+  if (stages > kTrackMaxStages) stages = kTrackMaxStages;
+  if (stages < 2 || (reinterpret_cast<uintptr_t>(lines) & 15u) != 0) {
+    head_track_generic_kernel<<<1, kHeadThreads, 0, st>>>(p);
+    FF_CUDA_TRY(cudaGetLastError());
+    return FF_OK;
+  }
+  const size_t smem = (size_t)stages * stage_bytes + fixed;
+  static bool configured = false;
+  if (!configured) {
+    FF_CUDA_TRY(cudaFuncSetAttribute(head_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  head_track_kernel<<<1, kTrackThreads, smem, st>>>(p, stages);
   FF_CUDA_TRY(cudaGetLastError());
   return FF_OK;
 }

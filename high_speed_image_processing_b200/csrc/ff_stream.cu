@@ -11,6 +11,8 @@
 //
 // Everything is integer arithmetic on values the reference holds as integer-valued float64
 // (scripts/process_videos.py:670-674, :397-399, :759), so results are bit-exact.
+#include <cstdlib>
+
 #include "ff_common.cuh"
 
 namespace ff {
@@ -114,7 +116,6 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const StreamParams p) 
 
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  int* warp_cnt = reinterpret_cast<int*>(full + kStages);  // [2][8]
 
   const int tid = threadIdx.x;
 
@@ -319,20 +320,157 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const StreamParams p) 
     if (kSimd) cnt += (int)(acc2 & 0xFFFFu) + (int)(acc2 >> 16);
     if (DIFF != FF_DIFF_NONE && !skipped) have_prev = true;
 
-    if (COUNT && !is_halo) {
+    if (COUNT && !is_halo) {   // one partial count per (frame, tile, warp); ff_detect sums them
       cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-      if ((tid & 31) == 0) warp_cnt[(git & 1) * 8 + (tid >> 5)] = cnt;
+      if ((tid & 31) == 0)
+        p.partial[((int64_t)f * p.tiles_per_frame + tile) * kWarpsPerCta + (tid >> 5)] = cnt;
     }
-    __syncthreads();  // stage s drained by every thread; warp_cnt visible
-    if (COUNT && !is_halo && tid == 0) {
-      const int* wc = warp_cnt + (git & 1) * 8;
-      int tot = 0;
-#pragma unroll
-      for (int w = 0; w < kThreads / 32; ++w) tot += wc[w];
-      p.partial[(int64_t)f * p.tiles_per_frame + tile] = tot;
-    }
+    __syncthreads();  // stage s drained by every thread
   }
   }  // segments
+}
+
+// ---- count-only kernel for packed 12-bit (the headline configuration) --------------------------
+// No output but the above-noise counts, so the pixels are never extracted.  Compared with the
+// general template: a dedicated producer warp feeds a full/empty mbarrier ring (consumer warps
+// never meet at a CTA-wide barrier and can run up to kCountStages items apart); every thread
+// owns 32 consecutive pixels = 48 bytes = three conflict-free LDS.128 (stride 48 B: each
+// quarter-warp covers all 32 banks); and the compare runs on 16x2 SIMD lanes (DPX):
+//   A lanes = (b0<<8 | b1) = hi<<4 | nibble   hi > c  <=>  A > (c<<4 | 15)   (junk below the field
+//                                                                              is dominated)
+//   B lanes = (b1<<8 | b2) & 0x0FFF = lo       lo > c  directly
+// 4 PRMT + 2 LOP3 + 6 DPX + 2 IADD3 per 8 pixels (the carry-chain form needs 20).
+constexpr int kCountTileBytes = 4 * kThreads * 12;        // 1024 groups = 8192 px
+constexpr int kCountThreads = kThreads + 32;              // 8 consumer warps + 1 producer warp
+constexpr int kCountCtasPerSm = 2;
+
+__device__ __forceinline__ uint32_t count12x8_simd(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t kA2,
+                                                   uint32_t nkA2, uint32_t nc2) {
+  const uint32_t one2 = 0x00010001u;
+  const uint32_t a0 = __byte_perm(w0, w1, 0x3401);                 // b1 b0 | b4 b3   (LSB first)
+  const uint32_t a1 = __byte_perm(w1, w2, 0x5623);                 // b7 b6 | b10 b9
+  const uint32_t b0 = __byte_perm(w0, w1, 0x4512) & 0x0FFF0FFFu;   // b2 b1 | b5 b4
+  const uint32_t b1 = __byte_perm(w1, w2, 0x6734) & 0x0FFF0FFFu;   // b8 b7 | b11 b10
+  // [a > kA] = min(max(a, kA) - kA, 1) on unsigned lanes;  [b > c] = relu(min(b - c, 1)) on signed lanes
+  const uint32_t fa0 = __viaddmin_u16x2(__vimax3_u16x2(a0, kA2, kA2), nkA2, one2);
+  const uint32_t fa1 = __viaddmin_u16x2(__vimax3_u16x2(a1, kA2, kA2), nkA2, one2);
+  const uint32_t fb0 = __viaddmin_s16x2_relu(b0, nc2, one2);
+  const uint32_t fb1 = __viaddmin_s16x2_relu(b1, nc2, one2);
+  return (fa0 + fa1) + (fb0 + fb1);
+}
+
+template <int kCountStages>
+__global__ void __launch_bounds__(kCountThreads) count12_kernel(const StreamParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kCountStages * kCountTileBytes);
+  uint64_t* empty = full + kCountStages;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kCountStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kWarpsPerCta);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int64_t total_work = (int64_t)p.tiles_per_frame * p.n_frames;
+  const int64_t work0 = (int64_t)blockIdx.x * p.items_per_cta;
+  const int n_items = (int)(min(work0 + p.items_per_cta, total_work) - work0);
+  if (n_items <= 0) return;
+  // Item order is frame-major (tile fastest): nothing is carried from frame to frame here, so
+  // every CTA reads ONE contiguous span of the clip (measured +2.5 % over the tile-major order
+  // the difference kernels need).
+  int f = (int)(work0 / p.tiles_per_frame);
+  int tile = (int)(work0 - (int64_t)f * p.tiles_per_frame);
+  auto advance = [&]() {
+    if (++tile == p.tiles_per_frame) { tile = 0; ++f; }
+  };
+  const int64_t groups_per_frame = p.px_per_frame / kGroupPx;
+
+  if (warp == kWarpsPerCta) {            // ---- producer: one elected lane drives the TMA ring
+    if ((tid & 31) == 0) {
+      const uint64_t policy = policy_evict_first();
+      for (int it = 0; it < n_items; ++it) {
+        const int s = it % kCountStages;
+        mbar_wait(&empty[s], ((it / kCountStages) & 1) ^ 1);   // first pass: fresh barriers pass at once
+        const int64_t g0 = (int64_t)tile * (4 * kThreads);
+        const uint32_t bytes = (uint32_t)min((int64_t)(4 * kThreads), groups_per_frame - g0) * 12u;
+        mbar_arrive_expect_tx(&full[s], bytes);
+        bulk_g2s(smem + s * kCountTileBytes, p.frames + (int64_t)f * p.frame_bytes + (int64_t)tile * kCountTileBytes,
+                 bytes, &full[s], policy);
+        advance();
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ---------------------------------------------------------------------------------
+  const int bg = __ldg(p.bg_dev);
+  const int ethr = p.empty_thr >= 0 ? p.empty_thr : max(10, bg >> 1);
+  const uint32_t c = (uint32_t)min(bg + ethr, 4095);       // 12-bit pixels never exceed 4095
+  const uint32_t kA = (c << 4) | 15u;
+  const uint32_t kA2 = kA * 0x00010001u;
+  const uint32_t nkA2 = ((0x10000u - kA) & 0xFFFFu) * 0x00010001u;
+  const uint32_t nc2 = ((0x10000u - c) & 0xFFFFu) * 0x00010001u;
+  const int my_group = tid * 4;
+
+  for (int it = 0; it < n_items; ++it) {
+    const int s = it % kCountStages;
+    mbar_wait(&full[s], (it / kCountStages) & 1);
+    const int tile_groups = (int)min((int64_t)(4 * kThreads), groups_per_frame - (int64_t)tile * (4 * kThreads));
+    uint32_t acc = 0;
+    if (my_group < tile_groups) {        // groups per frame are a multiple of 4: all four or none
+      const uint4* q = reinterpret_cast<const uint4*>(smem + s * kCountTileBytes + tid * 48);
+      const uint4 q0 = q[0], q1 = q[1], q2 = q[2];
+      acc = count12x8_simd(q0.x, q0.y, q0.z, kA2, nkA2, nc2) + count12x8_simd(q0.w, q1.x, q1.y, kA2, nkA2, nc2) +
+            count12x8_simd(q1.z, q1.w, q2.x, kA2, nkA2, nc2) + count12x8_simd(q2.y, q2.z, q2.w, kA2, nkA2, nc2);
+    }
+    int cnt = (int)(acc & 0xFFFFu) + (int)(acc >> 16);
+    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);      // also orders every lane's smem reads before the release
+    if ((tid & 31) == 0) {
+      mbar_arrive(&empty[s]);
+      p.partial[((int64_t)f * p.tiles_per_frame + tile) * kWarpsPerCta + warp] = cnt;
+    }
+    advance();
+  }
+}
+
+int sm_count_cached();
+
+template <int kCountStages>
+int launch_count12(StreamParams p, cudaStream_t st) {
+  constexpr int kSmem = kCountStages * kCountTileBytes + 2 * kCountStages * 8;
+  static bool configured[64] = {false};
+  static int ctas_per_sm[64] = {0};
+  int dev = 0;
+  FF_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return FF_ERR_INVALID;
+  auto kern = count12_kernel<kCountStages>;
+  if (!configured[dev]) {
+    FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    int occ = 0;
+    FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCountThreads, kSmem));
+    // Bytes in flight per SM decide the achieved bandwidth, and MORE is not better: measured on
+    // B200 (C2/C3, GB/s) 24 KB 5770, 48 KB 6740, 72 KB 7030-7160, 120 KB 6620, 144 KB 6500,
+    // 168 KB 6320 (profiles/r01_count12_sweep.txt).  2 CTAs x (4-1) stages x 12 KB = 72 KB.
+    int cap = kCountCtasPerSm;
+    if (const char* e = getenv("FF_COUNT12_CTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;   // tuning knob
+    if (occ > cap) occ = cap;
+    ctas_per_sm[dev] = occ > 0 ? occ : 1;
+    configured[dev] = true;
+  }
+  const int64_t wave = (int64_t)sm_count_cached() * ctas_per_sm[dev];
+  const int64_t total_work = (int64_t)p.tiles_per_frame * p.n_frames;
+  p.items_per_cta = (total_work + wave - 1) / wave;
+  if (p.items_per_cta < 1) p.items_per_cta = 1;
+  const int64_t grid = (total_work + p.items_per_cta - 1) / p.items_per_cta;
+  kern<<<(unsigned)grid, kCountThreads, kSmem, st>>>(p);
+  FF_CUDA_TRY(cudaGetLastError());
+  return FF_OK;
 }
 
 // Shapes the TMA path cannot take (P % 32 != 0): one thread per pixel pair, plain loads,
@@ -411,7 +549,7 @@ template <int BITS, bool COUNT, int DIFF, bool DECODED, int K>
 int launch_stream(StreamParams p, cudaStream_t st) {
   auto kern = stream_kernel<BITS, COUNT, DIFF, DECODED, K>;
   constexpr int kStageBytes = K * kThreads * BITS;
-  constexpr int kSmem = kStages * kStageBytes + kStages * 8 + 2 * 8 * 4;
+  constexpr int kSmem = kStages * kStageBytes + kStages * 8;
   static bool configured[64] = {false};
   static int ctas_per_sm[64] = {0};
   int dev = 0;
@@ -421,6 +559,7 @@ int launch_stream(StreamParams p, cudaStream_t st) {
     FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     int occ = 0;
     FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, kSmem));
+    if (const char* cap = getenv("FF_STREAM_CTAS")) occ = occ > atoi(cap) ? atoi(cap) : occ;
     ctas_per_sm[dev] = occ > 0 ? occ : 1;
     configured[dev] = true;
   }
@@ -519,6 +658,16 @@ int stream_frames_impl(const void* frames, const void* halo, int64_t n_frames, i
   const bool aligned = ((reinterpret_cast<uintptr_t>(frames) | reinterpret_cast<uintptr_t>(halo) |
                          reinterpret_cast<uintptr_t>(diff_out) | reinterpret_cast<uintptr_t>(decoded_out)) & 15u) == 0;
   if (t.fast && aligned) {
+    if (bits == 12 && diff_dtype == FF_DIFF_NONE && decoded_out == nullptr && t.k == 4) {
+      static const int stages = getenv("FF_COUNT12_STAGES") ? atoi(getenv("FF_COUNT12_STAGES")) : 4;   // tuning knob
+      switch (stages) {
+        case 2: return launch_count12<2>(p, st);
+        case 3: return launch_count12<3>(p, st);
+        case 6: return launch_count12<6>(p, st);
+        case 8: return launch_count12<8>(p, st);
+        default: return launch_count12<4>(p, st);
+      }
+    }
     switch (bits) {
       case 8: return dispatch_stream<8>(p, t.k, diff_dtype, decoded_out != nullptr, st);
       case 12: return dispatch_stream<12>(p, t.k, diff_dtype, decoded_out != nullptr, st);

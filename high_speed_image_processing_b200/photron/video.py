@@ -140,6 +140,13 @@ class PhotonVideo:
             raise IndexError(f"frame range [{start}, {stop}) out of range [0, {self._len}]")
         return self._require_open().raw_frames(start, stop)
 
+    def pin_memory(self) -> "PhotonVideo":
+        """Stage the recording's raw bytes in page-locked host memory (B200 extension; no
+        counterpart in the reference): later ``process_video`` calls then stream it with
+        asynchronous PCIe copies."""
+        self._require_open().pin_memory()
+        return self
+
     def _require_open(self) -> "_mraw.FrameStore":
         if self._images is None:
             raise ValueError("video is closed")

@@ -63,11 +63,12 @@ int         ff_device_count(int* count);
 int         ff_device_sm_count(int device, int* sm_count);
 
 /* ---- scratch sizing ---------------------------------------------------------------
- * ff_stream_frames writes per-(frame,tile) counts of above-noise pixels into a caller-owned
- * int32 scratch array; ff_detect sums them.  ff_partial_len returns its length in int32
- * elements and the tile count per frame for a given frame shape.                       */
+ * ff_stream_frames writes partial counts of above-noise pixels (one per frame, tile and warp
+ * of the streaming kernel) into a caller-owned int32 scratch array; ff_detect sums them.
+ * ff_partial_len returns its length in int32 elements and the number of partial counts per
+ * frame for a given frame shape.                                                        */
 int ff_partial_len(int64_t n_frames, int height, int width, int bits,
-                   int64_t* n_elems, int* tiles_per_frame);
+                   int64_t* n_elems, int* partials_per_frame);
 
 /* ---- stage 1: decode ------------------------------------------------------------------
  * Replaces pyMRAW.load_video's 12-bit unpack (call site src/photron/video.py:332) and the

@@ -34,7 +34,7 @@ def test_load_and_version():
     n = ctypes.c_int64(0)
     tiles = ctypes.c_int(0)
     assert lib.ff_partial_len(20000, 128, 1024, 12, ctypes.byref(n), ctypes.byref(tiles)) == 0
-    assert tiles.value == 16 and n.value == 20000 * 16
+    assert tiles.value == 16 * 8 and n.value == 20000 * 16 * 8      # 16 tiles x 8 warps
     assert lib.ff_partial_len(10, 5, 7, 12, ctypes.byref(n), ctypes.byref(tiles)) == 0 and tiles.value == 1
     assert lib.ff_partial_len(10, 5, 7, 10, ctypes.byref(n), ctypes.byref(tiles)) == _cabi.FF_ERR_UNSUPPORTED
 

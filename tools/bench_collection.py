@@ -1,0 +1,169 @@
+#!/usr/bin/env python
+"""BASELINE config C5: a VideoCollection of 64 synthetic Nova+Mini recordings, mixed detection
+methods and calibrations, sharded BY VIDEO across the GPUs (src/photron/parallel.py:173-208).
+
+    python tools/bench_collection.py [--clips 64] [--frames 2000] [--dir /tmp/ff_c5]
+    torchrun --nproc-per-node N tools/bench_collection.py ...
+
+Clips alternate C2 (1024x128, Nova-style) and C3 (1024x256, Mini-style) shapes, methods cycle
+half_maximum / threshold / gradient, every clip has its own FileCalibration rule.  The files are
+real .cihx/.mraw pairs on disk opened through ``open_collection``; each rank stages ITS videos in
+pinned host memory (``video.pin_memory()``, untimed I/O), then the timed region runs
+``process_collection``: per video frame 0 -> scalars, chunked H2D streaming + kernels, result
+rows on the host; one all_gather_object of the per-video results at the end.  A sample of clips
+is checked against the oracle.  Prints one JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import sys
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from high_speed_image_processing_b200 import synthetic as syn  # noqa: E402
+from high_speed_image_processing_b200.engine import FlameFrontEngine  # noqa: E402
+from high_speed_image_processing_b200.photron import open_collection  # noqa: E402
+from high_speed_image_processing_b200.process_videos import (FileCalibration, VideoSourceConfig,  # noqa: E402
+                                                             process_collection)
+from high_speed_image_processing_b200.sharding import RangeExchange, assign_videos, bind_to_gpu_numa_node  # noqa: E402
+
+METHODS = ("half_maximum", "threshold", "gradient")
+
+
+def clip_spec(i: int, frames: int) -> syn.SyntheticSpec:
+    base = syn.config_spec("C2" if i % 2 == 0 else "C3", n_frames=frames, seed=5000 + i)
+    # the front enters in the last ~55 % of the clip and leaves before the end on most clips
+    return syn.SyntheticSpec(**{**base.__dict__, "t_enter": float(max(2, frames - 1100 - 37 * (i % 5)))})
+
+
+def clip_config(i: int) -> VideoSourceConfig:
+    cfg = VideoSourceConfig(name=f"clip{i:02d}")
+    cfg.detection_method = METHODS[i % 3]
+    cfg.file_calibrations = [FileCalibration(calibration=0.0008 + 1e-6 * i, position_offset=0.05 * i,
+                                             files=[f"run-{i:02d}-"])]
+    return cfg
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--clips", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=2000)
+    ap.add_argument("--dir", default="/tmp/ff_c5")
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--check", type=int, default=3, help="clips per rank verified against the oracle")
+    ap.add_argument("--keep", action="store_true")
+    args = ap.parse_args()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    bind_to_gpu_numa_node(local)
+    eng = FlameFrontEngine(local)
+    exchange = RangeExchange(engine=eng)
+
+    # ---- write the recordings (each rank writes the ones it will process; untimed) -------------
+    vdir = Path(args.dir)
+    specs = [clip_spec(i, args.frames) for i in range(args.clips)]
+    weights = [s.n_frames * s.height * s.width for s in specs]
+    mine = assign_videos(args.clips, rank, world, weights)
+    t0 = time.perf_counter()
+    vdir.mkdir(parents=True, exist_ok=True)
+    for i in mine:
+        spec = specs[i]
+        packed = syn.render_packed_torch(spec, device).cpu().numpy()
+        (vdir / f"run-{i:02d}-.mraw").write_bytes(packed.tobytes())
+        (vdir / f"run-{i:02d}-.cihx").write_bytes(syn.cihx_bytes(spec, spec.n_frames))
+        del packed
+    write_s = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+
+    coll = open_collection(str(vdir))
+    assert len(coll) == args.clips, f"expected {args.clips} recordings, found {len(coll)}"
+    cfgs = [clip_config(i) for i in range(args.clips)]
+    t0 = time.perf_counter()
+    for i in mine:
+        coll[i].pin_memory()
+    stage_s = time.perf_counter() - t0
+    my_bytes = sum(coll[i].frame_store.nbytes_raw for i in mine)
+    total_frames = sum(len(v) for v in coll)
+    total_bytes = sum(v.frame_store.nbytes_raw for v in coll)
+
+    def run():
+        return process_collection(coll, cfgs, engine=eng, exchange=exchange if world > 1 else None)
+
+    results = run()                                   # warm-up (allocations, contexts)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    times = []
+    for _ in range(args.reps):
+        t0 = time.perf_counter()
+        results = run()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        times.append(dt)
+    sec = min(times)
+
+    # ---- oracle check on a sample of this rank's clips -------------------------------------------
+    from oracle import flame_oracle as fo
+    checked = 0
+    for i in mine[:args.check]:
+        spec, cfg, res = specs[i], cfgs[i], results[i]
+        n_chk = min(spec.n_frames, 260)             # the oracle is slow: compare the flame's first frames
+        a = max(1, int(spec.t_enter) - 20)
+        raw = np.asarray(coll[i].raw_frames(a - 1, a + n_chk))
+        frames = fo.frames_from_bytes(raw, n_chk + 1, spec.height, spec.width, 12)
+        frame0 = fo.frames_from_bytes(np.asarray(coll[i].raw_frames(0, 1)), 1, spec.height, spec.width, 12)[0]
+        want = fo.process_clip(frames[1:], fo.ClipParams(method=cfg.detection_method), frame0=frame0, first_index=a,
+                               prior_frame=frames[0])
+        hi = a + n_chk if res.first_exit is None else min(a + n_chk, res.first_exit)
+        assert np.array_equal(res.pos_px[a:hi], want.pos_px[:hi - a]), f"clip {i}: positions differ from the oracle"
+        cal, off = cfg.get_calibration_for_file(f"run-{i:02d}-.cihx")
+        for frame_idx, t_s, px, p_m, _ in res.rows[:50]:
+            assert p_m == px * cal + off
+        checked += 1
+
+    if rank == 0:
+        n_rows = sum(len(r.rows) for r in results.values())
+        exits = sum(1 for r in results.values() if r.first_exit is not None)
+        print(json.dumps({
+            "config": "C5", "clips": args.clips, "frames_per_clip": args.frames, "n_gpus": world,
+            "total_frames": total_frames, "total_gb": total_bytes / 1e9,
+            "sharding": "whole videos, size-balanced (assign_videos)", "seconds": sec,
+            "frames_per_s": total_frames / sec, "gbs_aggregate": total_bytes / sec / 1e9,
+            "gbs_per_gpu": total_bytes / sec / 1e9 / world, "ms_per_video": sec / (args.clips / world) * 1e3,
+            "all_times_s": times, "detections": n_rows, "clips_with_exit": exits,
+            "oracle_checked_clips_rank0": checked, "untimed": {"write_files_s": write_s, "pin_stage_s": stage_s,
+                                                                "rank0_bytes": my_bytes}}), flush=True)
+    coll.close_all()
+    if world > 1:
+        dist.barrier()
+    if rank == 0 and not args.keep:
+        shutil.rmtree(vdir, ignore_errors=True)
+    exchange.close()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
