@@ -213,6 +213,12 @@ constexpr int kTrackMaxStages = 8;
 
 struct TrackMeta { int f; int fl; };
 
+// Monotone map from the bits of a non-NaN double to an unsigned integer (-0.0 == +0.0).
+__device__ __forceinline__ unsigned long long order_key(unsigned long long bits) {
+  if (bits == 0x8000000000000000ull) bits = 0ull;
+  return (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
+}
+
 __global__ void __launch_bounds__(kTrackThreads) head_track_kernel(const HeadTrackParams p, int n_stages) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int W = p.width;
@@ -302,28 +308,38 @@ __global__ void __launch_bounds__(kTrackThreads) head_track_kernel(const HeadTra
       int pos_a = -1, pos_b = -1;
       if (fl == 1 && s1 > s0 && s0 >= 0) {     // non-empty search slice (:424)
         s1 = min(s1, W);
-        const double* sob = reinterpret_cast<const double*>(smem + (size_t)s * stage_bytes);
-        const double* grd = sob + W;
-        double mn = 1.0 / 0.0, amax = -1.0;
+        // The float64 comparisons of the reference run here on order-preserving integer keys
+        // (FP64 compare/min chains cost ~10x the latency of integer ones on this part, and this
+        // loop is a serial chain over the frames): key(x) is monotone in x for every non-NaN
+        // double, -0.0 is folded onto +0.0 so ties stay ties.
+        const unsigned long long* sob = reinterpret_cast<const unsigned long long*>(smem + (size_t)s * stage_bytes);
+        const unsigned long long* grd = sob + W;
+        unsigned long long mn = ~0ull, amax = 0ull;    // key(+inf) < ~0;  |x| keys start at 0
         int arg = INT_MAX;
         for (int x = s0 + lane; x < s1; x += 32) {
-          const double g = grd[x];
+          const unsigned long long g = order_key(grd[x]);
           if (g < mn) { mn = g; arg = x; }
-          amax = fmax(amax, fabs(sob[x]));
+          const unsigned long long a = sob[x] & 0x7FFFFFFFFFFFFFFFull;      // |sobel| as an ordered integer
+          amax = a > amax ? a : amax;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double om = __shfl_xor_sync(fullmask, mn, o);
-          const int oa = __shfl_xor_sync(fullmask, arg, o);
-          if (om < mn || (om == mn && oa < arg)) { mn = om; arg = oa; }
-          amax = fmax(amax, __shfl_xor_sync(fullmask, amax, o));
-        }
-        if (mn < -p.min_strength) pos_a = arg;                                  // :427-430
-        if (amax > p.min_strength) {                                            // :434-440
-          const double thr = __dmul_rn(amax, p.sobel_frac);
+        const bool any = s1 - s0 > 0;
+        // first minimum: smallest key, then smallest index (np.argmin)
+        const unsigned mn_hi = __reduce_min_sync(fullmask, (unsigned)(mn >> 32));
+        const unsigned lo_c = (unsigned)(mn >> 32) == mn_hi ? (unsigned)mn : 0xFFFFFFFFu;
+        const unsigned mn_lo = __reduce_min_sync(fullmask, lo_c);
+        const bool mine = (unsigned)(mn >> 32) == mn_hi && (unsigned)mn == mn_lo;
+        arg = (int)__reduce_min_sync(fullmask, mine ? (unsigned)arg : 0x7FFFFFFFu);
+        const unsigned long long mn_key = ((unsigned long long)mn_hi << 32) | mn_lo;
+        const unsigned am_hi = __reduce_max_sync(fullmask, (unsigned)(amax >> 32));
+        const unsigned am_lo = __reduce_max_sync(fullmask, (unsigned)(amax >> 32) == am_hi ? (unsigned)amax : 0u);
+        const unsigned long long am_bits = ((unsigned long long)am_hi << 32) | am_lo;
+        if (any && mn_key < order_key(__double_as_longlong(-p.min_strength))) pos_a = arg;   // :427-430
+        const double amax_d = __longlong_as_double((long long)am_bits);
+        if (any && amax_d > p.min_strength) {                                                 // :434-440
+          const unsigned long long thr = (unsigned long long)__double_as_longlong(__dmul_rn(amax_d, p.sobel_frac));
           int right = -1;
           for (int x = s0 + lane; x < s1; x += 32)
-            if (fabs(sob[x]) > thr) right = x;
+            if ((sob[x] & 0x7FFFFFFFFFFFFFFFull) > thr) right = x;
           pos_b = __reduce_max_sync(fullmask, right);
         }
       }

@@ -203,7 +203,10 @@ def process_video(video: PhotonVideo, config: VideoSourceConfig, calibration: fl
     nbytes = (b - a) * video.frame_store.frame_bytes
     multi = exchange is not None and exchange.size > 1
     if residency == "auto":
-        residency = "device" if (nbytes <= device_budget_bytes or multi) else "host"
+        # pinned recordings stream best chunk by chunk (copies overlap the kernels, nothing is copied
+        # past the exit frame); pageable ones go up in one staged copy when they fit
+        pinned = getattr(video.frame_store, "is_pinned", False)
+        residency = "device" if ((nbytes <= device_budget_bytes and not pinned) or multi) else "host"
     if residency not in ("device", "host"):
         raise ValueError("residency must be 'auto', 'device' or 'host'")
 

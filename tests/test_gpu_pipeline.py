@@ -111,13 +111,123 @@ def _fullsize_checks(engine, name, method, n_frames):
 
 
 def test_fullsize_c2_properties(engine):
-    _fullsize_checks(engine, "C2", "half_maximum", 4000)
+    _fullsize_checks(engine, "C2", "half_maximum", 20000)         # BASELINE size: 1024x128 x 20000
 
 
 def test_fullsize_c3_exit(engine):
-    pos, fe = _fullsize_checks(engine, "C3", "threshold", 4000)
-    spec = syn.config_spec("C3", n_frames=4000)
-    assert fe != FF_NO_EXIT and abs(fe - spec.exit_frame(10)) < 12
+    pos, fe = _fullsize_checks(engine, "C3", "threshold", 20000)  # BASELINE size: 1024x256 x 20000
+    spec = syn.config_spec("C3")
+    assert fe != FF_NO_EXIT and abs(fe - spec.exit_frame(10)) < 12 and abs(fe - 15000) < 40
+
+
+def _torch_diff_reference(dec, prev, bg, thr):
+    """Test-only integer restatement of subtract_scalar_background + frame difference
+    (scripts/process_videos.py:670-674, :397-399) in torch, on decoded frames."""
+    sub = torch.clamp(dec.to(torch.int32) - bg, min=0)
+    prior = torch.cat([prev[None], sub[:-1]])
+    d = sub - prior
+    d[d < thr] = 0
+    return d, sub[-1]
+
+
+def test_fullsize_c4_gradient_with_retained_uint16_difference(engine):
+    """BASELINE config 4 at full size (1024x1024 x 5000, gradient, diff retained): every frame of the
+    10.5 GB difference image is checked against an independent torch restatement computed from
+    the unpack kernel's output, and sampled frames against the oracle."""
+    spec = syn.config_spec("C4")
+    n, h, w, fb = spec.n_frames, spec.height, spec.width, spec.frame_bytes
+    packed = syn.render_packed_torch(spec, engine.device)
+    scalars, bg_dev = engine.clip_scalars(packed[:fb], h, w, 12)
+    params = DetectionParams(method="gradient")
+    res = engine.process_range(packed, n, h, w, 12, params, scalars, bg_dev, diff_dtype="uint16")
+    bg, thr = int(scalars.background), 5
+    assert res.diff.dtype == torch.uint16 and tuple(res.diff.shape) == (n, h, w)
+    assert int(res.diff[0].to(torch.int32).abs().sum()) == 0          # no prior for the first frame
+    prev = None
+    step = 250
+    for a in range(0, n, step):
+        dec = engine.unpack(packed[a * fb:(a + step) * fb], step, h, w, 12)
+        if prev is None:
+            prev = torch.clamp(dec[0].to(torch.int32) - bg, min=0)
+        want, prev = _torch_diff_reference(dec, prev, bg, thr)
+        got = res.diff[a:a + step].to(torch.int32)
+        if a == 0:
+            want[0] = 0
+        assert torch.equal(got, want), f"difference image differs in frames [{a}, {a + step})"
+        del dec, want, got
+    # the count-only and the difference kernels must agree on everything else
+    plain = engine.process_range(packed, n, h, w, 12, params, scalars, bg_dev)
+    assert torch.equal(plain.pos, res.pos) and torch.equal(plain.counts, res.counts)
+    assert int(plain.first_exit.item()) == int(res.first_exit.item())
+    # sampled frames against the oracle (positions, counts and the centre row of the difference)
+    frame0 = fo.frames_from_bytes(packed[:fb].cpu().numpy(), 1, h, w, 12)[0]
+    unt = engine.process_range(packed, n, h, w, 12, params, scalars, bg_dev, truncate=False)
+    upos, ucnt = unt.pos.cpu().numpy(), unt.counts.cpu().numpy()
+    t_in = int(spec.t_enter)
+    for f in (1, t_in - 1, t_in + 3, t_in + 200, n - 1):
+        two = fo.frames_from_bytes(packed[(f - 1) * fb:(f + 1) * fb].cpu().numpy(), 2, h, w, 12)
+        o = fo.process_clip(two[1:], fo.ClipParams(method="gradient"), frame0=frame0, first_index=f,
+                            prior_frame=two[0])
+        assert upos[f] == o.pos_px[0] and ucnt[f] == o.nonempty[0], f
+        sub = np.maximum(two.astype(np.int64) - bg, 0)
+        d = sub[1] - sub[0]
+        d[d < thr] = 0
+        assert np.array_equal(res.diff[f].cpu().numpy().astype(np.int64), d), f
+    fe = int(res.first_exit.item())
+    assert fe != FF_NO_EXIT and abs(fe - spec.exit_frame(10)) < 40
+
+
+def test_fullsize_unpack_roundtrip(engine):
+    """Stage 1 at BASELINE size: repacking the unpack kernel's output reproduces the .mraw bytes."""
+    spec = syn.config_spec("C3")
+    n, h, w, fb = spec.n_frames, spec.height, spec.width, spec.frame_bytes
+    packed = syn.render_packed_torch(spec, engine.device)
+    step = 2500
+    for a in range(0, n, step):
+        src = packed[a * fb:(a + step) * fb]
+        px = engine.unpack(src, step, h, w, 12).reshape(-1).to(torch.int32)
+        assert int(px.max()) <= 4095
+        p0, p1 = px[0::2], px[1::2]
+        trip = torch.stack((p0 >> 4, ((p0 & 15) << 4) | (p1 >> 8), p1 & 255), dim=1).to(torch.uint8).reshape(-1)
+        assert torch.equal(trip, src)
+        del px, p0, p1, trip
+
+
+def test_collection_of_pinned_recordings_matches_oracle(tmp_path, engine):
+    """Config 5 in miniature: files on disk -> open_collection -> pin_memory -> process_collection
+    (mixed methods / calibrations); every row against the oracle."""
+    from high_speed_image_processing_b200.photron import open_collection
+    from high_speed_image_processing_b200.process_videos import process_collection
+    methods = ("half_maximum", "threshold", "gradient", "half_maximum")
+    vdir = tmp_path / "videos"
+    specs, cfgs = [], []
+    for i, m in enumerate(methods):
+        base = syn.config_spec("C2" if i % 2 == 0 else "C1", n_frames=220 + 17 * i, seed=900 + i)
+        spec = syn.SyntheticSpec(**{**base.__dict__, "velocity": 6.0 if i != 3 else 1.0, "t_enter": 9.0 + i,
+                                    "style": "mini" if m != "half_maximum" else "nova"})
+        specs.append(spec)
+        syn.write_clip(vdir, f"run-{i}-", spec)
+        cfg = VideoSourceConfig(name=f"v{i}")
+        cfg.detection_method = m
+        cfg.file_calibrations = [FileCalibration(calibration=0.001 * (i + 1), position_offset=0.25 * i,
+                                                 files=[f"run-{i}-"])]
+        cfgs.append(cfg)
+    coll = open_collection(str(vdir))
+    for v in coll:
+        v.pin_memory()
+        assert v.frame_store.is_pinned
+    results = process_collection(coll, cfgs, engine=engine)
+    assert list(results) == [0, 1, 2, 3]
+    for i, spec in enumerate(specs):
+        frames = syn.render_frames(spec)
+        want = fo.process_clip(frames, fo.ClipParams(method=methods[i]))
+        res = results[i]
+        assert [(r[0], r[2]) for r in res.rows] == want.records, i
+        assert res.first_exit == (want.first_exit if want.first_exit < spec.n_frames else None)
+        for f, t, px, pm, _ in res.rows:
+            assert pm == fo.position_m(px, 0.001 * (i + 1), 0.25 * i)
+            assert t == fo.frame_time_absolute(f, spec.start_frame, spec.skip_frame, spec.record_rate)
+    coll.close_all()
 
 
 def test_fullsize_c1(engine):

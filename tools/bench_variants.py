@@ -80,12 +80,14 @@ def main() -> None:
         ("C4", "gradient", "float32", False),
         ("C4", "gradient", "float64", False),
         ("C2", "half_maximum", None, True),       # also materialise decoded uint16 frames
+        ("C3", "unpack", None, False),            # stage 1 alone: ff_unpack, packed 12-bit -> uint16
         ("C2", "head", None, False),              # the detector the reference runs at HEAD
         ("C4", "head", None, False),
     ]
     if args.only:
         want = {tuple(x.split(":")) for x in args.only.split(",")}
-        cases = [c for c in cases if ((c[0], str(c[2])) in want or (c[0], c[1]) in want) and not c[3]]
+        cases = [c for c in cases if (((c[0], str(c[2])) in want or (c[0], c[1]) in want) and not c[3])
+                 or (c[3] and (c[0], "decoded") in want)]
     cache = {}
     for name, method, diff, decoded in cases:
         base = syn.config_spec(name)
@@ -104,6 +106,20 @@ def main() -> None:
 
         if method == "head":
             bench_head(eng, name, spec, packed, n, args.reps)
+            torch.cuda.empty_cache()
+            continue
+        if method == "unpack":
+            keep = {}
+
+            def run_unpack():
+                keep["out"] = eng.unpack(packed, n, h, w, 12)
+            ms = time_call(run_unpack, args.reps)
+            alg_u = n * (fb + 2 * h * w)
+            print(json.dumps({"config": name, "frames": n, "shape": [h, w], "method": "ff_unpack (decode only)",
+                              "algorithmic_bytes_per_frame": fb + 2 * h * w, "kernel_ms": ms,
+                              "kernel_gbs": alg_u / ms / 1e6, "frac_of_measured_peak": alg_u / ms / 1e6 / peak}),
+                  flush=True)
+            keep.clear()
             torch.cuda.empty_cache()
             continue
 
