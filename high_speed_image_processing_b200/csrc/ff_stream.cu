@@ -661,16 +661,18 @@ int launch_stream12(StreamParams p, int ctas_cap, cudaStream_t st) {
 
 template <bool COUNT, bool DIFF, bool DECODED>
 int launch_stream12_tuned(const StreamParams& p, cudaStream_t st) {
-  static const int stages = getenv("FF_STREAM12_STAGES") ? atoi(getenv("FF_STREAM12_STAGES")) : 4;   // tuning knobs
-  static const int ctas = getenv("FF_STREAM12_CTAS") ? atoi(getenv("FF_STREAM12_CTAS")) : 3;
+  // One CTA per SM with a 5-deep ring (48 KB of reads in flight per SM) is the measured optimum for
+  // the read+write variants - fewer concurrent DRAM streams beat more parallelism (C4 uint16 diff:
+  // 0.85 of the copy rate at 3 CTAs x 4 stages, 0.92 at 1 x 5; profiles/r01_stream12_sweep.txt).
+  static const int stages = getenv("FF_STREAM12_STAGES") ? atoi(getenv("FF_STREAM12_STAGES")) : 5;   // tuning knobs
+  static const int ctas = getenv("FF_STREAM12_CTAS") ? atoi(getenv("FF_STREAM12_CTAS")) : 1;
   switch (stages) {
     case 2: return launch_stream12<COUNT, DIFF, DECODED, 2>(p, ctas, st);
     case 3: return launch_stream12<COUNT, DIFF, DECODED, 3>(p, ctas, st);
-    case 5: return launch_stream12<COUNT, DIFF, DECODED, 5>(p, ctas, st);
     case 6: return launch_stream12<COUNT, DIFF, DECODED, 6>(p, ctas, st);
     case 8: return launch_stream12<COUNT, DIFF, DECODED, 8>(p, ctas, st);
-    case 12: return launch_stream12<COUNT, DIFF, DECODED, 12>(p, ctas, st);
-    default: return launch_stream12<COUNT, DIFF, DECODED, 4>(p, ctas, st);
+    case 4: return launch_stream12<COUNT, DIFF, DECODED, 4>(p, ctas, st);
+    default: return launch_stream12<COUNT, DIFF, DECODED, 5>(p, ctas, st);
   }
 }
 
@@ -760,7 +762,12 @@ int launch_stream(StreamParams p, cudaStream_t st) {
     FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     int occ = 0;
     FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, kSmem));
-    if (const char* cap = getenv("FF_STREAM_CTAS")) occ = occ > atoi(cap) ? atoi(cap) : occ;
+    // Write-heavy variants run faster with FEWER resident CTAs (fewer concurrent DRAM streams):
+    // measured on C4, float64 difference 0.86 -> 0.95 of the copy rate at 1 CTA/SM, float32
+    // 0.82 -> 0.87 at 2 (profiles/r01_count12_sweep.txt).  FF_STREAM_CTAS overrides (tuning knob).
+    int cap = DIFF == FF_DIFF_F64 ? 1 : (DIFF == FF_DIFF_F32 ? 2 : occ);
+    if (const char* e = getenv("FF_STREAM_CTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;
+    if (occ > cap) occ = cap;
     ctas_per_sm[dev] = occ > 0 ? occ : 1;
     configured[dev] = true;
   }

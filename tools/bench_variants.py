@@ -101,7 +101,7 @@ def main() -> None:
             cache[key] = syn.render_packed_torch(spec, eng.device)
         packed = cache[key]
         h, w, fb = spec.height, spec.width, spec.frame_bytes
-        params = DetectionParams(method=method if method != "head" else "gradient")
+        params = DetectionParams(method=method if method not in ("head", "unpack") else "gradient")
         scalars, bg_dev = eng.clip_scalars(packed[:fb], h, w, 12)
 
         if method == "head":
