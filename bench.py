@@ -351,16 +351,21 @@ def own_arm(args) -> None:
     clocks = sampler.stop() if rank == 0 else {}
     assert fe_h == first_exit and np.array_equal(pos_h, pos), "host-streamed result differs from device-resident"
     e2e_value = total / e2e_sec
-    # PCIe roofline for the end-to-end path: plain pinned-host -> device copy of the same buffer
+    # PCIe / host-memory roofline for the end-to-end path: plain pinned-host -> device copies of the
+    # same buffer, (a) this rank alone is not separable under torchrun, so (b) ALL ranks at once
+    # behind a barrier - what the box sustains when every GPU pulls from host memory together -
+    # is the denominator; at N=1 the two coincide.
     h2d_peak = 0.0
     scratch = torch.empty_like(packed)
     for _ in range(3):
+        barrier()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
         scratch.copy_(host, non_blocking=True)
         c1.record()
         torch.cuda.synchronize()
-        h2d_peak = max(h2d_peak, host.numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9)
+        ms = max_over_ranks(c0.elapsed_time(c1))
+        h2d_peak = max(h2d_peak, host.numel() / (ms * 1e-3) / 1e9)
     del scratch
     # context for the roofline: what a library pure-read kernel (torch.sum over the same buffer)
     # reaches on this GPU - MEASURED_PEAKS' figure is a 50/50 read+write copy
@@ -419,6 +424,7 @@ def own_arm(args) -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": e2e_sec * 1e3,
                     "h2d_gbs_per_gpu": h2d / e2e_sec / 1e9, "h2d_peak_gbs_measured": h2d_peak,
+                    "h2d_peak_how": "pinned copy of the same buffer, all ranks concurrently, slowest rank",
                     "frac_of_h2d_peak": (h2d / e2e_sec / 1e9) / h2d_peak if h2d_peak else None,
                     "launches_per_step": launches_e2e},
             "gpu_launches": launches,

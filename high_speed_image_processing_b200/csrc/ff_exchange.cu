@@ -17,6 +17,7 @@
 //              directly.  A monotonically increasing epoch written into each peer's flag row
 //              (st.release.sys / ld.acquire.sys) replaces the collective's barrier, and blocks
 //              are double-buffered so no second barrier is needed before the next step.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -277,7 +278,10 @@ int ff_exchange_finish(ff_exchange* x, int64_t total_frames, int32_t* pos_out_de
   p.my_flags = x->local + x->flags_off;
   p.epoch = x->epoch;
   p.status = x->local + x->status_off;
-  p.spin_limit = 4000000000LL;      // ~2 s at 1.9 GHz: a peer that never arrives must not hang the GPU
+  // A peer that never arrives must not hang the GPU for ever: give up after FF_EXCHANGE_TIMEOUT_S
+  // seconds (default 20; ranks may legitimately reach this step seconds apart, e.g. after file I/O).
+  static const double timeout_s = getenv("FF_EXCHANGE_TIMEOUT_S") ? atof(getenv("FF_EXCHANGE_TIMEOUT_S")) : 20.0;
+  p.spin_limit = (long long)((timeout_s > 0.01 ? timeout_s : 0.01) * 1.9e9);
   merge_ranges_kernel<true><<<merge_grid(total_frames), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   FF_CUDA_TRY(cudaGetLastError());
   return FF_OK;

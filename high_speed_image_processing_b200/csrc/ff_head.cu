@@ -219,7 +219,8 @@ __device__ __forceinline__ unsigned long long order_key(unsigned long long bits)
   return (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
 }
 
-__global__ void __launch_bounds__(kTrackThreads) head_track_kernel(const HeadTrackParams p, int n_stages) {
+__global__ void __launch_bounds__(kTrackThreads) head_track_kernel(const HeadTrackParams p, int stage_shift) {
+  const int n_stages = 1 << stage_shift;      // ring depth is a power of two: slot and phase are a mask and a shift
   extern __shared__ __align__(128) uint8_t smem[];
   const int W = p.width;
   const size_t stage_bytes = (size_t)16 * W;
@@ -245,8 +246,8 @@ __global__ void __launch_bounds__(kTrackThreads) head_track_kernel(const HeadTra
     // ---- producer: scan the flags 512 frames at a time, push active frames in order -------------
     int it = 0;
     auto push = [&](int f, int fl) {      // lane 0 only
-      const int s = it % n_stages;
-      mbar_wait(&empty[s], ((it / n_stages) & 1) ^ 1);
+      const int s = it & (n_stages - 1);
+      mbar_wait(&empty[s], ((it >> stage_shift) & 1) ^ 1);
       meta[s].f = f;
       meta[s].fl = fl;
       if (fl == 1) {
@@ -290,8 +291,8 @@ __global__ void __launch_bounds__(kTrackThreads) head_track_kernel(const HeadTra
   int last_f = p.last_frame_in, last_p = p.last_pos_in;
   bool stopped = false;
   for (int it = 0;; ++it) {
-    const int s = it % n_stages;
-    mbar_wait(&full[s], (it / n_stages) & 1);
+    const int s = it & (n_stages - 1);
+    mbar_wait(&full[s], (it >> stage_shift) & 1);
     const int f = meta[s].f;
     const int fl = meta[s].fl;
     if (f < 0) break;
@@ -316,11 +317,31 @@ __global__ void __launch_bounds__(kTrackThreads) head_track_kernel(const HeadTra
         const unsigned long long* grd = sob + W;
         unsigned long long mn = ~0ull, amax = 0ull;    // key(+inf) < ~0;  |x| keys start at 0
         int arg = INT_MAX;
-        for (int x = s0 + lane; x < s1; x += 32) {
-          const unsigned long long g = order_key(grd[x]);
-          if (g < mn) { mn = g; arg = x; }
-          const unsigned long long a = sob[x] & 0x7FFFFFFFFFFFFFFFull;      // |sobel| as an ordered integer
-          amax = a > amax ? a : amax;
+        const bool small = s1 - s0 <= 128;             // the steady state: window = displacement bound + 100
+        unsigned long long a4[4];
+        if (small) {                                   // all loads issued up front, everything stays in registers
+          unsigned long long g4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int x = s0 + lane + 32 * j;
+            const bool in = x < s1;
+            g4[j] = in ? grd[x] : 0x7FF8000000000000ull;
+            a4[j] = in ? (sob[x] & 0x7FFFFFFFFFFFFFFFull) : 0ull;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int x = s0 + lane + 32 * j;
+            const unsigned long long g = x < s1 ? order_key(g4[j]) : ~0ull;
+            if (g < mn) { mn = g; arg = x; }
+            amax = a4[j] > amax ? a4[j] : amax;
+          }
+        } else {
+          for (int x = s0 + lane; x < s1; x += 32) {
+            const unsigned long long g = order_key(grd[x]);
+            if (g < mn) { mn = g; arg = x; }
+            const unsigned long long a = sob[x] & 0x7FFFFFFFFFFFFFFFull;      // |sobel| as an ordered integer
+            amax = a > amax ? a : amax;
+          }
         }
         const bool any = s1 - s0 > 0;
         // first minimum: smallest key, then smallest index (np.argmin)
@@ -338,8 +359,14 @@ __global__ void __launch_bounds__(kTrackThreads) head_track_kernel(const HeadTra
         if (any && amax_d > p.min_strength) {                                                 // :434-440
           const unsigned long long thr = (unsigned long long)__double_as_longlong(__dmul_rn(amax_d, p.sobel_frac));
           int right = -1;
-          for (int x = s0 + lane; x < s1; x += 32)
-            if ((sob[x] & 0x7FFFFFFFFFFFFFFFull) > thr) right = x;
+          if (small) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (a4[j] > thr) right = s0 + lane + 32 * j;      // out-of-window slots hold 0 and thr >= 0
+          } else {
+            for (int x = s0 + lane; x < s1; x += 32)
+              if ((sob[x] & 0x7FFFFFFFFFFFFFFFull) > thr) right = x;
+          }
           pos_b = __reduce_max_sync(fullmask, right);
         }
       }
@@ -543,9 +570,10 @@ int head_track_impl(const double* lines, const uint8_t* flags, int64_t n_frames,
   // ring of 16*W-byte stages: as many as fit (2..8); very wide rows take the generic kernel
   const size_t stage_bytes = (size_t)16 * width;
   const size_t fixed = (size_t)kTrackMaxStages * (8 + 8 + sizeof(TrackMeta)) + 16;
-  int stages = (int)((200 * 1024 - fixed) / stage_bytes);
-  if (stages > kTrackMaxStages) stages = kTrackMaxStages;
-  if (stages < 2 || (reinterpret_cast<uintptr_t>(lines) & 15u) != 0) {
+  const int fit = (int)((200 * 1024 - fixed) / stage_bytes);
+  const int shift = fit >= 8 ? 3 : (fit >= 4 ? 2 : (fit >= 2 ? 1 : 0));
+  const int stages = 1 << shift;
+  if (shift == 0 || (reinterpret_cast<uintptr_t>(lines) & 15u) != 0) {
     head_track_generic_kernel<<<1, kHeadThreads, 0, st>>>(p);
     FF_CUDA_TRY(cudaGetLastError());
     return FF_OK;
@@ -556,7 +584,7 @@ int head_track_impl(const double* lines, const uint8_t* flags, int64_t n_frames,
     FF_CUDA_TRY(cudaFuncSetAttribute(head_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  head_track_kernel<<<1, kTrackThreads, smem, st>>>(p, stages);
+  head_track_kernel<<<1, kTrackThreads, smem, st>>>(p, shift);
   FF_CUDA_TRY(cudaGetLastError());
   return FF_OK;
 }

@@ -167,7 +167,8 @@ int ff_truncate(int32_t* pos_dev, int64_t n_frames, int64_t first_frame,
  *   ff_exchange_finish      the fused publish/wait/pull/merge kernel; every rank must call it once
  *                           per ff_exchange_begin
  *   ff_exchange_status      synchronises `stream`; *status_out != 0 means a peer (value-1) never
- *                           published within ~2 s and the outputs are invalid                          */
+ *                           published within FF_EXCHANGE_TIMEOUT_S seconds (environment, default 20)
+ *                           and the outputs are invalid                                                */
 int ff_range_block_len(int64_t cap_frames, int64_t* n_elems);
 int ff_merge_ranges(const int32_t* gathered_dev, int world, int64_t block_cap_frames, int64_t total_frames,
                     int32_t* pos_out_dev, int32_t* count_out_dev, int32_t* first_exit_out_dev, void* stream);

@@ -80,6 +80,9 @@ def main() -> None:
         ("C4", "gradient", "float32", False),
         ("C4", "gradient", "float64", False),
         ("C2", "half_maximum", None, True),       # also materialise decoded uint16 frames
+        ("C2/16", "half_maximum", None, False),    # same clip stored as 16-bit little-endian MRAW
+        ("C2/8", "half_maximum", None, False),     # ... and as 8-bit
+        ("C4/16", "gradient", "uint16", False),
         ("C3", "unpack", None, False),            # stage 1 alone: ff_unpack, packed 12-bit -> uint16
         ("C2", "head", None, False),              # the detector the reference runs at HEAD
         ("C4", "head", None, False),
@@ -90,11 +93,19 @@ def main() -> None:
                  or (c[3] and (c[0], "decoded") in want)]
     cache = {}
     for name, method, diff, decoded in cases:
-        base = syn.config_spec(name)
+        cfg_name, _, bits_s = name.partition("/")
+        bits = int(bits_s) if bits_s else 12
+        base = syn.config_spec(cfg_name)
+        if bits != 12:
+            base = syn.SyntheticSpec(**{**base.__dict__, "bits": bits})
         n = max(8, int(base.n_frames * args.frames_scale))
         if diff == "float64":
             n = min(n, 2500)                       # 8 B/px x 1 Mpx x 2500 = 21 GB retained
-        spec = syn.config_spec(name, n_frames=n) if n != base.n_frames else base
+        spec = base
+        if n != base.n_frames:
+            spec = syn.config_spec(cfg_name, n_frames=n)
+            if bits != 12:
+                spec = syn.SyntheticSpec(**{**spec.__dict__, "bits": bits})
         key = (name, n)
         if key not in cache:
             cache.clear()
@@ -102,7 +113,7 @@ def main() -> None:
         packed = cache[key]
         h, w, fb = spec.height, spec.width, spec.frame_bytes
         params = DetectionParams(method=method if method not in ("head", "unpack") else "gradient")
-        scalars, bg_dev = eng.clip_scalars(packed[:fb], h, w, 12)
+        scalars, bg_dev = eng.clip_scalars(packed[:fb], h, w, bits)
 
         if method == "head":
             bench_head(eng, name, spec, packed, n, args.reps)
@@ -127,7 +138,7 @@ def main() -> None:
         out = {}
 
         def run():
-            out["res"] = eng.process_range(packed, n, h, w, 12, params, scalars, bg_dev, diff_dtype=diff,
+            out["res"] = eng.process_range(packed, n, h, w, bits, params, scalars, bg_dev, diff_dtype=diff,
                                            keep_decoded=decoded)
         whole_ms = time_call(run, args.reps)
         ev = eng._stream_events
