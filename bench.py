@@ -68,8 +68,9 @@ class ClockSampler:
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, period_ms: int = 100):
         self.gpu = gpu_index
+        self.period_ms = max(10, int(period_ms))
         self.proc = None
         self.path = None
 
@@ -78,7 +79,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", str(self.period_ms),
                  "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -283,8 +284,8 @@ def own_arm(args) -> None:
     for _ in range(args.warmup):
         pos_t, fe_t, cnt_t = step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(local_rank, period_ms=args.clock_period_ms)
+    if rank == 0 and args.clock_period_ms > 0:
         sampler.start()
         time.sleep(0.25)
     eng._stream_events = []
@@ -449,6 +450,7 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--sample-frames", type=int, default=4000, help="CPU baseline sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-period-ms", type=int, default=100, help="nvidia-smi sampling period (0 = off)")
     ap.add_argument("--exchange", choices=["auto", "peer", "gathered"], default="auto",
                     help="multi-GPU block transport: peer memory over NVLink (CUDA IPC) or one NCCL all-gather")
     args = ap.parse_args()

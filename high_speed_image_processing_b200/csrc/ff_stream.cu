@@ -766,6 +766,7 @@ int launch_stream(StreamParams p, cudaStream_t st) {
     // measured on C4, float64 difference 0.86 -> 0.95 of the copy rate at 1 CTA/SM, float32
     // 0.82 -> 0.87 at 2 (profiles/r01_count12_sweep.txt).  FF_STREAM_CTAS overrides (tuning knob).
     int cap = DIFF == FF_DIFF_F64 ? 1 : (DIFF == FF_DIFF_F32 ? 2 : occ);
+    if (BITS == 16 && DIFF == FF_DIFF_NONE && !DECODED && K == 4) cap = 2;   // 16-bit counts: 0.95 -> 1.08 (96 KB in flight)
     if (const char* e = getenv("FF_STREAM_CTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;
     if (occ > cap) occ = cap;
     ctas_per_sm[dev] = occ > 0 ? occ : 1;

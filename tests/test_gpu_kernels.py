@@ -232,6 +232,52 @@ def test_subrange_with_halo_equals_serial(engine):
     assert min(exits) == (serial.first_exit if serial.first_exit < n else FF_NO_EXIT)
 
 
+def test_big_tile_kernels_with_skips_halo_and_ragged_tiles(engine):
+    """Frames large enough for the 8192-pixel tiles (count12_kernel / stream12_kernel): ragged last
+    tile (130 rows -> 16.25 tiles), CTAs whose run of items crosses tile boundaries, skip_frames,
+    a sub-range with a halo frame, uint16 difference + decoded output, all against the oracle."""
+    frames = small_clip(w=1024, h=130, n=23, seed=41, style="mini")
+    n = len(frames)
+    skip = [3, 4, 9, 22]
+    mask = np.zeros(n, dtype=np.uint8)
+    mask[skip] = 1
+    want = fo.process_clip(frames, fo.ClipParams(method="threshold", skip_frames=skip, keep_diffs=True))
+    res, _ = run_range(engine, frames, 12, DetectionParams(method="threshold"), skip=dev(mask, engine),
+                       diff_dtype="uint16", keep_decoded=True)
+    live = mask == 0          # the reference never looks at skip_frames entries (:1443-1445): counts undefined there
+    assert np.array_equal(res.counts.cpu().numpy()[live], want.nonempty.astype(np.int32)[live])
+    assert np.array_equal(res.pos.cpu().numpy(), oracle_pos(want))
+    assert np.array_equal(res.diff.cpu().numpy().astype(np.float64), want.diffs)
+    assert np.array_equal(res.decoded.cpu().numpy(), frames)
+    # counts only (count12_kernel) and difference only (no decoded output)
+    plain, _ = run_range(engine, frames, 12, DetectionParams(method="threshold"), skip=dev(mask, engine))
+    assert np.array_equal(plain.counts.cpu().numpy()[live], want.nonempty.astype(np.int32)[live])
+    assert np.array_equal(plain.pos.cpu().numpy(), oracle_pos(want))
+    only, _ = run_range(engine, frames, 12, DetectionParams(method="threshold"), skip=dev(mask, engine),
+                        diff_dtype="uint16")
+    assert np.array_equal(only.diff.cpu().numpy().astype(np.float64), want.diffs)
+    # sub-range [10, 23) whose prior frame (9) is skipped: the halo is frame 8
+    a = 10
+    halo = dev(syn.pack_frames(frames[8:9], 12), engine)
+    sub, _ = run_range(engine, frames[a:], 12, DetectionParams(method="threshold"), frame0=frames[0], first_frame=a,
+                       halo=halo, skip=dev(mask[a:], engine), diff_dtype="uint16", truncate=False)
+    assert np.array_equal(sub.diff.cpu().numpy().astype(np.float64), want.diffs[a:])
+    assert np.array_equal(sub.pos.cpu().numpy(), want.pos_px[a:])
+    # zero difference threshold keeps every non-negative difference
+    z, _ = run_range(engine, frames[:6], 12, DetectionParams(method="gradient", frame_diff_threshold=0.0),
+                     diff_dtype="uint16")
+    wz = fo.process_clip(frames[:6], fo.ClipParams(method="gradient", frame_diff_threshold=0.0, keep_diffs=True))
+    assert np.array_equal(z.diff.cpu().numpy().astype(np.float64), wz.diffs)
+    # 16-bit and 8-bit storage of large frames (general template, 8192-pixel tiles)
+    for bits in (16, 8):
+        fr = small_clip(bits=bits, w=1024, h=130, n=7, seed=bits, style="mini")
+        r, _ = run_range(engine, fr, bits, DetectionParams(method="gradient"), diff_dtype="uint16")
+        w_ = fo.process_clip(fr, fo.ClipParams(method="gradient", keep_diffs=True))
+        assert np.array_equal(r.counts.cpu().numpy(), w_.nonempty.astype(np.int32)), bits
+        assert np.array_equal(r.pos.cpu().numpy(), oracle_pos(w_)), bits
+        assert np.array_equal(r.diff.cpu().numpy().astype(np.float64), w_.diffs), bits
+
+
 def test_empty_and_degenerate_inputs(engine):
     # all-dark clip: every frame empty, nothing detected, no exit
     dark = np.full((10, 8, 64), 40, dtype=np.uint16)
