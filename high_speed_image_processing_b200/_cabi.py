@@ -25,7 +25,7 @@ FF_DIFF_NONE, FF_DIFF_U16, FF_DIFF_F32, FF_DIFF_F64 = 0, 1, 2, 3
 FF_POS_NONE = -1
 FF_POS_DROPPED = -2
 FF_NO_EXIT = 2147483647
-FF_ABI_VERSION = 2
+FF_ABI_VERSION = 3
 
 
 class FlameFrontLibraryError(RuntimeError):
@@ -68,7 +68,7 @@ SIGNATURES = {
     "ff_exchange_status": (_int, [_vp, C.POINTER(_i32), _vp]),
     "ff_exchange_destroy": (_int, [_vp]),
     "ff_head_lines": (_int, [_vp, _vp, _i64, _int, _int, _int, _vp, _vp, _i64, _i32, C.POINTER(C.c_double), _int, _vp,
-                             _vp, _vp, _vp]),
+                             _vp, _vp, _vp, _vp]),
     "ff_head_track": (_int, [_vp, _vp, _i64, _i64, _int, _i32, _i32, _i32, C.c_double, C.c_double, _i32, _i32, _i32,
                              _vp, _vp, _vp]),
     "ff_host_ctx_create": (_int, [_int, _i64, C.POINTER(_vp)]),

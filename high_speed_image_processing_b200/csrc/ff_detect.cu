@@ -85,14 +85,47 @@ __global__ void __launch_bounds__(kDetectWarps * 32) detect_kernel(const DetectP
   const int nbytes = (int)(byte_hi - byte_lo);
   const int64_t qbase = (BITS == 12) ? (q0 & ~(int64_t)1) : q0;  // pixel held by raw byte 0
 
-  for (int f = blockIdx.x * kDetectWarps + warp; f < p.n_frames; f += gridDim.x * kDetectWarps) {
-    const bool skipped = p.skip != nullptr && p.skip[f] != 0;
-
-    // above-noise pixel count (is_empty_frame, scripts/process_videos.py:759-763)
-    int cnt = 0;
-    for (int t = lane; t < p.partials_per_frame; t += 32) cnt += __ldg(p.partial + (int64_t)f * p.partials_per_frame + t);
-    cnt = __reduce_add_sync(full, cnt);
-    if (lane == 0 && p.count_out != nullptr) p.count_out[f] = cnt;
+  // Frames are dealt to warps in strides: warp w looks at frames w, w + nw, w + 2 nw, ... 32 at a
+  // time, one candidate per lane.  Every lane sums its candidate's partial counts (the empty-frame
+  // decision of :759-763) in parallel; only the frames that need a profile - the few percent that
+  // hold a flame, and they are consecutive, so the stride spreads them over all warps - are then
+  // handled one by one by the whole warp.
+  const int nw = gridDim.x * kDetectWarps;
+  const int w = blockIdx.x * kDetectWarps + warp;
+  const bool vec = (p.partials_per_frame & 3) == 0 && (reinterpret_cast<uintptr_t>(p.partial) & 15u) == 0;
+  for (int64_t base = w; base < p.n_frames; base += (int64_t)32 * nw) {
+    const int64_t fc = base + (int64_t)lane * nw;
+    const bool valid = fc < p.n_frames;
+    int cnt_c = 0;
+    bool need_c = false;
+    if (valid) {
+      // above-noise pixel count (is_empty_frame, scripts/process_videos.py:759-763)
+      const int32_t* pc = p.partial + fc * p.partials_per_frame;
+      if (vec) {
+        const int4* p4 = reinterpret_cast<const int4*>(pc);
+#pragma unroll 8
+        for (int t = 0; t < p.partials_per_frame / 4; ++t) {
+          const int4 v = __ldg(p4 + t);
+          cnt_c += (v.x + v.y) + (v.z + v.w);
+        }
+      } else {
+        for (int t = 0; t < p.partials_per_frame; ++t) cnt_c += __ldg(pc + t);
+      }
+      if (p.count_out != nullptr) p.count_out[fc] = cnt_c;
+      const bool skipped_c = p.skip != nullptr && p.skip[fc] != 0;
+      const bool empty_c = (int64_t)cnt_c < p.min_signal_count;
+      // without a prior frame there is no difference profile: only frame 0 of a range without halo
+      // (or a range that starts with skipped frames) - resolved exactly in the per-frame path below
+      need_c = !skipped_c && (!empty_c || p.profile_out != nullptr);
+      if (!need_c) p.pos_out[fc] = FF_POS_NONE;
+    }
+    unsigned pending = __ballot_sync(full, need_c);
+    while (pending) {
+    const int src = __ffs((int)pending) - 1;
+    pending &= pending - 1;
+    const int f = (int)(base + (int64_t)src * nw);
+    const int cnt = __shfl_sync(full, cnt_c, src);
+    const bool skipped = false;
     const bool empty = (int64_t)cnt < p.min_signal_count;
 
     // prior frame: the latest non-skipped frame before f (:469, :1462, :1443-1445)
@@ -208,6 +241,7 @@ __global__ void __launch_bounds__(kDetectWarps * 32) detect_kernel(const DetectP
       if (pos >= 0 && pos >= W - p.exit_margin)  // scripts/process_videos.py:1488-1489
         atomicMin(p.first_exit, (int)(p.first_frame + f));
     }
+    }  // pending frames of this round
   }
 }
 
@@ -280,11 +314,16 @@ int detect_impl(const void* frames, const void* halo, int64_t n_frames, int64_t 
 
   const size_t smem = (size_t)kDetectWarps * width * sizeof(int) + (size_t)kDetectWarps * 2 * p.raw_stride;
   if (smem > 200 * 1024) return FF_ERR_UNSUPPORTED;  // W beyond ~5k columns: not a Photron sensor
-  int64_t blocks = (n_frames + kDetectWarps - 1) / kDetectWarps;
-  if (blocks > 148 * 64) blocks = 148 * 64;
   auto launch = [&](auto kern) -> int {
     if (smem > 48 * 1024)
       FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // one resident wave of warps; each takes every nw-th frame
+    int occ = 1, sms = 148, dev = 0;
+    FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDetectWarps * 32, smem));
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t blocks = (int64_t)sms * (occ > 0 ? occ : 1);
+    const int64_t enough = (n_frames + kDetectWarps - 1) / kDetectWarps;
+    if (blocks > enough) blocks = enough;
     kern<<<(unsigned)blocks, kDetectWarps * 32, smem, st>>>(p);
     FF_CUDA_TRY(cudaGetLastError());
     return FF_OK;

@@ -40,9 +40,37 @@ struct HeadBandParams {
   int radius;
   double* lines;   // [n][2][W]  (sobel row, gradient row)
   uint8_t* flags;  // [n]  0 = not processed (skipped / empty), 1 = lines valid, 2 = processed, no prior frame
+  int32_t* scratch;  // [0] number of frames with flag 1, [4 + k] their indices (any order)
 };
 
+// One warp per frame: the empty-frame decision (:759-763, sum of the streaming kernel's partial
+// counts), the flag, and the list of frames the band kernel has work for - so that kernel runs as
+// persistent CTAs over the ~5 % of frames that hold a flame instead of launching (and retiring)
+// a shared-memory-heavy CTA for every frame of the clip.
+__global__ void __launch_bounds__(kHeadThreads) head_flags_kernel(const HeadBandParams p) {
+  const int lane = threadIdx.x & 31;
+  const int f = blockIdx.x * (kHeadThreads / 32) + (threadIdx.x >> 5);
+  if (f >= p.n_frames) return;
+  const bool skipped = p.skip != nullptr && p.skip[f] != 0;
+  int cnt = 0;
+  if (!skipped)
+    for (int t = lane; t < p.partials_per_frame; t += 32) cnt += __ldg(p.partial + (int64_t)f * p.partials_per_frame + t);
+  cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+  if (lane != 0) return;
+  const bool empty = (int64_t)cnt < p.min_signal_count;
+  int flag = 0;
+  if (!skipped && !empty) {
+    int hf = f - 1;
+    if (p.skip != nullptr)
+      while (hf >= 0 && p.skip[hf]) --hf;
+    flag = (hf >= 0 || p.halo != nullptr) ? 1 : 2;
+  }
+  p.flags[f] = (uint8_t)flag;
+  if (flag == 1) p.scratch[4 + atomicAdd(p.scratch, 1)] = f;
+}
+
 __device__ __forceinline__ int reflect_idx(int i, int n) {
+  if ((unsigned)i < (unsigned)n) return i;      // interior: no division
   const int period = 2 * n;
   i %= period;
   if (i < 0) i += period;
@@ -52,40 +80,25 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 template <int BITS>
 __global__ void __launch_bounds__(kHeadThreads) head_band_kernel(const HeadBandParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int f = blockIdx.y;
   const int tid = threadIdx.x;
   const int W = p.width, H = p.height;
   const int R = p.radius;
   const int HALO = R + 3;
   const int NB = 2 * HALO + 1;            // band rows
-  const int x_begin = blockIdx.x * kHeadTileW;
+  const int c = H / 2;
+  const int tiles_x = (W + kHeadTileW - 1) / kHeadTileW;
+  const int n_work = __ldg(p.scratch) * tiles_x;
+  const int bg = __ldg(p.bg_dev);
+
+  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+  const int f = __ldg(p.scratch + 4 + work / tiles_x);
+  const int x_begin = (work % tiles_x) * kHeadTileW;
   const int tw = min(kHeadTileW, W - x_begin);
   const int LW = tw + 2 * HALO;           // band columns held by this CTA
-  const int c = H / 2;
-
-  // ---- frame state (uniform across the CTA) ------------------------------------------------
-  const bool skipped = p.skip != nullptr && p.skip[f] != 0;
-  __shared__ int s_cnt;
-  if (tid == 0) s_cnt = 0;
-  __syncthreads();
-  if (!skipped) {
-    int cnt = 0;
-    for (int t = tid; t < p.partials_per_frame; t += kHeadThreads) cnt += __ldg(p.partial + (int64_t)f * p.partials_per_frame + t);
-    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-    if ((tid & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
-  }
-  __syncthreads();
-  const bool empty = (int64_t)s_cnt < p.min_signal_count;
-  const uint8_t* prior = nullptr;
-  if (!skipped && !empty) {
-    int hf = f - 1;
-    if (p.skip != nullptr)
-      while (hf >= 0 && p.skip[hf]) --hf;
-    prior = hf >= 0 ? p.frames + (int64_t)hf * p.frame_bytes : p.halo;
-  }
-  const int flag = (skipped || empty) ? 0 : (prior != nullptr ? 1 : 2);
-  if (blockIdx.x == 0 && tid == 0) p.flags[f] = (uint8_t)flag;
-  if (flag != 1) return;
+  int hf = f - 1;
+  if (p.skip != nullptr)
+    while (hf >= 0 && p.skip[hf]) --hf;
+  const uint8_t* prior = hf >= 0 ? p.frames + (int64_t)hf * p.frame_bytes : p.halo;
 
   // ---- shared-memory carve-up -----------------------------------------------------------------
   uint16_t* bufA = reinterpret_cast<uint16_t*>(smem);                    // [NB][LW]
@@ -94,45 +107,50 @@ __global__ void __launch_bounds__(kHeadThreads) head_band_kernel(const HeadBandP
   double* g0 = reinterpret_cast<double*>(smem + u16_bytes);               // [3][LW]
   double* bl = g0 + 3 * LW;                                               // [3][LW]
 
-  const int bg = __ldg(p.bg_dev);
   const uint8_t* cur = p.frames + (int64_t)f * p.frame_bytes;
 
   // ---- D: thresholded difference on the reflect-extended band ----------------------------------
-  for (int e = tid; e < NB * LW; e += kHeadThreads) {
-    const int i = e / LW, j = e - i * LW;
-    const int r = reflect_idx(c - HALO + i, H);
-    const int x = reflect_idx(x_begin - HALO + j, W);
-    const int64_t q = (int64_t)r * W + x;
-    int d = max(load_px_generic<BITS>(cur, q) - bg, 0) - max(load_px_generic<BITS>(prior, q) - bg, 0);
-    if (d < p.diff_thr) d = 0;
-    bufA[e] = (uint16_t)d;              // diff_thr >= 0 is enforced by the launcher: 0 <= d <= 65535
+  // (warps walk rows, lanes walk columns: coalesced byte reads, no index division)
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int i = warp; i < NB; i += kHeadThreads / 32) {
+    const int64_t rowq = (int64_t)reflect_idx(c - HALO + i, H) * W;
+    for (int j = lane; j < LW; j += 32) {
+      const int64_t q = rowq + reflect_idx(x_begin - HALO + j, W);
+      int d = max(load_px_generic<BITS>(cur, q) - bg, 0) - max(load_px_generic<BITS>(prior, q) - bg, 0);
+      if (d < p.diff_thr) d = 0;
+      bufA[i * LW + j] = (uint16_t)d;   // diff_thr >= 0 is enforced by the launcher: 0 <= d <= 65535
+    }
   }
   __syncthreads();
   // ---- E = 3x3 minimum (valid rows [1,NB-1), cols [1,LW-1)) --------------------------------------
-  for (int e = tid; e < NB * LW; e += kHeadThreads) {
-    const int i = e / LW, j = e - i * LW;
-    unsigned m = 0;
-    if (i >= 1 && i < NB - 1 && j >= 1 && j < LW - 1) {
-      m = 0xFFFFu;
+  for (int i = warp; i < NB; i += kHeadThreads / 32) {
+    const bool row_ok = i >= 1 && i < NB - 1;
+    for (int j = lane; j < LW; j += 32) {
+      unsigned m = 0;
+      if (row_ok && j >= 1 && j < LW - 1) {
+        m = 0xFFFFu;
 #pragma unroll
-      for (int di = -1; di <= 1; ++di)
+        for (int di = -1; di <= 1; ++di)
 #pragma unroll
-        for (int dj = -1; dj <= 1; ++dj) m = min(m, (unsigned)bufA[(i + di) * LW + j + dj]);
+          for (int dj = -1; dj <= 1; ++dj) m = min(m, (unsigned)bufA[(i + di) * LW + j + dj]);
+      }
+      bufB[i * LW + j] = (uint16_t)m;
     }
-    bufB[e] = (uint16_t)m;
   }
   __syncthreads();
   // ---- NR = 3x3 maximum of E (valid rows [2,NB-2), cols [2,LW-2)) ---------------------------------
-  for (int e = tid; e < NB * LW; e += kHeadThreads) {
-    const int i = e / LW, j = e - i * LW;
-    unsigned m = 0;
-    if (i >= 2 && i < NB - 2 && j >= 2 && j < LW - 2) {
+  for (int i = warp; i < NB; i += kHeadThreads / 32) {
+    const bool row_ok = i >= 2 && i < NB - 2;
+    for (int j = lane; j < LW; j += 32) {
+      unsigned m = 0;
+      if (row_ok && j >= 2 && j < LW - 2) {
 #pragma unroll
-      for (int di = -1; di <= 1; ++di)
+        for (int di = -1; di <= 1; ++di)
 #pragma unroll
-        for (int dj = -1; dj <= 1; ++dj) m = max(m, (unsigned)bufB[(i + di) * LW + j + dj]);
+          for (int dj = -1; dj <= 1; ++dj) m = max(m, (unsigned)bufB[(i + di) * LW + j + dj]);
+      }
+      bufA[i * LW + j] = (uint16_t)m;
     }
-    bufA[e] = (uint16_t)m;
   }
   __syncthreads();
   // ---- G0 = Gaussian along rows (axis 0) for band rows HALO-1, HALO, HALO+1 ------------------------
@@ -184,6 +202,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_band_kernel(const HeadBandP
     else if (x == W - 1) g = __ddiv_rn(__dsub_rn(v[j], v[j - 1]), 1.0);
     else g = __ddiv_rn(__dsub_rn(v[j + 1], v[j - 1]), 2.0);
     out_g[x] = g;
+  }
+  __syncthreads();      // the next work item reuses the shared-memory band
   }
 }
 
@@ -486,11 +506,11 @@ __global__ void __launch_bounds__(kHeadThreads) head_track_generic_kernel(const 
 int head_lines_impl(const void* frames, const void* halo, int64_t n_frames, int height, int width, int bits,
                     const int32_t* bg_dev, const int32_t* partial, int64_t min_signal_count, int32_t diff_thr,
                     const double* gauss_weights_host, int radius, const uint8_t* skip, double* lines_out,
-                    uint8_t* flags_out, cudaStream_t st) {
+                    uint8_t* flags_out, int32_t* scratch, cudaStream_t st) {
   if (frames == nullptr || bg_dev == nullptr || partial == nullptr || gauss_weights_host == nullptr ||
-      lines_out == nullptr || flags_out == nullptr)
+      lines_out == nullptr || flags_out == nullptr || scratch == nullptr)
     return FF_ERR_INVALID;
-  if (n_frames <= 0 || height <= 0 || width < 2 || n_frames > 65535 * 64) return FF_ERR_INVALID;
+  if (n_frames <= 0 || height <= 0 || width < 2 || n_frames > 0x7FFFFFFF) return FF_ERR_INVALID;
   if (bits != 8 && bits != 12 && bits != 16) return FF_ERR_UNSUPPORTED;
   if (radius < 0 || radius > kMaxRadius) return FF_ERR_UNSUPPORTED;
   if (diff_thr < 0) return FF_ERR_UNSUPPORTED;       // band is held as uint16
@@ -518,23 +538,24 @@ int head_lines_impl(const void* frames, const void* halo, int64_t n_frames, int 
   const int nb = 2 * halo_px + 1;
   const int lw = kHeadTileW + 2 * halo_px;
   const size_t smem = (((size_t)2 * nb * lw * sizeof(uint16_t) + 15) & ~(size_t)15) + (size_t)6 * lw * sizeof(double);
+  p.n_frames = (int)n_frames;
+  p.scratch = scratch;
+  FF_CUDA_TRY(cudaMemsetAsync(scratch, 0, 4 * sizeof(int32_t), st));
+  const int warps = kHeadThreads / 32;
+  head_flags_kernel<<<(unsigned)((n_frames + warps - 1) / warps), kHeadThreads, 0, st>>>(p);
+  FF_CUDA_TRY(cudaGetLastError());
   const int tiles_x = (width + kHeadTileW - 1) / kHeadTileW;
   auto launch = [&](auto kern) -> int {
     if (smem > 48 * 1024) FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // gridDim.y is limited to 65535: walk the frames in slabs
-    for (int64_t f0 = 0; f0 < n_frames; f0 += 65535) {
-      HeadBandParams q = p;
-      const int nf = (int)((n_frames - f0 < 65535) ? n_frames - f0 : 65535);
-      q.n_frames = nf;
-      q.frames = p.frames + f0 * p.frame_bytes;
-      q.halo = f0 == 0 ? p.halo : p.frames + (f0 - 1) * p.frame_bytes;
-      q.partial = p.partial + f0 * p.partials_per_frame;
-      q.skip = p.skip ? p.skip + f0 : nullptr;
-      q.lines = p.lines + f0 * 2 * width;
-      q.flags = p.flags + f0;
-      kern<<<dim3((unsigned)tiles_x, (unsigned)nf), kHeadThreads, smem, st>>>(q);
-      FF_CUDA_TRY(cudaGetLastError());
-    }
+    int occ = 1;
+    FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kHeadThreads, smem));
+    int sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t grid = (int64_t)sms * (occ > 0 ? occ : 1);          // persistent CTAs over the active list
+    if (grid > n_frames * tiles_x) grid = n_frames * tiles_x;
+    kern<<<(unsigned)grid, kHeadThreads, smem, st>>>(p);
+    FF_CUDA_TRY(cudaGetLastError());
     return FF_OK;
   };
   switch (bits) {

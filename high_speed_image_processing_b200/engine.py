@@ -412,6 +412,7 @@ class FlameFrontEngine:
         flags = torch.empty(n_frames, dtype=torch.uint8, device=self.device)
         track = torch.empty((n_frames, 5), dtype=torch.int32, device=self.device)
         stop = torch.empty(3, dtype=torch.int32, device=self.device)
+        scratch = torch.empty(n_frames + 4, dtype=torch.int32, device=self.device)
         weights = np.ascontiguousarray(gaussian_weights(params.gaussian_sigma), dtype=np.float64)
         radius = (weights.size - 1) // 2
         st = self._stream()
@@ -423,14 +424,14 @@ class FlameFrontEngine:
                 frames.data_ptr(), _ptr(halo), n_frames, height, width, bits, bg_dev.data_ptr(),
                 partial.data_ptr(), min_signal_count(height * width, params.min_signal_fraction), diff_thr,
                 weights.ctypes.data_as(C.POINTER(C.c_double)), radius, _ptr(skip), lines.data_ptr(),
-                flags.data_ptr(), st), "ff_head_lines")
+                flags.data_ptr(), scratch.data_ptr(), st), "ff_head_lines")
             _cabi.check(self._lib.ff_head_track(
                 lines.data_ptr(), flags.data_ptr(), n_frames, first_frame, width, params.edge_margin_px,
                 max_displacement_px(frame_rate, calibration, params), params.search_window_px,
                 float(params.min_gradient_strength), float(params.sobel_threshold_fraction),
                 params.exit_margin_px, int(tracker_state[0]), int(tracker_state[1]), track.data_ptr(),
                 stop.data_ptr(), st), "ff_head_track")
-        self.launches += 3
+        self.launches += 4
         done, bg_host, line_host = fetch
         done.synchronize()
         scalars = ClipScalars.from_frame0_stats(int(bg_host.item()), line_host.numpy())

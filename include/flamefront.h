@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FF_ABI_VERSION 2
+#define FF_ABI_VERSION 3
 
 /* status codes */
 #define FF_OK                 0
@@ -193,6 +193,7 @@ int ff_exchange_destroy(ff_exchange* x);
  *   lines_out_dev       float64[n_frames,2,W]: [.,0,:] Sobel centre row, [.,1,:] gradient centre row
  *   flags_out_dev       uint8[n_frames]: 0 not processed (skipped/empty), 1 lines valid,
  *                       2 processed but no prior frame (detect() ran without a difference image)
+ *   scratch_dev         int32[n_frames + 4] scratch (list of the frames that reached the detector)
  * ff_head_track replaces the sequential part (:317-348 search bounds, :420-465 candidate
  * selection) and the exit stop (:1488-1494).
  *   last_frame_in/last_pos_in  tracker state carried in (-1/-1 = no detection yet)
@@ -202,7 +203,7 @@ int ff_exchange_destroy(ff_exchange* x);
 int ff_head_lines(const void* frames_dev, const void* halo_dev, int64_t n_frames, int height, int width,
                   int bits, const int32_t* bg_dev, const int32_t* partial_dev, int64_t min_signal_count,
                   int32_t diff_thr, const double* gauss_weights_host, int radius, const uint8_t* skip_dev,
-                  double* lines_out_dev, uint8_t* flags_out_dev, void* stream);
+                  double* lines_out_dev, uint8_t* flags_out_dev, int32_t* scratch_dev, void* stream);
 int ff_head_track(const double* lines_dev, const uint8_t* flags_dev, int64_t n_frames, int64_t first_frame,
                   int width, int32_t edge_margin_px, int32_t max_displacement_px, int32_t search_window_px,
                   double min_gradient_strength, double sobel_threshold_fraction, int32_t exit_margin_px,
