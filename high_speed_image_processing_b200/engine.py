@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Optional, Sequence, Union
 
@@ -172,6 +173,12 @@ class FlameFrontEngine:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self._host_chunk_bytes = int(host_chunk_bytes)
+        # ff_process_host copies pageable (memory-mapped) sources into pinned bounce buffers with a
+        # thread pool, by default half the host's cores; under torchrun share the cores between ranks
+        if "FF_HOST_COPY_THREADS" not in os.environ and os.environ.get("LOCAL_WORLD_SIZE", "1").isdigit():
+            ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+            if ranks > 1:
+                os.environ["FF_HOST_COPY_THREADS"] = str(max(1, min(8, (os.cpu_count() or 2) // ranks)))
         self._host_ctx: Optional[C.c_void_p] = None
         self.launches = 0                             # kernels launched through this engine
         self._side_stream = None

@@ -157,13 +157,13 @@ def build_rows(video: PhotonVideo, pos_px: np.ndarray, calibration: float, offse
 
 
 def process_video(video: PhotonVideo, config: VideoSourceConfig, calibration: float, offset: float,
-                  engine=None, exchange=None, residency: str = "auto",
-                  device_budget_bytes: int = 64 << 30) -> VideoResult:
+                  engine=None, exchange=None, residency: str = "auto") -> VideoResult:
     """Run the flame-front path on one recording.
 
-    ``residency``: "device" uploads the (rank's) packed frames once and runs the
-    device-resident kernels; "host" streams chunks from the mmapped file through
-    ``ff_process_host``; "auto" picks "device" when the range fits ``device_budget_bytes``.
+    ``residency``: "host" (= "auto") streams chunks from host memory through ``ff_process_host``
+    - the memory-mapped file via threaded pinned bounce buffers, or a ``pin_memory()``-staged
+    recording in place; "device" uploads the (rank's) packed frames once and runs the
+    device-resident kernels.
     ``exchange`` (a ``sharding.RangeExchange``) splits the clip into contiguous frame ranges
     across ranks; results are identical on every rank.
     """
@@ -200,29 +200,40 @@ def process_video(video: PhotonVideo, config: VideoSourceConfig, calibration: fl
             halo_idx -= 1
     halo_np = video.raw_frames(halo_idx, halo_idx + 1) if halo_idx >= 0 else None
 
-    nbytes = (b - a) * video.frame_store.frame_bytes
     multi = exchange is not None and exchange.size > 1
     if residency == "auto":
-        # pinned recordings stream best chunk by chunk (copies overlap the kernels, nothing is copied
-        # past the exit frame); pageable ones go up in one staged copy when they fit
-        pinned = getattr(video.frame_store, "is_pinned", False)
-        residency = "device" if ((nbytes <= device_budget_bytes and not pinned) or multi) else "host"
+        # stream from host memory chunk by chunk: copies overlap the kernels, nothing is copied past
+        # the exit frame, pinned recordings are DMA'd in place and memory-mapped (pageable) ones go
+        # through ff_process_host's threaded bounce buffers
+        residency = "host"
     if residency not in ("device", "host"):
         raise ValueError("residency must be 'auto', 'device' or 'host'")
+    skip_range = None if skip_np is None else skip_np[a:b]
 
     if multi:
-        # every rank fills its range block in place; one exchange kernel per rank finishes the clip
+        # every rank handles its contiguous range; one exchange kernel per rank finishes the clip
         if exchange.engine is None:
             exchange.engine = eng
-        blk = exchange.begin(n, eng.device)
-        if b - a > 0:
-            frames_dev = torch.from_numpy(np.ascontiguousarray(video.raw_frames(a, b))).to(eng.device)
-            halo_dev = None if halo_np is None else torch.from_numpy(np.ascontiguousarray(halo_np)).to(eng.device)
-            skip_dev = None if skip_np is None else torch.from_numpy(skip_np[a:b].copy()).to(eng.device)
-            eng.process_range(frames_dev, b - a, h, w, bits, params, scalars, bg_dev, first_frame=a,
-                              halo=halo_dev, skip=skip_dev, truncate=False, pos_out=blk.pos,
-                              counts_out=blk.counts, first_exit=blk.first_exit)
-        g = exchange.finish(blk)
+        if residency == "device":       # range uploaded once; ff_detect fills the range block in place
+            blk = exchange.begin(n, eng.device)
+            if b - a > 0:
+                frames_dev = torch.from_numpy(np.ascontiguousarray(video.raw_frames(a, b))).to(eng.device)
+                halo_dev = None if halo_np is None else torch.from_numpy(np.ascontiguousarray(halo_np)).to(eng.device)
+                skip_dev = None if skip_range is None else torch.from_numpy(skip_range.copy()).to(eng.device)
+                eng.process_range(frames_dev, b - a, h, w, bits, params, scalars, bg_dev, first_frame=a,
+                                  halo=halo_dev, skip=skip_dev, truncate=False, pos_out=blk.pos,
+                                  counts_out=blk.counts, first_exit=blk.first_exit)
+            g = exchange.finish(blk)
+        else:                           # range streamed from host memory
+            if b - a > 0:
+                hres = eng.process_host(video.raw_frames(a, b), b - a, h, w, bits, params, scalars, first_frame=a,
+                                        halo=halo_np, skip=skip_range)
+                pos_l, cnt_l, fe_l = hres.pos, hres.counts, hres.first_exit
+            else:
+                pos_l, cnt_l, fe_l = np.empty(0, np.int32), np.empty(0, np.int32), FF_NO_EXIT
+            g = exchange.finish_arrays(torch.from_numpy(pos_l).to(eng.device),
+                                       torch.tensor([fe_l], dtype=torch.int32, device=eng.device), n,
+                                       counts_local=torch.from_numpy(cnt_l).to(eng.device))
         pos_np, cnt_np, first_exit = g.pos.cpu().numpy(), g.counts.cpu().numpy(), g.first_exit
         exchange.check()
     elif residency == "device":
@@ -233,7 +244,7 @@ def process_video(video: PhotonVideo, config: VideoSourceConfig, calibration: fl
         first_exit = int(res.first_exit.cpu().item())
     else:
         hres = eng.process_host(video.raw_frames(a, b), b - a, h, w, bits, params, scalars, first_frame=a,
-                                halo=halo_np, skip=None if skip_np is None else skip_np[a:b])
+                                halo=halo_np, skip=skip_range)
         pos_np, cnt_np, first_exit = hres.pos, hres.counts, hres.first_exit
 
     kb_min = eng_min_signal(params, h * w)

@@ -62,6 +62,9 @@ def main() -> None:
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--check", type=int, default=3, help="clips per rank verified against the oracle")
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--no-pin", action="store_true", help="leave the recordings memory-mapped (pageable) instead of "
+                    "staging them in pinned memory: the page-cache -> GPU path a plain script would take")
+    ap.add_argument("--residency", default="auto", choices=["auto", "device", "host"])
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -96,15 +99,22 @@ def main() -> None:
     assert len(coll) == args.clips, f"expected {args.clips} recordings, found {len(coll)}"
     cfgs = [clip_config(i) for i in range(args.clips)]
     t0 = time.perf_counter()
-    for i in mine:
-        coll[i].pin_memory()
+    if not args.no_pin:
+        for i in mine:
+            coll[i].pin_memory()
     stage_s = time.perf_counter() - t0
     my_bytes = sum(coll[i].frame_store.nbytes_raw for i in mine)
     total_frames = sum(len(v) for v in coll)
     total_bytes = sum(v.frame_store.nbytes_raw for v in coll)
 
+    from high_speed_image_processing_b200.process_videos import process_video
+
+    def per_video(video, cfg, cal, off):
+        return process_video(video, cfg, cal, off, engine=eng, exchange=None, residency=args.residency)
+
     def run():
-        return process_collection(coll, cfgs, engine=eng, exchange=exchange if world > 1 else None)
+        return process_collection(coll, cfgs, engine=eng, exchange=exchange if world > 1 else None,
+                                  per_video=per_video)
 
     results = run()                                   # warm-up (allocations, contexts)
     torch.cuda.synchronize()
@@ -146,7 +156,7 @@ def main() -> None:
         n_rows = sum(len(r.rows) for r in results.values())
         exits = sum(1 for r in results.values() if r.first_exit is not None)
         print(json.dumps({
-            "config": "C5", "clips": args.clips, "frames_per_clip": args.frames, "n_gpus": world,
+            "config": "C5", "pinned": not args.no_pin, "residency": args.residency, "clips": args.clips, "frames_per_clip": args.frames, "n_gpus": world,
             "total_frames": total_frames, "total_gb": total_bytes / 1e9,
             "sharding": "whole videos, size-balanced (assign_videos)", "seconds": sec,
             "frames_per_s": total_frames / sec, "gbs_aggregate": total_bytes / sec / 1e9,

@@ -84,6 +84,38 @@ def main() -> None:
                                            "finish_us_min": lat[0] if lat else None, "samples": len(lat)}
         ex.close()
 
+    # ---- the drop-in driver on a file, range-sharded, both residencies ------------------------------
+    import tempfile
+    from high_speed_image_processing_b200.photron import open_video
+    from high_speed_image_processing_b200.process_videos import VideoSourceConfig, process_video
+    spec = syn.SyntheticSpec(width=512, height=64, n_frames=301, style="nova", t_enter=15.0, velocity=2.5, seed=5)
+    frames = syn.render_frames(spec)
+    want = fo.process_clip(frames, fo.ClipParams(method="half_maximum"))
+    root = [tempfile.mkdtemp(prefix="ff_xchg_") if rank == 0 else None]
+    dist.broadcast_object_list(root, src=0)
+    if rank == 0:
+        syn.write_clip(root[0], "run-1-", spec, frames=frames)
+    dist.barrier()
+    cfg = VideoSourceConfig(name="t")
+    cfg.detection_method = "half_maximum"
+    cfg.skip_frames = [40, 41]
+    want_skip = fo.process_clip(frames, fo.ClipParams(method="half_maximum", skip_frames=[40, 41]))
+    ex = RangeExchange(engine=eng)
+    for residency in ("host", "device"):
+        with open_video(f"{root[0]}/run-1-.cihx") as video:
+            res = process_video(video, cfg, 0.001, 0.5, engine=eng, exchange=ex, residency=residency)
+        same = ([(r[0], r[2]) for r in res.rows] == want_skip.records and
+                res.first_exit == (want_skip.first_exit if want_skip.first_exit < spec.n_frames else None))
+        if not same:
+            report["ok"] = False
+            print(f"[rank {rank}] MISMATCH process_video residency={residency}", flush=True)
+    report["process_video_sharded"] = "host+device residency vs oracle rows"
+    ex.close()
+    dist.barrier()
+    if rank == 0:
+        import shutil
+        shutil.rmtree(root[0], ignore_errors=True)
+
     flag = torch.tensor([1 if report["ok"] else 0], device=device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     report["ok"] = bool(flag.item())
