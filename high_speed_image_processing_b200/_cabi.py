@@ -73,6 +73,7 @@ SIGNATURES = {
                              _vp, _vp, _vp]),
     "ff_host_ctx_create": (_int, [_int, _i64, C.POINTER(_vp)]),
     "ff_host_ctx_destroy": (_int, [_vp]),
+    "ff_host_upload": (_int, [_vp, _vp, _vp, _i64]),
     "ff_process_host": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _int, _int, _i32, _i32, _i64, _int, _int, _i32,
                                _i32, _i32, _i32, _i32, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_i32)]),
 }

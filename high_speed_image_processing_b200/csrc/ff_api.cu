@@ -359,6 +359,41 @@ int ff_host_ctx_create(int device, int64_t chunk_bytes, ff_host_ctx** ctx_out) {
 
 int ff_host_ctx_destroy(ff_host_ctx* ctx) { return ctx_release(ctx); }
 
+int ff_host_upload(ff_host_ctx* c, const void* src_host, void* dst_dev, int64_t bytes) {
+  if (c == nullptr || src_host == nullptr || dst_dev == nullptr || bytes < 0) return FF_ERR_INVALID;
+  if (bytes == 0) return FF_OK;
+  FF_CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t cs = c->copy_stream;
+  cudaPointerAttributes attr{};
+  bool pageable = true;
+  if (cudaPointerGetAttributes(&attr, src_host) == cudaSuccess)
+    pageable = !(attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+  else
+    cudaGetLastError();
+  const uint8_t* src = static_cast<const uint8_t*>(src_host);
+  uint8_t* dst = static_cast<uint8_t*>(dst_dev);
+  if (!pageable) {
+    FF_CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, cs));
+    FF_CUDA_TRY(cudaStreamSynchronize(cs));
+    return FF_OK;
+  }
+  const int64_t piece = c->chunk_bytes > 0 ? c->chunk_bytes : (64 << 20);
+  int rc = ctx_reserve_bounce(c, piece);
+  if (rc != FF_OK) return rc;
+  bool used[2] = {false, false};
+  int b = 0;
+  for (int64_t off = 0; off < bytes; off += piece, b ^= 1) {
+    const int64_t n = off + piece <= bytes ? piece : bytes - off;
+    if (used[b]) FF_CUDA_TRY(cudaEventSynchronize(c->bounce_free[b]));
+    c->pool->copy(c->bounce[b], src + off, (size_t)n);      // overlaps the previous piece's DMA
+    FF_CUDA_TRY(cudaMemcpyAsync(dst + off, c->bounce[b], (size_t)n, cudaMemcpyHostToDevice, cs));
+    FF_CUDA_TRY(cudaEventRecord(c->bounce_free[b], cs));
+    used[b] = true;
+  }
+  FF_CUDA_TRY(cudaStreamSynchronize(cs));
+  return FF_OK;
+}
+
 int ff_process_host(ff_host_ctx* c, const void* frames_host, const void* halo_host, int64_t n_frames,
                     int64_t first_frame, int height, int width, int bits, int32_t bg, int32_t empty_thr,
                     int64_t min_signal_count, int method, int use_frame_diff, int32_t diff_thr,

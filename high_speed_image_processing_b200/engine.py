@@ -474,6 +474,24 @@ class FlameFrontEngine:
         self.launches += 1
 
     # ------------------------------------------------------------------ host-resident clips
+    def _ctx(self) -> C.c_void_p:
+        if self._host_ctx is None:
+            ctx = C.c_void_p()
+            _cabi.check(self._lib.ff_host_ctx_create(self.device.index, self._host_chunk_bytes, C.byref(ctx)),
+                        "ff_host_ctx_create")
+            self._host_ctx = ctx
+        return self._host_ctx
+
+    def upload(self, host: Union[np.ndarray, torch.Tensor]) -> torch.Tensor:
+        """Host bytes -> a uint8 device tensor (``ff_host_upload``): in place DMA for pinned memory,
+        threaded pinned bounce buffers for pageable memory such as the memory-mapped .mraw file."""
+        ptr, nbytes, _keep = _host_buffer(host)
+        out = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        if nbytes:
+            torch.cuda.current_stream(self.device).synchronize()     # the copy runs on the context's own stream
+            _cabi.check(self._lib.ff_host_upload(self._ctx(), ptr, out.data_ptr(), nbytes), "ff_host_upload")
+        return out
+
     def process_host(self, frames: Union[np.ndarray, torch.Tensor], n_frames: int, height: int, width: int,
                      bits: int, params: DetectionParams, scalars: ClipScalars, *, first_frame: int = 0,
                      halo: Union[np.ndarray, torch.Tensor, None] = None,
@@ -499,11 +517,7 @@ class FlameFrontEngine:
             raise ValueError("Shape of array too small to calculate a numerical gradient, "
                              "at least 2 elements are required.")
         kb = derive_kernel_bounds(scalars, params, height * width)
-        if self._host_ctx is None:
-            ctx = C.c_void_p()
-            _cabi.check(self._lib.ff_host_ctx_create(self.device.index, self._host_chunk_bytes, C.byref(ctx)),
-                        "ff_host_ctx_create")
-            self._host_ctx = ctx
+        self._ctx()
         pos = np.empty(n_frames, dtype=np.int32)
         counts = np.empty(n_frames, dtype=np.int32)
         done = C.c_int64(0)

@@ -200,11 +200,9 @@ class FrameStore:
         if self.bits == 16:
             return np.array(self.raw_frames(start, stop).view("<u2").reshape(n, h, w))
         # packed 12-bit: decode on the GPU (stage-1 kernel); no CPU decoder exists here
-        import torch
         from .engine import get_engine
         eng = get_engine()
-        packed = torch.from_numpy(np.ascontiguousarray(self.raw_frames(start, stop))).to(eng.device)
-        return eng.unpack(packed, n, h, w, 12).cpu().numpy()
+        return eng.unpack(eng.upload(self.raw_frames(start, stop)), n, h, w, 12).cpu().numpy()
 
     def __getitem__(self, key):
         n = self.shape[0]

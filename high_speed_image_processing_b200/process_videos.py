@@ -183,7 +183,7 @@ def process_video(video: PhotonVideo, config: VideoSourceConfig, calibration: fl
     params = config.detection_params()
 
     # per-clip scalars from frame 0 (every rank reads frame 0 itself: 1 frame of H2D)
-    frame0 = torch.from_numpy(np.ascontiguousarray(video.raw_frames(0, 1))).to(eng.device)
+    frame0 = eng.upload(video.raw_frames(0, 1))
     scalars, bg_dev = eng.clip_scalars(frame0, h, w, bits)
 
     skip_np = None
@@ -217,8 +217,8 @@ def process_video(video: PhotonVideo, config: VideoSourceConfig, calibration: fl
         if residency == "device":       # range uploaded once; ff_detect fills the range block in place
             blk = exchange.begin(n, eng.device)
             if b - a > 0:
-                frames_dev = torch.from_numpy(np.ascontiguousarray(video.raw_frames(a, b))).to(eng.device)
-                halo_dev = None if halo_np is None else torch.from_numpy(np.ascontiguousarray(halo_np)).to(eng.device)
+                frames_dev = eng.upload(video.raw_frames(a, b))
+                halo_dev = None if halo_np is None else eng.upload(halo_np)
                 skip_dev = None if skip_range is None else torch.from_numpy(skip_range.copy()).to(eng.device)
                 eng.process_range(frames_dev, b - a, h, w, bits, params, scalars, bg_dev, first_frame=a,
                                   halo=halo_dev, skip=skip_dev, truncate=False, pos_out=blk.pos,
@@ -237,7 +237,7 @@ def process_video(video: PhotonVideo, config: VideoSourceConfig, calibration: fl
         pos_np, cnt_np, first_exit = g.pos.cpu().numpy(), g.counts.cpu().numpy(), g.first_exit
         exchange.check()
     elif residency == "device":
-        frames_dev = torch.from_numpy(np.ascontiguousarray(video.raw_frames(a, b))).to(eng.device)
+        frames_dev = eng.upload(video.raw_frames(a, b))
         skip_dev = None if skip_np is None else torch.from_numpy(skip_np).to(eng.device)
         res = eng.process_range(frames_dev, n, h, w, bits, params, scalars, bg_dev, skip=skip_dev)
         pos_np, cnt_np = res.pos.cpu().numpy(), res.counts.cpu().numpy()
@@ -265,7 +265,7 @@ def _process_video_head(video: PhotonVideo, config: VideoSourceConfig, calibrati
 
     hp = config.head_params
     n, (h, w), bits = len(video), video.frame_shape, video.storage_bits
-    frames_dev = torch.from_numpy(np.ascontiguousarray(video.raw_frames(0, n))).to(eng.device)
+    frames_dev = eng.upload(video.raw_frames(0, n))
     skip_dev = skip_np = None
     if config.skip_frames:
         skip_np = np.zeros(n, dtype=np.uint8)

@@ -215,7 +215,8 @@ int ff_head_track(const double* lines_dev, const uint8_t* flags_dev, int64_t n_f
  * (scripts/process_videos.py:1441-1516) for one video / one contiguous frame range.
  * Frames are copied in chunks on a copy stream, double-buffered against the kernels; once a
  * finished chunk has reported an exit frame no further chunks are copied (the reference
- * `break`s at :1494).  Blocking: returns when pos_out_host/count_out_host are complete.
+ * `break`s at :1494).  Pageable sources go through the threaded bounce buffers described at
+ * ff_host_upload.  Blocking: returns when pos_out_host/count_out_host are complete.
  *   ctx               from ff_host_ctx_create (owns staging buffers, streams, events)
  *   frames_host       n_frames frames; halo_host the frame before them or NULL
  *   bg                background scalar by value (host already synchronised on it)
@@ -225,6 +226,13 @@ int ff_head_track(const double* lines_dev, const uint8_t* flags_dev, int64_t n_f
 typedef struct ff_host_ctx ff_host_ctx;
 int ff_host_ctx_create(int device, int64_t chunk_bytes, ff_host_ctx** ctx_out);
 int ff_host_ctx_destroy(ff_host_ctx* ctx);
+/* Blocking host -> device copy of `bytes` bytes for the device-resident entry points.  Pinned or
+ * registered sources are DMA'd in place; pageable ones (e.g. np.memmap of the .mraw file, the
+ * array the reference gets from pyMRAW at src/photron/video.py:332) are moved through the
+ * context's pinned bounce buffers, filled by FF_HOST_COPY_THREADS threads (default: half the
+ * cores) while the previous piece's DMA is in flight - 40 GB/s from the page cache against
+ * 11 GB/s for a plain cudaMemcpy of pageable memory on the measured box.                        */
+int ff_host_upload(ff_host_ctx* ctx, const void* src_host, void* dst_dev, int64_t bytes);
 int ff_process_host(ff_host_ctx* ctx,
                     const void* frames_host, const void* halo_host, int64_t n_frames,
                     int64_t first_frame, int height, int width, int bits,
