@@ -352,6 +352,23 @@ def own_arm(args) -> None:
     clocks = sampler.stop() if rank == 0 else {}
     assert fe_h == first_exit and np.array_equal(pos_h, pos), "host-streamed result differs from device-resident"
     e2e_value = total / e2e_sec
+    # the same call on a PAGEABLE copy of the clip (what np.memmap of the .mraw file is): the library
+    # stages it through pinned bounce buffers with a thread pool.  Informational, rank 0 at N=1.
+    pageable = None
+    if world == 1 and not args.no_pageable:
+        host_np = np.empty(fpr * fb, dtype=np.uint8)
+        host_np[:] = host.numpy()
+        f0 = frame0_host.to(device)
+        sc, _ = eng.clip_scalars(f0, h, w, 12)
+        eng.process_host(host_np, fpr, h, w, 12, params, sc)
+        tp = time.perf_counter()
+        for _ in range(2):
+            hp = eng.process_host(host_np, fpr, h, w, 12, params, sc)
+        tp = (time.perf_counter() - tp) / 2
+        assert hp.first_exit == first_exit and np.array_equal(hp.pos, pos)
+        pageable = {"value": fpr / tp, "unit": UNIT, "h2d_gbs": fpr * fb / tp / 1e9,
+                    "copy_threads": int(os.environ.get("FF_HOST_COPY_THREADS", (os.cpu_count() or 2) // 2))}
+        del host_np
     # PCIe / host-memory roofline for the end-to-end path: plain pinned-host -> device copies of the
     # same buffer, (a) this rank alone is not separable under torchrun, so (b) ALL ranks at once
     # behind a barrier - what the box sustains when every GPU pulls from host memory together -
@@ -427,7 +444,7 @@ def own_arm(args) -> None:
                     "h2d_gbs_per_gpu": h2d / e2e_sec / 1e9, "h2d_peak_gbs_measured": h2d_peak,
                     "h2d_peak_how": "pinned copy of the same buffer, all ranks concurrently, slowest rank",
                     "frac_of_h2d_peak": (h2d / e2e_sec / 1e9) / h2d_peak if h2d_peak else None,
-                    "launches_per_step": launches_e2e},
+                    "launches_per_step": launches_e2e, "pageable_source": pageable},
             "gpu_launches": launches,
             "clocks": clocks,
             "result": {"first_exit_frame": first_exit, "detections": int(det.size)},
@@ -450,6 +467,7 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--sample-frames", type=int, default=4000, help="CPU baseline sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-source end-to-end leg")
     ap.add_argument("--clock-period-ms", type=int, default=100, help="nvidia-smi sampling period (0 = off)")
     ap.add_argument("--exchange", choices=["auto", "peer", "gathered"], default="auto",
                     help="multi-GPU block transport: peer memory over NVLink (CUDA IPC) or one NCCL all-gather")

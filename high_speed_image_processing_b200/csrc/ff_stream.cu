@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const StreamParams p) 
   }  // segments
 }
 
-// ---- count-only kernel for packed 12-bit (the headline configuration) --------------------------
+// ---- count-only kernel (packed 12-bit is the headline configuration; 8- and 16-bit share it) -----
 // No output but the above-noise counts, so the pixels are never extracted.  Compared with the
 // general template: a dedicated producer warp feeds a full/empty mbarrier ring (consumer warps
 // never meet at a CTA-wide barrier and can run up to kCountStages items apart); every thread
@@ -340,7 +340,9 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const StreamParams p) 
 //                                                                              is dominated)
 //   B lanes = (b1<<8 | b2) & 0x0FFF = lo       lo > c  directly
 // 4 PRMT + 2 LOP3 + 6 DPX + 2 IADD3 per 8 pixels (the carry-chain form needs 20).
-constexpr int kCountTileBytes = 4 * kThreads * 12;        // 1024 groups = 8192 px
+// 16-bit pixels already are 16x2 lanes (unsigned compare: max, add, min); 8-bit pixels are widened
+// with two PRMTs per word.  Those two read 16-byte pieces t, t+256, ... (conflict-free LDS.128).
+constexpr int kCountTileBytes = 4 * kThreads * 12;        // 1024 groups = 8192 px (12-bit)
 constexpr int kCountThreads = kThreads + 32;              // 8 consumer warps + 1 producer warp
 constexpr int kCountCtasPerSm = 2;
 
@@ -359,10 +361,12 @@ __device__ __forceinline__ uint32_t count12x8_simd(uint32_t w0, uint32_t w1, uin
   return (fa0 + fa1) + (fb0 + fb1);
 }
 
-template <int kCountStages>
+template <int BITS, int kCountStages>
 __global__ void __launch_bounds__(kCountThreads) count12_kernel(const StreamParams p) {
+  constexpr int kTileBytes = 4 * kThreads * BITS;
+  constexpr int kMaxPx = BITS == 8 ? 255 : (BITS == 12 ? 4095 : 65535);
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kCountStages * kCountTileBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kCountStages * kTileBytes);
   uint64_t* empty = full + kCountStages;
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -398,9 +402,9 @@ __global__ void __launch_bounds__(kCountThreads) count12_kernel(const StreamPara
         const int s = it % kCountStages;
         mbar_wait(&empty[s], ((it / kCountStages) & 1) ^ 1);   // first pass: fresh barriers pass at once
         const int64_t g0 = (int64_t)tile * (4 * kThreads);
-        const uint32_t bytes = (uint32_t)min((int64_t)(4 * kThreads), groups_per_frame - g0) * 12u;
+        const uint32_t bytes = (uint32_t)min((int64_t)(4 * kThreads), groups_per_frame - g0) * (uint32_t)BITS;
         mbar_arrive_expect_tx(&full[s], bytes);
-        bulk_g2s(smem + s * kCountTileBytes, p.frames + (int64_t)f * p.frame_bytes + (int64_t)tile * kCountTileBytes,
+        bulk_g2s(smem + s * kTileBytes, p.frames + (int64_t)f * p.frame_bytes + (int64_t)tile * kTileBytes,
                  bytes, &full[s], policy);
         advance();
       }
@@ -411,8 +415,8 @@ __global__ void __launch_bounds__(kCountThreads) count12_kernel(const StreamPara
   // ---- consumers ---------------------------------------------------------------------------------
   const int bg = __ldg(p.bg_dev);
   const int ethr = p.empty_thr >= 0 ? p.empty_thr : max(10, bg >> 1);
-  const uint32_t c = (uint32_t)min(bg + ethr, 4095);       // 12-bit pixels never exceed 4095
-  const uint32_t kA = (c << 4) | 15u;
+  const uint32_t c = (uint32_t)min((int64_t)bg + ethr, (int64_t)kMaxPx);       // no pixel exceeds kMaxPx
+  const uint32_t kA = BITS == 12 ? ((c << 4) | 15u) : c;
   const uint32_t kA2 = kA * 0x00010001u;
   const uint32_t nkA2 = ((0x10000u - kA) & 0xFFFFu) * 0x00010001u;
   const uint32_t nc2 = ((0x10000u - c) & 0xFFFFu) * 0x00010001u;
@@ -423,11 +427,34 @@ __global__ void __launch_bounds__(kCountThreads) count12_kernel(const StreamPara
     mbar_wait(&full[s], (it / kCountStages) & 1);
     const int tile_groups = (int)min((int64_t)(4 * kThreads), groups_per_frame - (int64_t)tile * (4 * kThreads));
     uint32_t acc = 0;
-    if (my_group < tile_groups) {        // groups per frame are a multiple of 4: all four or none
-      const uint4* q = reinterpret_cast<const uint4*>(smem + s * kCountTileBytes + tid * 48);
-      const uint4 q0 = q[0], q1 = q[1], q2 = q[2];
-      acc = count12x8_simd(q0.x, q0.y, q0.z, kA2, nkA2, nc2) + count12x8_simd(q0.w, q1.x, q1.y, kA2, nkA2, nc2) +
-            count12x8_simd(q1.z, q1.w, q2.x, kA2, nkA2, nc2) + count12x8_simd(q2.y, q2.z, q2.w, kA2, nkA2, nc2);
+    if (BITS == 12) {
+      if (my_group < tile_groups) {        // groups per frame are a multiple of 4: all four or none
+        const uint4* q = reinterpret_cast<const uint4*>(smem + s * kTileBytes + tid * 48);
+        const uint4 q0 = q[0], q1 = q[1], q2 = q[2];
+        acc = count12x8_simd(q0.x, q0.y, q0.z, kA2, nkA2, nc2) + count12x8_simd(q0.w, q1.x, q1.y, kA2, nkA2, nc2) +
+              count12x8_simd(q1.z, q1.w, q2.x, kA2, nkA2, nc2) + count12x8_simd(q2.y, q2.z, q2.w, kA2, nkA2, nc2);
+      }
+    } else {
+      const uint32_t one2 = 0x00010001u;
+      const int pieces = tile_groups * BITS / 16;                      // 16-byte pieces in this tile
+      const uint4* q = reinterpret_cast<const uint4*>(smem + s * kTileBytes);
+#pragma unroll
+      for (int k = 0; k < kTileBytes / 16 / kThreads; ++k) {
+        const int i = tid + k * kThreads;
+        if (i < pieces) {
+          const uint4 v = q[i];
+          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (BITS == 16) {
+              acc += __viaddmin_u16x2(__vimax3_u16x2(w4[j], kA2, kA2), nkA2, one2);
+            } else {
+              acc += __viaddmin_s16x2_relu(__byte_perm(w4[j], 0u, 0x4140), nc2, one2) +
+                     __viaddmin_s16x2_relu(__byte_perm(w4[j], 0u, 0x4342), nc2, one2);
+            }
+          }
+        }
+      }
     }
     int cnt = (int)(acc & 0xFFFFu) + (int)(acc >> 16);
     cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);      // also orders every lane's smem reads before the release
@@ -441,15 +468,15 @@ __global__ void __launch_bounds__(kCountThreads) count12_kernel(const StreamPara
 
 int sm_count_cached();
 
-template <int kCountStages>
+template <int BITS, int kCountStages>
 int launch_count12(StreamParams p, cudaStream_t st) {
-  constexpr int kSmem = kCountStages * kCountTileBytes + 2 * kCountStages * 8;
+  constexpr int kSmem = kCountStages * (4 * kThreads * BITS) + 2 * kCountStages * 8;
   static bool configured[64] = {false};
   static int ctas_per_sm[64] = {0};
   int dev = 0;
   FF_CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return FF_ERR_INVALID;
-  auto kern = count12_kernel<kCountStages>;
+  auto kern = count12_kernel<BITS, kCountStages>;
   if (!configured[dev]) {
     FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     int occ = 0;
@@ -473,7 +500,7 @@ int launch_count12(StreamParams p, cudaStream_t st) {
   return FF_OK;
 }
 
-// ---- packed 12-bit with outputs: uint16 difference image and / or decoded uint16 pixels ----------
+// ---- uint16 difference image and / or decoded uint16 pixels (8-bit, packed 12-bit, 16-bit input) ---
 // Same skeleton as count12_kernel (producer warp, full/empty ring, no CTA-wide barrier), same
 // pixel ownership as the general template (thread t owns groups t, t+256, t+512, t+768 of the
 // tile, so every warp-level 16-byte store covers 512 contiguous bytes) and all arithmetic on
@@ -483,12 +510,36 @@ int launch_count12(StreamParams p, cudaStream_t st) {
 // version of this kernel at 0.85 of the copy rate (ncu: ALU 71 % busy, FMA 6 %).
 // Item order: tile-major with a halo item per segment when the difference is retained (the
 // carry needs consecutive frames of one tile); frame-major otherwise.
+// 8-bit pixels are widened to 16x2 lanes with two PRMTs per word and share the signed-lane
+// arithmetic with 12-bit (every value fits 13 bits).  Full-range 16-bit pixels do not: there the
+// lanes are unsigned and every subtraction is "max, then subtract" (sub = max(x,bg) - bg,
+// relu(d) = max(sub,prev) - prev, ...), which cannot borrow across lanes.
 constexpr int kOutThreads = kThreads + 32;
 
-template <bool COUNT, bool DIFF, bool DECODED, int STAGES>
-__global__ void __launch_bounds__(kOutThreads) stream12_kernel(const StreamParams p) {
+template <int BITS>
+__device__ __forceinline__ void load_lanes(const uint8_t* stage, int g, uint32_t (&x)[4]) {
+  if (BITS == 12) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(stage) + 3 * g;
+    decode12x8_16x2(w[0], w[1], w[2], x);
+  } else if (BITS == 16) {
+    const uint4 q = reinterpret_cast<const uint4*>(stage)[g];
+    x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+  } else {
+    const uint2 q = reinterpret_cast<const uint2*>(stage)[g];
+    x[0] = __byte_perm(q.x, 0u, 0x4140);   // b0 0 b1 0  (LSB first)
+    x[1] = __byte_perm(q.x, 0u, 0x4342);
+    x[2] = __byte_perm(q.y, 0u, 0x4140);
+    x[3] = __byte_perm(q.y, 0u, 0x4342);
+  }
+}
+
+template <int BITS, bool COUNT, bool DIFF, bool DECODED, int STAGES>
+__global__ void __launch_bounds__(kOutThreads) streamx_kernel(const StreamParams p) {
+  constexpr int kTileBytes = 4 * kThreads * BITS;          // 1024 groups of 8 pixels
+  constexpr bool kUnsigned = BITS == 16;
+  constexpr int kMaxPx = BITS == 8 ? 255 : (BITS == 12 ? 4095 : 65535);
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * kCountTileBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * kTileBytes);
   uint64_t* empty = full + STAGES;
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -515,23 +566,31 @@ __global__ void __launch_bounds__(kOutThreads) stream12_kernel(const StreamParam
 
   // consumer constants
   int bg = 0;
-  uint32_t nc2 = 0, nbg2 = 0, k2 = 0;
+  uint32_t nc2 = 0, nbg2 = 0, k2 = 0, c2 = 0, bg2 = 0, t2 = 0;
   int tm1 = 0;
   const uint32_t one2 = 0x00010001u;
   if (!producer && (COUNT || DIFF)) {
-    bg = min(__ldg(p.bg_dev), 4095);                     // 12-bit pixels: a larger bg zeroes everything anyway
+    bg = min(__ldg(p.bg_dev), kMaxPx);                   // a larger bg zeroes everything anyway
     const int ethr = p.empty_thr >= 0 ? p.empty_thr : max(10, __ldg(p.bg_dev) >> 1);
-    const uint32_t c = (uint32_t)min((int64_t)__ldg(p.bg_dev) + ethr, (int64_t)4095);
-    nc2 = ((0x10000u - c) & 0xFFFFu) * one2;             // -c per lane
-    nbg2 = ((0x10000u - (uint32_t)bg) & 0xFFFFu) * one2;  // -bg per lane
-    tm1 = min(max(p.diff_thr, 0) - 1, 8190);             // thr-1 (thr > 4095 keeps nothing)
-    k2 = ((uint32_t)(-(0x4000 + tm1)) & 0xFFFFu) * one2;  // relu(E + k) = relu(d - (thr-1))
+    const uint32_t c = (uint32_t)min((int64_t)__ldg(p.bg_dev) + ethr, (int64_t)kMaxPx);   // no pixel exceeds kMaxPx
+    if (kUnsigned) {
+      c2 = c * one2;
+      nc2 = ((0x10000u - c) & 0xFFFFu) * one2;
+      bg2 = (uint32_t)bg * one2;
+      tm1 = min(max(p.diff_thr - 1, 0), 65535);          // lanes hold relu(d): thr 0 and 1 coincide there
+      t2 = (uint32_t)tm1 * one2;
+    } else {
+      nc2 = ((0x10000u - c) & 0xFFFFu) * one2;             // -c per lane
+      nbg2 = ((0x10000u - (uint32_t)bg) & 0xFFFFu) * one2;  // -bg per lane
+      tm1 = min(max(p.diff_thr, 0) - 1, 8190);             // thr-1 (thr > 4095 keeps nothing)
+      k2 = ((uint32_t)(-(0x4000 + tm1)) & 0xFFFFu) * one2;  // relu(E + k) = relu(d - (thr-1))
+    }
   }
-  uint32_t pn[4][4];                                      // 0x4000 - (previous frame, bg-subtracted), 16x2
+  uint32_t pn[4][4];       // carry, 16x2: 0x4000 - sub (signed lanes) or sub itself (unsigned lanes)
 #pragma unroll
   for (int k = 0; k < 4; ++k)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) pn[k][j] = 0x40004000u;
+    for (int j = 0; j < 4; ++j) pn[k][j] = kUnsigned ? 0u : 0x40004000u;
   uint32_t git = 0;
 
   while (work < work_end) {
@@ -574,15 +633,15 @@ __global__ void __launch_bounds__(kOutThreads) stream12_kernel(const StreamParam
 
       if (producer) {
         mbar_wait(&empty[s], ph ^ 1u);
-        const uint8_t* src = (is_halo ? halo_ptr : p.frames + (int64_t)f * p.frame_bytes) + (int64_t)t * kCountTileBytes;
-        const uint32_t bytes = (uint32_t)tile_groups * 12u;
+        const uint8_t* src = (is_halo ? halo_ptr : p.frames + (int64_t)f * p.frame_bytes) + (int64_t)t * kTileBytes;
+        const uint32_t bytes = (uint32_t)tile_groups * (uint32_t)BITS;
         mbar_arrive_expect_tx(&full[s], bytes);
-        bulk_g2s(smem + s * kCountTileBytes, src, bytes, &full[s], policy);
+        bulk_g2s(smem + s * kTileBytes, src, bytes, &full[s], policy);
         continue;
       }
 
       mbar_wait(&full[s], ph);
-      const uint32_t* stage = reinterpret_cast<const uint32_t*>(smem + s * kCountTileBytes);
+      const uint8_t* stage = smem + s * kTileBytes;
       const bool skipped = DIFF && !is_halo && p.skip != nullptr && p.skip[f] != 0;
       const bool diff_valid = have_prev && !skipped;
       const int64_t px0 = (int64_t)f * p.px_per_frame + (int64_t)t * (kTileGroups * kGroupPx);
@@ -591,12 +650,13 @@ __global__ void __launch_bounds__(kOutThreads) stream12_kernel(const StreamParam
       for (int k = 0; k < 4; ++k) {
         const int g = tid + k * kThreads;
         if (g < tile_groups) {
-          const uint32_t* w = stage + 3 * g;
           uint32_t x[4];
-          decode12x8_16x2(w[0], w[1], w[2], x);
+          load_lanes<BITS>(stage, g, x);
           if (COUNT) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc2 += __viaddmin_s16x2_relu(x[j], nc2, one2);
+            for (int j = 0; j < 4; ++j)
+              acc2 += kUnsigned ? __viaddmin_u16x2(__vimax3_u16x2(x[j], c2, c2), nc2, one2)   // [x > c], unsigned
+                                : __viaddmin_s16x2_relu(x[j], nc2, one2);                       // [x > c], signed
           }
           if (DECODED && !is_halo)
             __stcs(reinterpret_cast<uint4*>(p.decoded_out + px0 + (int64_t)g * kGroupPx), make_uint4(x[0], x[1], x[2], x[3]));
@@ -604,12 +664,21 @@ __global__ void __launch_bounds__(kOutThreads) stream12_kernel(const StreamParam
             uint32_t o[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint32_t sub2 = __viaddmax_s16x2(x[j], nbg2, 0u);            // max(x - bg, 0)
-              const uint32_t e2 = sub2 + pn[k][j];                                // 0x4000 + d per lane
-              const uint32_t r2 = __viaddmax_s16x2_relu(e2, k2, 0u);              // relu(d - (thr-1))
-              const uint32_t m2 = __vimin_s16x2_relu(r2, one2);                   // [d >= thr]
-              o[j] = r2 + m2 * (uint32_t)tm1;                                     // d where d >= thr, else 0
-              if (!skipped) pn[k][j] = 0x40004000u - sub2;
+              if (kUnsigned) {
+                const uint32_t sub2 = __vimax3_u16x2(x[j], bg2, bg2) - bg2;                 // max(x - bg, 0)
+                const uint32_t rd2 = __vimax3_u16x2(sub2, pn[k][j], pn[k][j]) - pn[k][j];   // relu(d)
+                const uint32_t r2 = __vimax3_u16x2(rd2, t2, t2) - t2;                        // relu(relu(d) - (thr-1))
+                const uint32_t m2 = __vimin3_u16x2(r2, one2, one2);                          // [d >= thr]
+                o[j] = r2 + m2 * (uint32_t)tm1;                                              // d where d >= thr, else 0
+                if (!skipped) pn[k][j] = sub2;
+              } else {
+                const uint32_t sub2 = __viaddmax_s16x2(x[j], nbg2, 0u);            // max(x - bg, 0)
+                const uint32_t e2 = sub2 + pn[k][j];                                // 0x4000 + d per lane
+                const uint32_t r2 = __viaddmax_s16x2_relu(e2, k2, 0u);              // relu(d - (thr-1))
+                const uint32_t m2 = __vimin_s16x2_relu(r2, one2);                   // [d >= thr]
+                o[j] = r2 + m2 * (uint32_t)tm1;                                     // d where d >= thr, else 0
+                if (!skipped) pn[k][j] = 0x40004000u - sub2;
+              }
             }
             if (!is_halo) {
               uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.diff_out) + px0 + (int64_t)g * kGroupPx);
@@ -632,15 +701,15 @@ __global__ void __launch_bounds__(kOutThreads) stream12_kernel(const StreamParam
 
 int sm_count_cached();
 
-template <bool COUNT, bool DIFF, bool DECODED, int STAGES>
-int launch_stream12(StreamParams p, int ctas_cap, cudaStream_t st) {
-  constexpr int kSmem = STAGES * kCountTileBytes + 2 * STAGES * 8;
+template <int BITS, bool COUNT, bool DIFF, bool DECODED, int STAGES>
+int launch_streamx(StreamParams p, int ctas_cap, cudaStream_t st) {
+  constexpr int kSmem = STAGES * (4 * kThreads * BITS) + 2 * STAGES * 8;
   static bool configured[64] = {false};
   static int ctas_per_sm[64] = {0};
   int dev = 0;
   FF_CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return FF_ERR_INVALID;
-  auto kern = stream12_kernel<COUNT, DIFF, DECODED, STAGES>;
+  auto kern = streamx_kernel<BITS, COUNT, DIFF, DECODED, STAGES>;
   if (!configured[dev]) {
     FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     int occ = 0;
@@ -659,20 +728,19 @@ int launch_stream12(StreamParams p, int ctas_cap, cudaStream_t st) {
   return FF_OK;
 }
 
-template <bool COUNT, bool DIFF, bool DECODED>
-int launch_stream12_tuned(const StreamParams& p, cudaStream_t st) {
-  // One CTA per SM with a 5-deep ring (48 KB of reads in flight per SM) is the measured optimum for
-  // the read+write variants - fewer concurrent DRAM streams beat more parallelism (C4 uint16 diff:
-  // 0.85 of the copy rate at 3 CTAs x 4 stages, 0.92 at 1 x 5; profiles/r01_stream12_sweep.txt).
+template <int BITS, bool COUNT, bool DIFF, bool DECODED>
+int launch_streamx_tuned(const StreamParams& p, cudaStream_t st) {
+  // One CTA per SM with a 5-deep ring (48 KB of reads in flight per SM at 12 bits) is the measured
+  // optimum for the read+write variants - fewer concurrent DRAM streams beat more parallelism (C4
+  // uint16 diff: 0.85 of the copy rate at 3 CTAs x 4 stages, 0.92 at 1 x 5;
+  // profiles/r01_stream12_sweep.txt).
   static const int stages = getenv("FF_STREAM12_STAGES") ? atoi(getenv("FF_STREAM12_STAGES")) : 5;   // tuning knobs
   static const int ctas = getenv("FF_STREAM12_CTAS") ? atoi(getenv("FF_STREAM12_CTAS")) : 1;
   switch (stages) {
-    case 2: return launch_stream12<COUNT, DIFF, DECODED, 2>(p, ctas, st);
-    case 3: return launch_stream12<COUNT, DIFF, DECODED, 3>(p, ctas, st);
-    case 6: return launch_stream12<COUNT, DIFF, DECODED, 6>(p, ctas, st);
-    case 8: return launch_stream12<COUNT, DIFF, DECODED, 8>(p, ctas, st);
-    case 4: return launch_stream12<COUNT, DIFF, DECODED, 4>(p, ctas, st);
-    default: return launch_stream12<COUNT, DIFF, DECODED, 5>(p, ctas, st);
+    case 3: return launch_streamx<BITS, COUNT, DIFF, DECODED, 3>(p, ctas, st);
+    case 4: return launch_streamx<BITS, COUNT, DIFF, DECODED, 4>(p, ctas, st);
+    case 6: return launch_streamx<BITS, COUNT, DIFF, DECODED, 6>(p, ctas, st);
+    default: return launch_streamx<BITS, COUNT, DIFF, DECODED, 5>(p, ctas, st);
   }
 }
 
@@ -766,7 +834,6 @@ int launch_stream(StreamParams p, cudaStream_t st) {
     // measured on C4, float64 difference 0.86 -> 0.95 of the copy rate at 1 CTA/SM, float32
     // 0.82 -> 0.87 at 2 (profiles/r01_count12_sweep.txt).  FF_STREAM_CTAS overrides (tuning knob).
     int cap = DIFF == FF_DIFF_F64 ? 1 : (DIFF == FF_DIFF_F32 ? 2 : occ);
-    if (BITS == 16 && DIFF == FF_DIFF_NONE && !DECODED && K == 4) cap = 2;   // 16-bit counts: 0.95 -> 1.08 (96 KB in flight)
     if (const char* e = getenv("FF_STREAM_CTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;
     if (occ > cap) occ = cap;
     ctas_per_sm[dev] = occ > 0 ? occ : 1;
@@ -867,23 +934,27 @@ int stream_frames_impl(const void* frames, const void* halo, int64_t n_frames, i
   const bool aligned = ((reinterpret_cast<uintptr_t>(frames) | reinterpret_cast<uintptr_t>(halo) |
                          reinterpret_cast<uintptr_t>(diff_out) | reinterpret_cast<uintptr_t>(decoded_out)) & 15u) == 0;
   if (t.fast && aligned) {
-    if (bits == 12 && diff_dtype == FF_DIFF_NONE && decoded_out == nullptr && t.k == 4) {
+    if (diff_dtype == FF_DIFF_NONE && decoded_out == nullptr && t.k == 4) {      // counts only
       static const int stages = getenv("FF_COUNT12_STAGES") ? atoi(getenv("FF_COUNT12_STAGES")) : 4;   // tuning knob
+      if (bits == 16) return launch_count12<16, 4>(p, st);      // 2 CTAs x 3 x 16 KB in flight
+      if (bits == 8) return launch_count12<8, 6>(p, st);        // 2 CTAs x 5 x 8 KB in flight
       switch (stages) {
-        case 2: return launch_count12<2>(p, st);
-        case 3: return launch_count12<3>(p, st);
-        case 6: return launch_count12<6>(p, st);
-        case 8: return launch_count12<8>(p, st);
-        default: return launch_count12<4>(p, st);
+        case 2: return launch_count12<12, 2>(p, st);
+        case 3: return launch_count12<12, 3>(p, st);
+        case 6: return launch_count12<12, 6>(p, st);
+        case 8: return launch_count12<12, 8>(p, st);
+        default: return launch_count12<12, 4>(p, st);
       }
     }
-    if (bits == 12 && t.k == 4 && (diff_dtype == FF_DIFF_NONE || diff_dtype == FF_DIFF_U16) &&
-        getenv("FF_STREAM12_LEGACY") == nullptr) {
+    if (t.k == 4 && diff_dtype == FF_DIFF_U16) {          // uint16 difference image (+ decoded pixels, 12-bit)
       const bool dec = decoded_out != nullptr;
-      if (diff_dtype == FF_DIFF_U16)
-        return dec ? launch_stream12_tuned<true, true, true>(p, st) : launch_stream12_tuned<true, true, false>(p, st);
-      return launch_stream12_tuned<true, false, true>(p, st);     // count + decoded (count-only went to count12)
+      if (bits == 12)
+        return dec ? launch_streamx_tuned<12, true, true, true>(p, st) : launch_streamx_tuned<12, true, true, false>(p, st);
+      if (!dec) return bits == 16 ? launch_streamx_tuned<16, true, true, false>(p, st)
+                                  : launch_streamx_tuned<8, true, true, false>(p, st);
     }
+    if (t.k == 4 && bits == 12 && diff_dtype == FF_DIFF_NONE)        // counts + decoded (counts alone: count12)
+      return launch_streamx_tuned<12, true, false, true>(p, st);
     switch (bits) {
       case 8: return dispatch_stream<8>(p, t.k, diff_dtype, decoded_out != nullptr, st);
       case 12: return dispatch_stream<12>(p, t.k, diff_dtype, decoded_out != nullptr, st);
@@ -919,9 +990,8 @@ int unpack_impl(const void* packed, void* out, int64_t n_frames, int height, int
     p.n_frames = (int)n_frames;
     p.tiles_per_frame = t.tiles_per_frame;
     p.decoded_out = static_cast<uint16_t*>(out);
-    if (t.k == 4 && getenv("FF_STREAM12_LEGACY") == nullptr) return launch_stream12_tuned<false, false, true>(p, st);
-    return t.k == 4 ? launch_stream<12, false, FF_DIFF_NONE, true, 4>(p, st)
-                    : launch_stream<12, false, FF_DIFF_NONE, true, 1>(p, st);
+    if (t.k == 4) return launch_streamx_tuned<12, false, false, true>(p, st);
+    return launch_stream<12, false, FF_DIFF_NONE, true, 1>(p, st);
   }
   const int64_t n_px = n_frames * px;
   int64_t blocks = (n_px + 255) / 256;
