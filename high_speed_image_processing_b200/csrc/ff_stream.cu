@@ -1,13 +1,18 @@
 // Stage 1 + 2b: the frame-streaming kernels.
 //
-// One kernel template serves the packed-12-bit unpack (ff_unpack) and the fused front end
-// (ff_stream_frames): a CTA owns one pixel tile and marches over a chunk of consecutive
-// frames, so each frame is fetched from HBM exactly once even when the frame difference
-// needs the previous frame (it is carried in registers; the only re-read is one halo tile
-// per chunk).  Tiles are staged into shared memory by 1-D TMA bulk copies
-// (cp.async.bulk -> UBLKCP) through a kStages-deep mbarrier ring and decoded from there:
-// thread t takes 8-pixel groups t, t+256, ... (12 bytes = 3 conflict-free LDS.32 for packed
-// 12-bit, one LDS.128 for 16-bit, one LDS.64 for 8-bit) and writes 16-byte vectors.
+// Every kernel here reads each frame from HBM exactly once.  A frame is a flat stream of pixels
+// cut into tiles (8192 px, or 2048 px for small frames); a launch is one resident wave of
+// long-lived CTAs, each walking a contiguous run of (frame, tile) items whose bytes arrive in
+// shared memory through 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) behind mbarriers.
+//
+//   count12_kernel<BITS>   above-noise counts only (no image output): producer warp + full/empty
+//                          ring, compares on 16x2 SIMD lanes without extracting the pixels.
+//   streamx_kernel<BITS>   uint16 difference image and/or decoded pixels: same skeleton; the
+//                          previous frame's tile is carried in registers, so the difference
+//                          costs no second read (one halo tile per run of frames).
+//   stream_kernel<...>     general template: float32 / float64 difference outputs, 2048-px tiles,
+//                          CTA-wide barrier per item.
+//   stream_generic_kernel  shapes the TMA path cannot take (P % 32 != 0).
 //
 // Everything is integer arithmetic on values the reference holds as integer-valued float64
 // (scripts/process_videos.py:670-674, :397-399, :759), so results are bit-exact.
@@ -342,7 +347,6 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const StreamParams p) 
 // 4 PRMT + 2 LOP3 + 6 DPX + 2 IADD3 per 8 pixels (the carry-chain form needs 20).
 // 16-bit pixels already are 16x2 lanes (unsigned compare: max, add, min); 8-bit pixels are widened
 // with two PRMTs per word.  Those two read 16-byte pieces t, t+256, ... (conflict-free LDS.128).
-constexpr int kCountTileBytes = 4 * kThreads * 12;        // 1024 groups = 8192 px (12-bit)
 constexpr int kCountThreads = kThreads + 32;              // 8 consumer warps + 1 producer warp
 constexpr int kCountCtasPerSm = 2;
 

@@ -329,3 +329,66 @@ def test_process_host_equals_device_path_and_oracle(method):
                                                  skip_frames=[6, 7, 13, 14, 20]))
     assert np.array_equal(got.pos, full.pos_px[a:])
     eng.close()
+
+
+# ------------------------------------------------------------------------ output bounds (canaries)
+@pytest.mark.parametrize("h,w,n", [(130, 1024, 5), (36, 1000, 7), (5, 70, 9), (128, 1024, 3)])
+@pytest.mark.parametrize("bits", [8, 12, 16])
+def test_kernels_stay_inside_their_output_buffers(engine, h, w, n, bits):
+    """compute-sanitizer is not available on the GPU pool, so every output of the streaming and
+    detection entry points is placed between canary regions and the canaries are checked."""
+    import ctypes as C
+    from high_speed_image_processing_b200._cabi import FF_DIFF_F32, FF_DIFF_F64, FF_DIFF_NONE, FF_DIFF_U16
+    lib, dev_ = engine._lib, engine.device
+    frames = small_clip(bits=bits, w=w, h=h, n=n, seed=h + w + bits, style="mini")
+    packed = dev(syn.pack_frames(frames, bits), engine)
+    bg = torch.tensor([int(frames[0].max())], dtype=torch.int32, device=dev_)
+    n_elems, per_frame = C.c_int64(0), C.c_int(0)
+    assert lib.ff_partial_len(n, h, w, bits, C.byref(n_elems), C.byref(per_frame)) == 0
+    guard = 1024                                            # elements of canary on each side
+
+    def padded(n_items, dtype):
+        buf = torch.full((n_items + 2 * guard,), 0x5A, dtype=torch.uint8, device=dev_).repeat_interleave(
+            torch.tensor([], dtype=dtype).element_size()).view(dtype)
+        return buf, buf[guard:guard + n_items]
+
+    def intact(buf, n_items):
+        raw = buf.view(torch.uint8)
+        es = buf.element_size()
+        return bool((raw[:guard * es] == 0x5A).all()) and bool((raw[(guard + n_items) * es:] == 0x5A).all())
+
+    st = torch.cuda.current_stream().cuda_stream
+    px = n * h * w
+    cases = [(FF_DIFF_NONE, None, False), (FF_DIFF_U16, torch.uint16, False), (FF_DIFF_F32, torch.float32, False),
+             (FF_DIFF_F64, torch.float64, False)]
+    if bits == 12:
+        cases += [(FF_DIFF_NONE, None, True), (FF_DIFF_U16, torch.uint16, True)]
+    for code, dt, decoded in cases:
+        pbuf, pview = padded(n_elems.value, torch.int32)
+        dbuf, dview = padded(px, dt) if dt is not None else (None, None)
+        ebuf, eview = padded(px, torch.uint16) if decoded else (None, None)
+        rc = lib.ff_stream_frames(packed.data_ptr(), None, n, h, w, bits, bg.data_ptr(), -1, 5, None,
+                                  pview.data_ptr(), None if dview is None else dview.data_ptr(), code,
+                                  None if eview is None else eview.data_ptr(), st)
+        assert rc == 0, (code, decoded, rc)
+        torch.cuda.synchronize()
+        assert intact(pbuf, n_elems.value), ("partial", code, decoded)
+        if dbuf is not None:
+            assert intact(dbuf, px), ("diff", code)
+        if ebuf is not None:
+            assert intact(ebuf, px), ("decoded", code)
+        # detection outputs
+        posb, posv = padded(n, torch.int32)
+        cntb, cntv = padded(n, torch.int32)
+        prob, prov = padded(n * w, torch.int32)
+        fe = torch.full((1,), FF_NO_EXIT, dtype=torch.int32, device=dev_)
+        rc = lib.ff_detect(packed.data_ptr(), None, n, 0, h, w, bits, bg.data_ptr(), pview.data_ptr(), 1, 1, 1, 5,
+                           100, -20, 1, 10, None, posv.data_ptr(), cntv.data_ptr(), fe.data_ptr(), prov.data_ptr(), st)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert intact(posb, n) and intact(cntb, n) and intact(prob, n * w)
+    if bits == 12:
+        ubuf, uview = padded(px, torch.uint16)
+        assert lib.ff_unpack(packed.data_ptr(), uview.data_ptr(), n, h, w, 12, st) == 0
+        torch.cuda.synchronize()
+        assert intact(ubuf, px) and np.array_equal(uview.cpu().numpy().reshape(n, h, w), frames)
