@@ -857,8 +857,13 @@ int launch_stream(StreamParams p, cudaStream_t st) {
 
 template <int BITS, bool COUNT, int DIFF, bool DECODED>
 int launch_stream_k(const StreamParams& p, int k, cudaStream_t st) {
-  return k == 4 ? launch_stream<BITS, COUNT, DIFF, DECODED, 4>(p, st)
-                : launch_stream<BITS, COUNT, DIFF, DECODED, 1>(p, st);
+  // 8192-px tiles reach this template only with float difference outputs: everything else at
+  // that tile size is served by count12_kernel / streamx_kernel.
+  if (k == 4) {
+    if constexpr (DIFF == FF_DIFF_F32 || DIFF == FF_DIFF_F64) return launch_stream<BITS, COUNT, DIFF, DECODED, 4>(p, st);
+    else return FF_ERR_UNSUPPORTED;
+  }
+  return launch_stream<BITS, COUNT, DIFF, DECODED, 1>(p, st);
 }
 
 template <int BITS>
