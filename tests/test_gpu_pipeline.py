@@ -242,3 +242,33 @@ def test_fullsize_c1(engine):
     exp[want.first_exit:] = FF_POS_DROPPED
     assert np.array_equal(res.pos.cpu().numpy(), exp)
     assert int(res.first_exit.cpu().item()) == want.first_exit
+
+
+@pytest.mark.parametrize("bits,header", [(16, "cihx"), (8, "cih"), (16, "cih")])
+def test_file_level_driver_on_16bit_and_8bit_recordings(tmp_path, bits, header):
+    """Decode row a1 end to end for the other storage depths: .cihx / legacy .cih + .mraw on disk ->
+    process_video_source (memory-mapped streaming) -> rows identical to the oracle's."""
+    spec = syn.SyntheticSpec(width=256, height=48, n_frames=140, bits=bits, style="mini", t_enter=10.0,
+                             velocity=3.0, seed=160 + bits)
+    frames = syn.render_frames(spec)
+    vdir = tmp_path / "Mini-Video-Files"
+    syn.write_clip(vdir, "run-2-", spec, frames=frames, header=header)
+    cfg = VideoSourceConfig(name="Mini")
+    cfg.enabled = True
+    cfg.detection_method = "threshold"
+    cfg.video_path = str(vdir)
+    cfg.output_dir = str(tmp_path / "out")
+    cfg.file_calibrations = [FileCalibration(calibration=0.000869565, position_offset=0.050237,
+                                             files=["run-1-:run-10-"])]
+    want = fo.process_clip(frames, fo.ClipParams(method="threshold"))
+    if header == "cihx":
+        res = process_video_source(cfg, None, verbose=False)["run-2-.cihx"]
+    else:                                            # process_video_source globs *.cihx like the reference (:1300)
+        with open_video(str(vdir / "run-2-.cih")) as video:
+            assert video.storage_bits == bits and video[3].dtype == (np.uint8 if bits == 8 else np.uint16)
+            assert np.array_equal(video[3], frames[3])
+            res = process_video(video, cfg, 0.000869565, 0.050237)
+    assert [(r[0], r[2]) for r in res.rows] == want.records
+    assert res.first_exit == (want.first_exit if want.first_exit < len(frames) else None)
+    for f, t, px, pm, _ in res.rows:
+        assert pm == fo.position_m(px, 0.000869565, 0.050237)
