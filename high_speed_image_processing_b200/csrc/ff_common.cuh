@@ -2,6 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <mutex>
+
 #include "../../include/flamefront.h"
 
 namespace ff {
@@ -17,6 +20,29 @@ void set_cuda_error(cudaError_t e, const char* where);
       return FF_ERR_CUDA;                                        \
     }                                                            \
   } while (0)
+
+// ---- launch configuration computed once per device (thread-safe; entry points may be called
+// from several host threads, one per GPU) ----------------------------------------------------
+struct PerDeviceInt {
+  std::mutex m;
+  bool have[64] = {};
+  int value[64] = {};
+  // init(int* v) -> FF status; runs once per device under the lock.
+  template <class Init>
+  int get(Init&& init, int* out) {
+    int dev = 0;
+    FF_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return FF_ERR_INVALID;
+    std::lock_guard<std::mutex> g(m);
+    if (!have[dev]) {
+      const int rc = init(&value[dev]);
+      if (rc != FF_OK) return rc;
+      have[dev] = true;
+    }
+    *out = value[dev];
+    return FF_OK;
+  }
+};
 
 // ---- tiling shared by ff_partial_len / ff_stream_frames / ff_detect ---------------------
 // A "group" is 8 consecutive pixels = `bits` bytes of the packed stream.  A tile is

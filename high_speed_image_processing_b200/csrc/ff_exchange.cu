@@ -280,7 +280,8 @@ int ff_exchange_finish(ff_exchange* x, int64_t total_frames, int32_t* pos_out_de
   p.status = x->local + x->status_off;
   // A peer that never arrives must not hang the GPU for ever: give up after FF_EXCHANGE_TIMEOUT_S
   // seconds (default 20; ranks may legitimately reach this step seconds apart, e.g. after file I/O).
-  static const double timeout_s = getenv("FF_EXCHANGE_TIMEOUT_S") ? atof(getenv("FF_EXCHANGE_TIMEOUT_S")) : 20.0;
+  const char* env_t = getenv("FF_EXCHANGE_TIMEOUT_S");
+  const double timeout_s = env_t ? atof(env_t) : 20.0;
   p.spin_limit = (long long)((timeout_s > 0.01 ? timeout_s : 0.01) * 1.9e9);
   merge_ranges_kernel<true><<<merge_grid(total_frames), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   FF_CUDA_TRY(cudaGetLastError());

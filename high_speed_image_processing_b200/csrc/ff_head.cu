@@ -14,6 +14,7 @@
 //     window from the last detected position, arg-min gradient / rightmost Sobel, max of the
 //     candidates, stop at the exit frame (:1488-1494).  One CTA walks the frames in order.
 #include <climits>
+#include <cstdlib>
 
 #include "ff_common.cuh"
 
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(kTrackThreads) head_track_kernel(const HeadTra
   if (warp == 1) {
     // ---- producer: scan the flags 512 frames at a time, push active frames in order -------------
     int it = 0;
+    const uint64_t pol = policy_evict_first();
     auto push = [&](int f, int fl) {      // lane 0 only
       const int s = it & (n_stages - 1);
       mbar_wait(&empty[s], ((it >> stage_shift) & 1) ^ 1);
@@ -272,25 +274,40 @@ __global__ void __launch_bounds__(kTrackThreads) head_track_kernel(const HeadTra
       meta[s].fl = fl;
       if (fl == 1) {
         mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
-        bulk_g2s(smem + (size_t)s * stage_bytes, p.lines + (int64_t)f * 2 * W, (uint32_t)stage_bytes, &full[s],
-                 policy_evict_first());
+        bulk_g2s(smem + (size_t)s * stage_bytes, p.lines + (int64_t)f * 2 * W, (uint32_t)stage_bytes, &full[s], pol);
       } else {
         mbar_arrive(&full[s]);
       }
       ++it;
     };
     bool stopped = false;
+    const bool vec_flags = (reinterpret_cast<uintptr_t>(p.flags) & 15u) == 0;
     for (int base = 0; base < p.n_frames && !stopped; base += 32 * 16) {
       // lane l inspects frames [base + 16 l, base + 16 l + 16): bit j = flag != 0, bit 16+j = flag == 1
+      // (one 16-byte load per lane: a byte-by-byte scan of a long empty lead-in cost 85 us at C2)
       uint32_t bits = 0;
       const int f0 = base + lane * 16;
-      for (int j = 0; j < 16; ++j) {
-        const int f = f0 + j;
-        const int fl = f < p.n_frames ? (int)p.flags[f] : 0;
-        if (fl != 0) bits |= 1u << j;
-        if (fl == 1) bits |= 1u << (16 + j);
+      if (vec_flags && f0 + 16 <= p.n_frames) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.flags + f0));
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t fl = (w4[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+          if (fl != 0) bits |= 1u << j;
+          if (fl == 1) bits |= 1u << (16 + j);
+        }
+      } else {
+        for (int j = 0; j < 16; ++j) {
+          const int f = f0 + j;
+          const int fl = f < p.n_frames ? (int)p.flags[f] : 0;
+          if (fl != 0) bits |= 1u << j;
+          if (fl == 1) bits |= 1u << (16 + j);
+        }
       }
-      for (int l = 0; l < 32 && !stopped; ++l) {
+      unsigned lanes = __ballot_sync(fullmask, (bits & 0xFFFFu) != 0);     // lanes that hold active frames
+      while (lanes && !stopped) {
+        const int l = __ffs((int)lanes) - 1;
+        lanes &= lanes - 1;
         uint32_t b = __shfl_sync(fullmask, bits, l);
         if (lane == 0) {
           while (b & 0xFFFFu) {
@@ -600,11 +617,14 @@ int head_track_impl(const double* lines, const uint8_t* flags, int64_t n_frames,
     return FF_OK;
   }
   const size_t smem = (size_t)stages * stage_bytes + fixed;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceInt cache;
+  int unused = 0;
+  const int rc_attr = cache.get([](int* v) -> int {
     FF_CUDA_TRY(cudaFuncSetAttribute(head_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+    *v = 1;
+    return FF_OK;
+  }, &unused);
+  if (rc_attr != FF_OK) return rc_attr;
   head_track_kernel<<<1, kTrackThreads, smem, st>>>(p, shift);
   FF_CUDA_TRY(cudaGetLastError());
   return FF_OK;

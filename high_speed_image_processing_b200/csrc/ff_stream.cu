@@ -475,13 +475,10 @@ int sm_count_cached();
 template <int BITS, int kCountStages>
 int launch_count12(StreamParams p, cudaStream_t st) {
   constexpr int kSmem = kCountStages * (4 * kThreads * BITS) + 2 * kCountStages * 8;
-  static bool configured[64] = {false};
-  static int ctas_per_sm[64] = {0};
-  int dev = 0;
-  FF_CUDA_TRY(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) return FF_ERR_INVALID;
   auto kern = count12_kernel<BITS, kCountStages>;
-  if (!configured[dev]) {
+  static PerDeviceInt cache;
+  int ctas = 1;
+  int rc = cache.get([&](int* v) -> int {
     FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     int occ = 0;
     FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCountThreads, kSmem));
@@ -491,10 +488,11 @@ int launch_count12(StreamParams p, cudaStream_t st) {
     int cap = kCountCtasPerSm;
     if (const char* e = getenv("FF_COUNT12_CTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;   // tuning knob
     if (occ > cap) occ = cap;
-    ctas_per_sm[dev] = occ > 0 ? occ : 1;
-    configured[dev] = true;
-  }
-  const int64_t wave = (int64_t)sm_count_cached() * ctas_per_sm[dev];
+    *v = occ > 0 ? occ : 1;
+    return FF_OK;
+  }, &ctas);
+  if (rc != FF_OK) return rc;
+  const int64_t wave = (int64_t)sm_count_cached() * ctas;
   const int64_t total_work = (int64_t)p.tiles_per_frame * p.n_frames;
   p.items_per_cta = (total_work + wave - 1) / wave;
   if (p.items_per_cta < 1) p.items_per_cta = 1;
@@ -708,21 +706,19 @@ int sm_count_cached();
 template <int BITS, bool COUNT, bool DIFF, bool DECODED, int STAGES>
 int launch_streamx(StreamParams p, int ctas_cap, cudaStream_t st) {
   constexpr int kSmem = STAGES * (4 * kThreads * BITS) + 2 * STAGES * 8;
-  static bool configured[64] = {false};
-  static int ctas_per_sm[64] = {0};
-  int dev = 0;
-  FF_CUDA_TRY(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) return FF_ERR_INVALID;
   auto kern = streamx_kernel<BITS, COUNT, DIFF, DECODED, STAGES>;
-  if (!configured[dev]) {
+  static PerDeviceInt cache;
+  int ctas = 1;
+  int rc = cache.get([&](int* v) -> int {
     FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     int occ = 0;
     FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kOutThreads, kSmem));
     if (occ > ctas_cap) occ = ctas_cap;
-    ctas_per_sm[dev] = occ > 0 ? occ : 1;
-    configured[dev] = true;
-  }
-  const int64_t wave = (int64_t)sm_count_cached() * ctas_per_sm[dev];
+    *v = occ > 0 ? occ : 1;
+    return FF_OK;
+  }, &ctas);
+  if (rc != FF_OK) return rc;
+  const int64_t wave = (int64_t)sm_count_cached() * ctas;
   const int64_t total_work = (int64_t)p.tiles_per_frame * p.n_frames;
   p.items_per_cta = (total_work + wave - 1) / wave;
   if (p.items_per_cta < 1) p.items_per_cta = 1;
@@ -809,15 +805,17 @@ __global__ void unpack12_generic_kernel(const uint8_t* __restrict__ in, uint16_t
 }
 
 int sm_count_cached() {
-  static int cached[64] = {0};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-  if (cached[dev] == 0) {
-    int n = 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    cached[dev] = n;
-  }
-  return cached[dev];
+  static PerDeviceInt cache;
+  int n = 148;
+  cache.get([](int* v) -> int {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+    *v = sms;
+    return FF_OK;
+  }, &n);
+  return n;
 }
 
 template <int BITS, bool COUNT, int DIFF, bool DECODED, int K>
@@ -825,12 +823,9 @@ int launch_stream(StreamParams p, cudaStream_t st) {
   auto kern = stream_kernel<BITS, COUNT, DIFF, DECODED, K>;
   constexpr int kStageBytes = K * kThreads * BITS;
   constexpr int kSmem = kStages * kStageBytes + kStages * 8;
-  static bool configured[64] = {false};
-  static int ctas_per_sm[64] = {0};
-  int dev = 0;
-  FF_CUDA_TRY(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) return FF_ERR_INVALID;
-  if (!configured[dev]) {
+  static PerDeviceInt cache;
+  int ctas = 1;
+  int rc = cache.get([&](int* v) -> int {
     FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     int occ = 0;
     FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, kSmem));
@@ -840,11 +835,12 @@ int launch_stream(StreamParams p, cudaStream_t st) {
     int cap = DIFF == FF_DIFF_F64 ? 1 : (DIFF == FF_DIFF_F32 ? 2 : occ);
     if (const char* e = getenv("FF_STREAM_CTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;
     if (occ > cap) occ = cap;
-    ctas_per_sm[dev] = occ > 0 ? occ : 1;
-    configured[dev] = true;
-  }
+    *v = occ > 0 ? occ : 1;
+    return FF_OK;
+  }, &ctas);
+  if (rc != FF_OK) return rc;
   // One resident wave: the (tile, frame) items are split evenly over SMs x CTAs/SM long-lived CTAs.
-  const int64_t wave = (int64_t)sm_count_cached() * ctas_per_sm[dev];
+  const int64_t wave = (int64_t)sm_count_cached() * ctas;
   const int64_t total_work = (int64_t)p.tiles_per_frame * p.n_frames;
   p.items_per_cta = (total_work + wave - 1) / wave;
   if (p.items_per_cta < 1) p.items_per_cta = 1;
