@@ -45,10 +45,8 @@ def workload_spec(total_frames: int):
                                 "t_enter": float(max(2, total_frames - FLAME_FRAMES))})
 
 
-def config_dict(world: int, frames_per_gpu: int, chunk_mb: int, transport: str = "") -> dict:
-    extra = {"exchange_transport": transport} if transport else {}
+def config_dict(world: int, frames_per_gpu: int, chunk_mb: int) -> dict:
     return {
-        **extra,
         "workload": "C2: Nova-style synthetic 1024x128, packed 12-bit MRAW, half_maximum on the "
                     "frame-difference centre-row profile, per-file calibration",
         "frames_per_gpu": frames_per_gpu, "total_frames": frames_per_gpu * world,
@@ -431,7 +429,8 @@ def own_arm(args) -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": config_dict(world, fpr, args.chunk_mb, exchange.transport if world > 1 else ""),
+            "config": config_dict(world, fpr, args.chunk_mb),
+            "exchange_transport": exchange.transport if world > 1 else None,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "kernel": "ff::count12_kernel<4 stages>",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": fpr * alg_bytes_per_frame,
