@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     procs = []
     for src in SOURCES:
         obj = LIB_DIR / (Path(src).stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("FF_NVCC_EXTRA", "").split(), "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")

@@ -518,6 +518,10 @@ int launch_count12(StreamParams p, cudaStream_t st) {
 // relu(d) = max(sub,prev) - prev, ...), which cannot borrow across lanes.
 constexpr int kOutThreads = kThreads + 32;
 
+// Output stores are streaming (st.global.cs); plain and write-through stores measured the same
+// (C4 uint16 difference 0.920 / 0.925 / 0.926 of the copy rate).
+__device__ __forceinline__ void st_out(uint4* p, uint4 v) { __stcs(p, v); }
+
 template <int BITS>
 __device__ __forceinline__ void load_lanes(const uint8_t* stage, int g, uint32_t (&x)[4]) {
   if (BITS == 12) {
@@ -661,7 +665,7 @@ __global__ void __launch_bounds__(kOutThreads) streamx_kernel(const StreamParams
                                 : __viaddmin_s16x2_relu(x[j], nc2, one2);                       // [x > c], signed
           }
           if (DECODED && !is_halo)
-            __stcs(reinterpret_cast<uint4*>(p.decoded_out + px0 + (int64_t)g * kGroupPx), make_uint4(x[0], x[1], x[2], x[3]));
+            st_out(reinterpret_cast<uint4*>(p.decoded_out + px0 + (int64_t)g * kGroupPx), make_uint4(x[0], x[1], x[2], x[3]));
           if (DIFF) {
             uint32_t o[4];
 #pragma unroll
@@ -684,7 +688,7 @@ __global__ void __launch_bounds__(kOutThreads) streamx_kernel(const StreamParams
             }
             if (!is_halo) {
               uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.diff_out) + px0 + (int64_t)g * kGroupPx);
-              __stcs(dst, diff_valid ? make_uint4(o[0], o[1], o[2], o[3]) : make_uint4(0u, 0u, 0u, 0u));
+              st_out(dst, diff_valid ? make_uint4(o[0], o[1], o[2], o[3]) : make_uint4(0u, 0u, 0u, 0u));
             }
           }
         }
