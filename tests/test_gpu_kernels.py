@@ -319,6 +319,12 @@ def test_process_host_equals_device_path_and_oracle(method):
         assert np.array_equal(got.pos, oracle_pos(want))
         assert got.frames_done < n, "copy should stop after the exit frame was seen"
         assert np.array_equal(got.counts[:got.frames_done], want.nonempty[:got.frames_done].astype(np.int32))
+    # profile = bg-subtracted centre row instead of the frame difference (use_frame_diff=False)
+    nd = DetectionParams(method=method, use_frame_diff=False)
+    want_nd = fo.process_clip(frames, fo.ClipParams(method=method, use_frame_diff=False))
+    got = eng.process_host(packed, n, h, w, 12, nd, scalars)
+    assert got.first_exit == (want_nd.first_exit if want_nd.first_exit < n else FF_NO_EXIT)
+    assert np.array_equal(got.pos, oracle_pos(want_nd))
     # with skip frames and a sub-range halo
     skip = np.zeros(n, dtype=np.uint8)
     skip[[6, 7, 13, 14, 20]] = 1
