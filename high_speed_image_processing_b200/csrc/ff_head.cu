@@ -10,9 +10,12 @@
 //     symmetric pairs outermost -> innermost) - positions come out bit-identical.
 //     Boundaries: scipy mode 'reflect'.  Every stage is symmetric, so evaluating the stages on
 //     the reflect-EXTENDED band equals reflecting each stage's output.
-// head_track_kernel - the sequential part (:317-348, :420-465): velocity-constrained search
+// head_flags_kernel - empty-frame decision per frame + the list of frames with work.
+// head_track_*      - the sequential part (:317-348, :420-465): velocity-constrained search
 //     window from the last detected position, arg-min gradient / rightmost Sobel, max of the
-//     candidates, stop at the exit frame (:1488-1494).  One CTA walks the frames in order.
+//     candidates, stop at the exit frame (:1488-1494) - run as a speculative parallel walk
+//     (full-width answers for every frame, 32-frame segments walked at once, validated in
+//     order); head_track_generic_kernel is the plain sequential walk kept as its cross-check.
 #include <climits>
 #include <cstdlib>
 
@@ -221,216 +224,16 @@ struct HeadTrackParams {
   int32_t* stop;                   // [3]: exit frame (global) or FF_NO_EXIT, last frame, last pos
 };
 
-// The sequential walk is latency-bound: every frame's search window depends on the previous
-// frame's answer, so the work per frame is a dependent chain of ~100-element scans.  This kernel
-// takes the memory latency out of the chain: a producer warp finds the frames that reached the
-// detector (flags != 0) and streams their two float64 lines (16*W bytes, contiguous) into a
-// shared-memory ring with TMA bulk copies, several frames ahead; a single consumer warp walks
-// the ring in frame order and scans its window out of shared memory with warp shuffles.
-// Same comparisons, same tie-breaks as the generic kernel below (first minimum of the gradient,
-// rightmost |Sobel| above the fraction of the window's peak).
-constexpr int kTrackThreads = 64;          // warp 0: tracker, warp 1: producer
-constexpr int kTrackMaxStages = 8;
-
-struct TrackMeta { int f; int fl; };
-
-// Monotone map from the bits of a non-NaN double to an unsigned integer (-0.0 == +0.0).
+// Monotone map from the bits of a non-NaN double to an unsigned integer (-0.0 == +0.0): the
+// float64 comparisons of the reference run on these keys (integer compares and REDUX instead of
+// FP64 compare chains); ties stay ties.
 __device__ __forceinline__ unsigned long long order_key(unsigned long long bits) {
   if (bits == 0x8000000000000000ull) bits = 0ull;
   return (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
 }
 
-__global__ void __launch_bounds__(kTrackThreads) head_track_kernel(const HeadTrackParams p, int stage_shift) {
-  const int n_stages = 1 << stage_shift;      // ring depth is a power of two: slot and phase are a mask and a shift
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int W = p.width;
-  const size_t stage_bytes = (size_t)16 * W;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)n_stages * stage_bytes);
-  uint64_t* empty = full + kTrackMaxStages;
-  TrackMeta* meta = reinterpret_cast<TrackMeta*>(empty + kTrackMaxStages);
-  volatile int* s_stop = reinterpret_cast<volatile int*>(meta + kTrackMaxStages);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned fullmask = 0xFFFFFFFFu;
-
-  if (tid == 0) {
-    for (int s = 0; s < n_stages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
-    *s_stop = 0;
-    p.stop[0] = FF_NO_EXIT;
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  if (warp == 1) {
-    // ---- producer: scan the flags 512 frames at a time, push active frames in order -------------
-    int it = 0;
-    const uint64_t pol = policy_evict_first();
-    auto push = [&](int f, int fl) {      // lane 0 only
-      const int s = it & (n_stages - 1);
-      mbar_wait(&empty[s], ((it >> stage_shift) & 1) ^ 1);
-      meta[s].f = f;
-      meta[s].fl = fl;
-      if (fl == 1) {
-        mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
-        bulk_g2s(smem + (size_t)s * stage_bytes, p.lines + (int64_t)f * 2 * W, (uint32_t)stage_bytes, &full[s], pol);
-      } else {
-        mbar_arrive(&full[s]);
-      }
-      ++it;
-    };
-    bool stopped = false;
-    const bool vec_flags = (reinterpret_cast<uintptr_t>(p.flags) & 15u) == 0;
-    for (int base = 0; base < p.n_frames && !stopped; base += 32 * 16) {
-      // lane l inspects frames [base + 16 l, base + 16 l + 16): bit j = flag != 0, bit 16+j = flag == 1
-      // (one 16-byte load per lane: a byte-by-byte scan of a long empty lead-in cost 85 us at C2)
-      uint32_t bits = 0;
-      const int f0 = base + lane * 16;
-      if (vec_flags && f0 + 16 <= p.n_frames) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.flags + f0));
-        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint32_t fl = (w4[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-          if (fl != 0) bits |= 1u << j;
-          if (fl == 1) bits |= 1u << (16 + j);
-        }
-      } else {
-        for (int j = 0; j < 16; ++j) {
-          const int f = f0 + j;
-          const int fl = f < p.n_frames ? (int)p.flags[f] : 0;
-          if (fl != 0) bits |= 1u << j;
-          if (fl == 1) bits |= 1u << (16 + j);
-        }
-      }
-      unsigned lanes = __ballot_sync(fullmask, (bits & 0xFFFFu) != 0);     // lanes that hold active frames
-      while (lanes && !stopped) {
-        const int l = __ffs((int)lanes) - 1;
-        lanes &= lanes - 1;
-        uint32_t b = __shfl_sync(fullmask, bits, l);
-        if (lane == 0) {
-          while (b & 0xFFFFu) {
-            const int j = __ffs((int)(b & 0xFFFFu)) - 1;
-            b &= ~(1u << j);
-            if (*s_stop) { stopped = true; break; }
-            push(base + l * 16 + j, ((b >> (16 + j)) & 1u) ? 1 : 2);
-          }
-        }
-        stopped = __shfl_sync(fullmask, (int)stopped, 0) != 0;
-      }
-    }
-    if (lane == 0) push(-1, 0);           // sentinel: no more frames
-    return;
-  }
-
-  // ---- consumer: the reference's sequential search (:317-348, :420-465, :1488-1494) -----------------
-  int last_f = p.last_frame_in, last_p = p.last_pos_in;
-  bool stopped = false;
-  for (int it = 0;; ++it) {
-    const int s = it & (n_stages - 1);
-    mbar_wait(&full[s], (it >> stage_shift) & 1);
-    const int f = meta[s].f;
-    const int fl = meta[s].fl;
-    if (f < 0) break;
-    if (!stopped) {
-      const int gf = (int)(p.first_frame + f);
-      int s0, s1;
-      if (last_p < 0) {
-        s0 = p.edge_margin;
-        s1 = W - p.edge_margin;
-      } else {
-        s0 = last_p;
-        s1 = min(W - p.edge_margin, last_p + p.max_disp * max(1, gf - last_f) + p.window);
-      }
-      int pos_a = -1, pos_b = -1;
-      if (fl == 1 && s1 > s0 && s0 >= 0) {     // non-empty search slice (:424)
-        s1 = min(s1, W);
-        // The float64 comparisons of the reference run here on order-preserving integer keys
-        // (FP64 compare/min chains cost ~10x the latency of integer ones on this part, and this
-        // loop is a serial chain over the frames): key(x) is monotone in x for every non-NaN
-        // double, -0.0 is folded onto +0.0 so ties stay ties.
-        const unsigned long long* sob = reinterpret_cast<const unsigned long long*>(smem + (size_t)s * stage_bytes);
-        const unsigned long long* grd = sob + W;
-        unsigned long long mn = ~0ull, amax = 0ull;    // key(+inf) < ~0;  |x| keys start at 0
-        int arg = INT_MAX;
-        const bool small = s1 - s0 <= 128;             // the steady state: window = displacement bound + 100
-        unsigned long long a4[4];
-        if (small) {                                   // all loads issued up front, everything stays in registers
-          unsigned long long g4[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int x = s0 + lane + 32 * j;
-            const bool in = x < s1;
-            g4[j] = in ? grd[x] : 0x7FF8000000000000ull;
-            a4[j] = in ? (sob[x] & 0x7FFFFFFFFFFFFFFFull) : 0ull;
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int x = s0 + lane + 32 * j;
-            const unsigned long long g = x < s1 ? order_key(g4[j]) : ~0ull;
-            if (g < mn) { mn = g; arg = x; }
-            amax = a4[j] > amax ? a4[j] : amax;
-          }
-        } else {
-          for (int x = s0 + lane; x < s1; x += 32) {
-            const unsigned long long g = order_key(grd[x]);
-            if (g < mn) { mn = g; arg = x; }
-            const unsigned long long a = sob[x] & 0x7FFFFFFFFFFFFFFFull;      // |sobel| as an ordered integer
-            amax = a > amax ? a : amax;
-          }
-        }
-        const bool any = s1 - s0 > 0;
-        // first minimum: smallest key, then smallest index (np.argmin)
-        const unsigned mn_hi = __reduce_min_sync(fullmask, (unsigned)(mn >> 32));
-        const unsigned lo_c = (unsigned)(mn >> 32) == mn_hi ? (unsigned)mn : 0xFFFFFFFFu;
-        const unsigned mn_lo = __reduce_min_sync(fullmask, lo_c);
-        const bool mine = (unsigned)(mn >> 32) == mn_hi && (unsigned)mn == mn_lo;
-        arg = (int)__reduce_min_sync(fullmask, mine ? (unsigned)arg : 0x7FFFFFFFu);
-        const unsigned long long mn_key = ((unsigned long long)mn_hi << 32) | mn_lo;
-        const unsigned am_hi = __reduce_max_sync(fullmask, (unsigned)(amax >> 32));
-        const unsigned am_lo = __reduce_max_sync(fullmask, (unsigned)(amax >> 32) == am_hi ? (unsigned)amax : 0u);
-        const unsigned long long am_bits = ((unsigned long long)am_hi << 32) | am_lo;
-        if (any && mn_key < order_key(__double_as_longlong(-p.min_strength))) pos_a = arg;   // :427-430
-        const double amax_d = __longlong_as_double((long long)am_bits);
-        if (any && amax_d > p.min_strength) {                                                 // :434-440
-          const unsigned long long thr = (unsigned long long)__double_as_longlong(__dmul_rn(amax_d, p.sobel_frac));
-          int right = -1;
-          if (small) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (a4[j] > thr) right = s0 + lane + 32 * j;      // out-of-window slots hold 0 and thr >= 0
-          } else {
-            for (int x = s0 + lane; x < s1; x += 32)
-              if ((sob[x] & 0x7FFFFFFFFFFFFFFFull) > thr) right = x;
-          }
-          pos_b = __reduce_max_sync(fullmask, right);
-        }
-      }
-      const int final_pos = max(pos_a, pos_b);                                  // :452-465
-      if (lane == 0) {
-        int32_t* o = p.out + (int64_t)f * 5;
-        o[0] = final_pos; o[1] = pos_a; o[2] = pos_b; o[3] = s0; o[4] = s1;
-      }
-      if (final_pos >= 0) { last_f = gf; last_p = final_pos; }
-      if (final_pos >= 0 && final_pos >= W - p.exit_margin) {                   // :1488-1494
-        if (lane == 0) {
-          p.stop[0] = gf;
-          *s_stop = 1;
-        }
-        stopped = true;
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
-  }
-  if (lane == 0) {
-    p.stop[1] = last_f;
-    p.stop[2] = last_p;
-  }
-}
-
-// Any width (rows too long for a useful shared-memory ring): the lines are read from global memory.
+// The sequential walk, one CTA, frame by frame, straight from the reference (:317-348, :420-465,
+// :1488-1494): the cross-check for the speculative tracker below (FF_TRACK_SEQUENTIAL=1).
 __global__ void __launch_bounds__(kHeadThreads) head_track_generic_kernel(const HeadTrackParams p) {
   __shared__ double s_min[kHeadThreads / 32];
   __shared__ int s_arg[kHeadThreads / 32];
@@ -516,6 +319,289 @@ __global__ void __launch_bounds__(kHeadThreads) head_track_generic_kernel(const 
     p.stop[1] = s_last_f;
     p.stop[2] = s_last_p;
   }
+}
+
+// ---- speculative parallel tracker ---------------------------------------------------------------
+// The walk is sequential only through its state (last detection frame, last position).  The clip
+// is cut into segments of 32 consecutive frames, one warp each, spread over the whole GPU
+// (head_track_spec_kernel): segment 0 starts from the true state, every other segment from
+// "nothing detected yet", and each warp walks its segment SPECULATIVELY, writing its results.
+// One warp then validates the segments in order (head_track_commit_kernel): it re-runs the first
+// active frame(s) of a segment from the true state until its state equals the state the
+// speculation had at the same point - from there on the two walks are the same deterministic
+// function of (state, data), so the rest of the segment stands as computed - and finally clears
+// everything after the exit frame.  The flame front moves a few pixels per frame and dominates its
+// neighbourhood, so a walk started from scratch locks onto it within a frame or two; if it never
+// does, validation simply degrades into the sequential walk.  Results are bit-identical to the
+// sequential kernel either way (tests run both).  Lines are read straight from global memory
+// (they sit in L2 after head_band_kernel).
+constexpr int kSegFrames = 32;               // frames per segment = lanes of the validating warp
+constexpr int kSpecWarpsPerCta = 8;
+
+struct TrackState { int last_f, last_p; };
+struct FrameResult { int final_pos, pos_a, pos_b, s0, s1; };
+
+__device__ __forceinline__ FrameResult track_frame(const HeadTrackParams& p, int f, int fl, TrackState st, int lane) {
+  const unsigned fullmask = 0xFFFFFFFFu;
+  const int W = p.width;
+  const int gf = (int)(p.first_frame + f);
+  FrameResult r;
+  if (st.last_p < 0) {
+    r.s0 = p.edge_margin;
+    r.s1 = W - p.edge_margin;
+  } else {
+    r.s0 = st.last_p;
+    r.s1 = min(W - p.edge_margin, st.last_p + p.max_disp * max(1, gf - st.last_f) + p.window);
+  }
+  r.pos_a = r.pos_b = -1;
+  if (fl == 1 && r.s1 > r.s0 && r.s0 >= 0) {     // non-empty search slice (:424)
+    r.s1 = min(r.s1, W);
+    const int s0 = r.s0, s1 = r.s1;
+    const unsigned long long* sob = reinterpret_cast<const unsigned long long*>(p.lines + (int64_t)f * 2 * W);
+    const unsigned long long* grd = sob + W;
+    unsigned long long mn = ~0ull, amax = 0ull;    // key(+inf) < ~0;  |x| keys start at 0
+    int arg = INT_MAX;
+    const bool small = s1 - s0 <= 128;
+    unsigned long long a4[4];
+    if (small) {                                   // all loads issued up front, window held in registers
+      unsigned long long g4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int x = s0 + lane + 32 * j;
+        const bool in = x < s1;
+        g4[j] = in ? __ldg(grd + x) : 0x7FF8000000000000ull;
+        a4[j] = in ? (__ldg(sob + x) & 0x7FFFFFFFFFFFFFFFull) : 0ull;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int x = s0 + lane + 32 * j;
+        const unsigned long long g = x < s1 ? order_key(g4[j]) : ~0ull;
+        if (g < mn) { mn = g; arg = x; }
+        amax = a4[j] > amax ? a4[j] : amax;
+      }
+    } else {
+      // wide window (nothing detected yet): 128 columns per round, the 8 loads of a round in flight together
+      for (int x0 = s0; x0 < s1; x0 += 128) {
+        unsigned long long g4[4], b4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int x = x0 + lane + 32 * j;
+          const bool in = x < s1;
+          g4[j] = in ? __ldg(grd + x) : 0x7FF8000000000000ull;
+          b4[j] = in ? (__ldg(sob + x) & 0x7FFFFFFFFFFFFFFFull) : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int x = x0 + lane + 32 * j;
+          const unsigned long long g = x < s1 ? order_key(g4[j]) : ~0ull;
+          if (g < mn) { mn = g; arg = x; }
+          amax = b4[j] > amax ? b4[j] : amax;
+        }
+      }
+    }
+    // first minimum: smallest key, then smallest index (np.argmin)
+    const unsigned mn_hi = __reduce_min_sync(fullmask, (unsigned)(mn >> 32));
+    const unsigned lo_c = (unsigned)(mn >> 32) == mn_hi ? (unsigned)mn : 0xFFFFFFFFu;
+    const unsigned mn_lo = __reduce_min_sync(fullmask, lo_c);
+    const bool mine = (unsigned)(mn >> 32) == mn_hi && (unsigned)mn == mn_lo;
+    arg = (int)__reduce_min_sync(fullmask, mine ? (unsigned)arg : 0x7FFFFFFFu);
+    const unsigned long long mn_key = ((unsigned long long)mn_hi << 32) | mn_lo;
+    const unsigned am_hi = __reduce_max_sync(fullmask, (unsigned)(amax >> 32));
+    const unsigned am_lo = __reduce_max_sync(fullmask, (unsigned)(amax >> 32) == am_hi ? (unsigned)amax : 0u);
+    if (mn_key < order_key((unsigned long long)__double_as_longlong(-p.min_strength))) r.pos_a = arg;   // :427-430
+    const double amax_d = __longlong_as_double((long long)(((unsigned long long)am_hi << 32) | am_lo));
+    if (amax_d > p.min_strength) {                                                        // :434-440
+      const unsigned long long thr = (unsigned long long)__double_as_longlong(__dmul_rn(amax_d, p.sobel_frac));
+      int right = -1;
+      if (small) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (a4[j] > thr) right = s0 + lane + 32 * j;      // out-of-window slots hold 0 and thr >= 0
+      } else {
+        for (int x0 = s0; x0 < s1; x0 += 128) {
+          unsigned long long b4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int x = x0 + lane + 32 * j;
+            b4[j] = x < s1 ? (__ldg(sob + x) & 0x7FFFFFFFFFFFFFFFull) : 0ull;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (b4[j] > thr) right = x0 + lane + 32 * j;
+        }
+      }
+      r.pos_b = __reduce_max_sync(fullmask, right);
+    }
+  }
+  r.final_pos = max(r.pos_a, r.pos_b);                                                   // :452-465
+  return r;
+}
+
+// Search result of every active frame for the state "nothing detected yet" (whole width between
+// the edge margins) - one warp per frame, all frames at once.  The speculative walks start in that
+// state and stay in it through frames without a detection (flame entering, burnt gas after the
+// exit), so without this a walk would pay a 1000-column search again and again.
+__global__ void __launch_bounds__(kSpecWarpsPerCta * 32) head_track_fullwidth_kernel(const HeadTrackParams p) {
+  const int lane = threadIdx.x & 31;
+  const int f = blockIdx.x * kSpecWarpsPerCta + (threadIdx.x >> 5);
+  if (f >= p.n_frames) return;
+  const int fl = (int)p.flags[f];
+  if (fl == 0) return;
+  TrackState none;
+  none.last_f = -1;
+  none.last_p = -1;
+  const FrameResult r = track_frame(p, f, fl, none, lane);
+  if (lane == 0) {
+    int32_t* o = p.out + (int64_t)f * 5;
+    o[0] = r.final_pos; o[1] = r.pos_a; o[2] = r.pos_b; o[3] = r.s0; o[4] = r.s1;
+  }
+}
+
+__global__ void __launch_bounds__(kSpecWarpsPerCta * 32) head_track_spec_kernel(const HeadTrackParams p) {
+  const int lane = threadIdx.x & 31;
+  const int seg = blockIdx.x * kSpecWarpsPerCta + (threadIdx.x >> 5);
+  const int f_lo = seg * kSegFrames;
+  if (f_lo >= p.n_frames) return;
+  const unsigned fullmask = 0xFFFFFFFFu;
+  const int fme = f_lo + lane;
+  const int flme = fme < p.n_frames ? (int)p.flags[fme] : 0;
+  unsigned act = __ballot_sync(fullmask, flme != 0);
+  TrackState st;
+  st.last_f = seg == 0 ? p.last_frame_in : -1;
+  st.last_p = seg == 0 ? p.last_pos_in : -1;
+  while (act) {
+    const int l = __ffs((int)act) - 1;
+    act &= act - 1;
+    const int f = f_lo + l;
+    const int fl = __shfl_sync(fullmask, flme, l);
+    if (st.last_p < 0) {            // still nothing detected: the full-width answer is already in out[f]
+      const int fp = __ldcg(p.out + (int64_t)f * 5);
+      if (fp >= 0) {
+        st.last_f = (int)(p.first_frame + f);
+        st.last_p = fp;
+      }
+      continue;
+    }
+    const FrameResult r = track_frame(p, f, fl, st, lane);
+    if (r.final_pos >= 0) {
+      st.last_f = (int)(p.first_frame + f);
+      st.last_p = r.final_pos;
+    }
+    if (lane == 0) {
+      int32_t* o = p.out + (int64_t)f * 5;
+      o[0] = r.final_pos; o[1] = r.pos_a; o[2] = r.pos_b; o[3] = r.s0; o[4] = r.s1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) head_track_commit_kernel(const HeadTrackParams p) {
+  __shared__ int s_exit_f;          // range-local index of the exit frame, or n_frames
+  const int tid = threadIdx.x, lane = tid & 31;
+  const unsigned fullmask = 0xFFFFFFFFu;
+  const int W = p.width;
+  if (tid < 32) {
+    TrackState cur;
+    cur.last_f = p.last_frame_in;
+    cur.last_p = p.last_pos_in;
+    int exit_f = p.n_frames;
+    const int n_seg = (p.n_frames + kSegFrames - 1) / kSegFrames;
+    const bool vec_flags = (reinterpret_cast<uintptr_t>(p.flags) & 15u) == 0;
+    for (int seg0 = 0; seg0 < n_seg && exit_f == p.n_frames; seg0 += 32) {
+    // lane L summarises segment seg0 + L: bit j of m_act = frame j reached the detector, bit j of
+    // m_one = it has a difference image (flag 1).  One round of loads per 1024 frames keeps the
+    // long empty stretches of a clip off the sequential path.
+    unsigned m_act = 0, m_one = 0;
+    {
+      const int fs = (seg0 + lane) * kSegFrames;
+      if (vec_flags && fs + kSegFrames <= p.n_frames) {
+        const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(p.flags + fs));
+        const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(p.flags + fs) + 1);
+        const uint32_t w8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t fl = (w8[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+          if (fl != 0) m_act |= 1u << j;
+          if (fl == 1) m_one |= 1u << j;
+        }
+      } else {
+        for (int j = 0; j < kSegFrames; ++j) {
+          const int f = fs + j;
+          const int fl = f < p.n_frames ? (int)p.flags[f] : 0;
+          if (fl != 0) m_act |= 1u << j;
+          if (fl == 1) m_one |= 1u << j;
+        }
+      }
+    }
+    unsigned busy = __ballot_sync(fullmask, m_act != 0);
+    while (busy && exit_f == p.n_frames) {
+      const int sl = __ffs((int)busy) - 1;
+      busy &= busy - 1;
+      const int seg = seg0 + sl;
+      const int f_lo = seg * kSegFrames;
+      const int fme = f_lo + lane;
+      unsigned act = __shfl_sync(fullmask, m_act, sl);
+      const unsigned one = __shfl_sync(fullmask, m_one, sl);
+      const int flme = ((act >> lane) & 1u) ? (((one >> lane) & 1u) ? 1 : 2) : 0;
+      if (!act) continue;
+      // what the speculation produced for my frame (before anything is overwritten)
+      const int spec_final = flme != 0 ? p.out[(int64_t)fme * 5] : -1;
+      TrackState spec;              // the speculation's state BEFORE the next active frame
+      spec.last_f = seg == 0 ? p.last_frame_in : -1;
+      spec.last_p = seg == 0 ? p.last_pos_in : -1;
+      // ---- re-run from the true state until it meets the speculation's state -------------------------
+      while (act && !(spec.last_f == cur.last_f && spec.last_p == cur.last_p)) {
+        const int l = __ffs((int)act) - 1;
+        act &= act - 1;
+        const int f = f_lo + l;
+        const int fl = __shfl_sync(fullmask, flme, l);
+        const int sf = __shfl_sync(fullmask, spec_final, l);
+        if (sf >= 0) {                                   // the speculation's state after this frame
+          spec.last_f = (int)(p.first_frame + f);
+          spec.last_p = sf;
+        }
+        const FrameResult r = track_frame(p, f, fl, cur, lane);
+        if (r.final_pos >= 0) {
+          cur.last_f = (int)(p.first_frame + f);
+          cur.last_p = r.final_pos;
+        }
+        if (lane == 0) {
+          int32_t* o = p.out + (int64_t)f * 5;
+          o[0] = r.final_pos; o[1] = r.pos_a; o[2] = r.pos_b; o[3] = r.s0; o[4] = r.s1;
+        }
+        if (r.final_pos >= 0 && r.final_pos >= W - p.exit_margin) {                      // :1488-1494
+          exit_f = f;
+          act = 0;
+        }
+      }
+      if (exit_f != p.n_frames || !act) continue;
+      // ---- the remaining frames of the segment stand as speculated ----------------------------------------
+      const bool mine = ((act >> lane) & 1u) != 0;
+      const unsigned det = __ballot_sync(fullmask, mine && spec_final >= 0);
+      const unsigned ext = __ballot_sync(fullmask, mine && spec_final >= 0 && spec_final >= W - p.exit_margin);
+      unsigned upto = det;                                // detections up to and including the exit frame
+      if (ext) {
+        const int le = __ffs((int)ext) - 1;
+        exit_f = f_lo + le;
+        upto &= (2u << le) - 1u;
+      }
+      if (upto) {
+        const int ll = 31 - __clz((int)upto);
+        cur.last_f = (int)(p.first_frame + f_lo + ll);
+        cur.last_p = __shfl_sync(fullmask, spec_final, ll);
+      }
+    }   // busy segments of this group
+    }   // groups of 32 segments
+    if (lane == 0) {
+      s_exit_f = exit_f;
+      p.stop[0] = exit_f == p.n_frames ? FF_NO_EXIT : (int)(p.first_frame + exit_f);
+      p.stop[1] = cur.last_f;
+      p.stop[2] = cur.last_p;
+    }
+  }
+  __syncthreads();
+  // frames after the exit frame were never reached by the reference loop (:1494)
+  const int64_t first_dead = (int64_t)s_exit_f + 1;
+  for (int64_t i = first_dead * 5 + tid; i < (int64_t)p.n_frames * 5; i += blockDim.x) p.out[i] = -1;
 }
 
 }  // namespace
@@ -605,27 +691,17 @@ int head_track_impl(const double* lines, const uint8_t* flags, int64_t n_frames,
   p.last_pos_in = last_pos_in;
   p.out = out;
   p.stop = stop;
-  // ring of 16*W-byte stages: as many as fit (2..8); very wide rows take the generic kernel
-  const size_t stage_bytes = (size_t)16 * width;
-  const size_t fixed = (size_t)kTrackMaxStages * (8 + 8 + sizeof(TrackMeta)) + 16;
-  const int fit = (int)((200 * 1024 - fixed) / stage_bytes);
-  const int shift = fit >= 8 ? 3 : (fit >= 4 ? 2 : (fit >= 2 ? 1 : 0));
-  const int stages = 1 << shift;
-  if (shift == 0 || (reinterpret_cast<uintptr_t>(lines) & 15u) != 0) {
-    head_track_generic_kernel<<<1, kHeadThreads, 0, st>>>(p);
+  if (getenv("FF_TRACK_SEQUENTIAL") == nullptr) {       // default: speculative parallel walk
+    const int64_t n_seg = (n_frames + kSegFrames - 1) / kSegFrames;
+    head_track_fullwidth_kernel<<<(unsigned)((n_frames + kSpecWarpsPerCta - 1) / kSpecWarpsPerCta), kSpecWarpsPerCta * 32, 0, st>>>(p);
+    FF_CUDA_TRY(cudaGetLastError());
+    head_track_spec_kernel<<<(unsigned)((n_seg + kSpecWarpsPerCta - 1) / kSpecWarpsPerCta), kSpecWarpsPerCta * 32, 0, st>>>(p);
+    FF_CUDA_TRY(cudaGetLastError());
+    head_track_commit_kernel<<<1, 256, 0, st>>>(p);
     FF_CUDA_TRY(cudaGetLastError());
     return FF_OK;
   }
-  const size_t smem = (size_t)stages * stage_bytes + fixed;
-  static PerDeviceInt cache;
-  int unused = 0;
-  const int rc_attr = cache.get([](int* v) -> int {
-    FF_CUDA_TRY(cudaFuncSetAttribute(head_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    *v = 1;
-    return FF_OK;
-  }, &unused);
-  if (rc_attr != FF_OK) return rc_attr;
-  head_track_kernel<<<1, kTrackThreads, smem, st>>>(p, shift);
+  head_track_generic_kernel<<<1, kHeadThreads, 0, st>>>(p);      // sequential walk (cross-check)
   FF_CUDA_TRY(cudaGetLastError());
   return FF_OK;
 }

@@ -146,3 +146,55 @@ def test_head_with_skip_frames_and_no_detection(engine):
     s, g = ho.detect_lines_scipy(d)
     lines = res.lines.cpu().numpy()
     assert np.array_equal(lines[12, 0], s) and np.array_equal(lines[12, 1], g)
+
+
+def _track_both_ways(engine, packed, n, h, w, hp, rate, cal, monkeypatch, **kw):
+    """(speculative, sequential) tracker outputs on the same lines."""
+    monkeypatch.delenv("FF_TRACK_SEQUENTIAL", raising=False)
+    spec_res = engine.process_head(packed, n, h, w, 12, hp, rate, cal, **kw)
+    spec_out = (spec_res.track.cpu().numpy(), spec_res.stop.cpu().numpy(), spec_res.flags.cpu().numpy())
+    monkeypatch.setenv("FF_TRACK_SEQUENTIAL", "1")
+    seq_res = engine.process_head(packed, n, h, w, 12, hp, rate, cal, **kw)
+    seq_out = (seq_res.track.cpu().numpy(), seq_res.stop.cpu().numpy(), seq_res.flags.cpu().numpy())
+    monkeypatch.delenv("FF_TRACK_SEQUENTIAL", raising=False)
+    return spec_out, seq_out
+
+
+@pytest.mark.parametrize("case", ["long_flame", "slow_no_exit", "noise", "late_start"])
+def test_speculative_tracker_equals_sequential_walk(engine, monkeypatch, case):
+    """The speculative parallel tracker (32 segments walked at once, then validated in order) must
+    reproduce the sequential walk exactly - several batches of 1024 frames, segments that do not
+    lock on at once, an exit in the middle of a batch, frames without detections."""
+    rng = np.random.default_rng(7)
+    if case == "long_flame":        # ~2700 flame frames: 3 batches, exit well inside the last one
+        spec = syn.SyntheticSpec(width=1024, height=32, n_frames=3000, style="nova", t_enter=40.0, velocity=0.37,
+                                 seed=21)
+        frames = syn.render_frames(spec)
+    elif case == "slow_no_exit":    # the front never reaches the exit margin
+        spec = syn.SyntheticSpec(width=512, height=24, n_frames=1500, style="mini", t_enter=100.0, velocity=0.2,
+                                 seed=22)
+        frames = syn.render_frames(spec)
+    elif case == "late_start":      # long empty lead-in (batches without active frames), then the flame
+        spec = syn.SyntheticSpec(width=256, height=16, n_frames=2600, style="mini", t_enter=2300.0, velocity=1.1,
+                                 seed=23)
+        frames = syn.render_frames(spec)
+    else:                           # bright random blobs: every frame non-empty, erratic detections
+        frames = rng.integers(30, 60, size=(1300, 16, 256)).astype(np.uint16)
+        for i in range(1, len(frames)):
+            x = int(rng.integers(0, 230))
+            frames[i, :, x:x + int(rng.integers(4, 25))] += int(rng.integers(300, 3000))
+    n, h, w = frames.shape
+    packed = dev(syn.pack_frames(frames, 12), engine)
+    hp = HeadParams(exit_margin_px=15 if case != "noise" else 1)
+    (t1, s1, f1), (t2, s2, f2) = _track_both_ways(engine, packed, n, h, w, hp, 160000, 0.000833333, monkeypatch)
+    assert np.array_equal(f1, f2)
+    assert np.array_equal(s1, s2), (s1, s2)
+    assert np.array_equal(t1, t2), np.nonzero((t1 != t2).any(axis=1))[0][:10]
+    if case == "long_flame":
+        assert (f1 == 1).sum() > 2048 and s1[0] != 2**31 - 1
+    if case == "slow_no_exit":
+        assert s1[0] == 2**31 - 1 and (t1[:, 0] >= 0).sum() > 100
+    # carried-in tracker state (a range that continues an earlier one)
+    (t3, s3, _), (t4, s4, _) = _track_both_ways(engine, packed, n, h, w, hp, 160000, 0.000833333, monkeypatch,
+                                                tracker_state=(3, 17))
+    assert np.array_equal(t3, t4) and np.array_equal(s3, s4)
