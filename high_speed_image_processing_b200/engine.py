@@ -438,7 +438,7 @@ class FlameFrontEngine:
                 float(params.min_gradient_strength), float(params.sobel_threshold_fraction),
                 params.exit_margin_px, int(tracker_state[0]), int(tracker_state[1]), track.data_ptr(),
                 stop.data_ptr(), st), "ff_head_track")
-        self.launches += 4
+        self.launches += 6      # stream, flags, band, full-width, speculative walk, commit
         done, bg_host, line_host = fetch
         done.synchronize()
         scalars = ClipScalars.from_frame0_stats(int(bg_host.item()), line_host.numpy())
