@@ -413,6 +413,26 @@ def own_arm(args) -> None:
         cpu = {"value": r["value"], "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{r['frames']} frames ({l1 - l0} lead-in + {f1 - f0_} flame frames, the clip's "
                          f"proportions) in {r['seconds']:.1f} s: NumPy decode + per-frame path, serial"}
+        # ... and on every host core, the reference's round-robin decomposition (parallel.py:99-100),
+        # one worker process per core (what `mpiexec -n <cores>` would run; mpi4py is not installed)
+        try:
+            import multiprocessing as mp
+            from oracle import flame_oracle as fo
+            sample = np.concatenate([b[fb:] for _, b in blocks])
+            cores = os.cpu_count() or 1
+            _POOL_STATE.update(packed=sample, frame0=fo.frames_from_bytes(frame0.cpu().numpy(), 1, h, w, 12)[0],
+                               h=h, w=w, fb=fb, n=sample.size // fb, method="half_maximum")
+            with mp.get_context("fork").Pool(cores) as pool:
+                jobs = [(k, cores) for k in range(cores)]
+                pool.map(_pool_worker, jobs, chunksize=1)                      # warm-up
+                t_all = time.perf_counter()
+                for _ in range(2):
+                    pool.map(_pool_worker, jobs, chunksize=1)
+                t_all = (time.perf_counter() - t_all) / 2
+            cpu["all_cores"] = {"value": (sample.size // fb) / t_all, "unit": UNIT, "cores": cores,
+                                "how": "same sample, round-robin over one worker process per core"}
+        except Exception as exc:                                               # never fail the GPU line over it
+            cpu["all_cores"] = {"error": repr(exc)}
 
     if rank == 0:
         peaks_path = REPO / "MEASURED_PEAKS.json"

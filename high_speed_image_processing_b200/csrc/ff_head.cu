@@ -554,12 +554,12 @@ __global__ void __launch_bounds__(256) head_track_commit_kernel(const HeadTrackP
         act &= act - 1;
         const int f = f_lo + l;
         const int fl = __shfl_sync(fullmask, flme, l);
+        const FrameResult r = track_frame(p, f, fl, cur, lane);      // first: its loads overlap spec_final's
         const int sf = __shfl_sync(fullmask, spec_final, l);
         if (sf >= 0) {                                   // the speculation's state after this frame
           spec.last_f = (int)(p.first_frame + f);
           spec.last_p = sf;
         }
-        const FrameResult r = track_frame(p, f, fl, cur, lane);
         if (r.final_pos >= 0) {
           cur.last_f = (int)(p.first_frame + f);
           cur.last_p = r.final_pos;
