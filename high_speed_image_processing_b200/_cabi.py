@@ -25,7 +25,8 @@ FF_DIFF_NONE, FF_DIFF_U16, FF_DIFF_F32, FF_DIFF_F64 = 0, 1, 2, 3
 FF_POS_NONE = -1
 FF_POS_DROPPED = -2
 FF_NO_EXIT = 2147483647
-FF_ABI_VERSION = 3
+FF_PX_U8, FF_PX_U16, FF_PX_F64 = 0, 1, 3
+FF_ABI_VERSION = 4
 
 
 class FlameFrontLibraryError(RuntimeError):
@@ -71,6 +72,12 @@ SIGNATURES = {
                              _vp, _vp, _vp, _vp]),
     "ff_head_track": (_int, [_vp, _vp, _i64, _i64, _int, _i32, _i32, _i32, C.c_double, C.c_double, _i32, _i32, _i32,
                              _vp, _vp, _vp]),
+    "ff_frame_subtract_background": (_int, [_vp, _int, _i64, C.c_double, _vp, _vp]),
+    "ff_frame_difference": (_int, [_vp, _vp, _int, _i64, C.c_double, _vp, _vp]),
+    "ff_frame_three_difference": (_int, [_vp, _vp, _vp, _int, _i64, C.c_double, _vp, _vp]),
+    "ff_frame_count_above": (_int, [_vp, _int, _i64, C.c_double, _vp, _vp]),
+    "ff_head_images": (_int, [_vp, _vp, _i64, _int, _int, _int, _i32, _i32, _i32, _int, C.POINTER(C.c_double), _int,
+                              _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ff_host_ctx_create": (_int, [_int, _i64, C.POINTER(_vp)]),
     "ff_host_ctx_destroy": (_int, [_vp]),
     "ff_host_upload": (_int, [_vp, _vp, _vp, _i64]),

@@ -32,6 +32,12 @@ int head_lines_impl(const void*, const void*, int64_t, int, int, int, const int3
                     const double*, int, const uint8_t*, double*, uint8_t*, int32_t*, cudaStream_t);
 int head_track_impl(const double*, const uint8_t*, int64_t, int64_t, int, int32_t, int32_t, int32_t, double, double,
                     int32_t, int32_t, int32_t, int32_t*, int32_t*, cudaStream_t);
+int frame_subtract_background_impl(const void*, int, int64_t, double, double*, cudaStream_t);
+int frame_difference_impl(const void*, const void*, int, int64_t, double, double*, cudaStream_t);
+int frame_three_difference_impl(const void*, const void*, const void*, int, int64_t, double, double*, cudaStream_t);
+int frame_count_above_impl(const void*, int, int64_t, double, int64_t*, cudaStream_t);
+int head_images_impl(const void*, const void*, int64_t, int, int, int, int32_t, int32_t, int32_t, int, const double*,
+                     int, const uint8_t*, double*, double*, double*, double*, double*, double*, uint8_t*, cudaStream_t);
 
 }  // namespace ff
 
@@ -321,6 +327,38 @@ int ff_head_track(const double* lines_dev, const uint8_t* flags_dev, int64_t n_f
   return head_track_impl(lines_dev, flags_dev, n_frames, first_frame, width, edge_margin_px, max_displacement_px,
                          search_window_px, min_gradient_strength, sobel_threshold_fraction, exit_margin_px,
                          last_frame_in, last_pos_in, out_dev, stop_dev, static_cast<cudaStream_t>(stream));
+}
+
+int ff_frame_subtract_background(const void* image_dev, int px_type, int64_t n_px, double background,
+                                 double* out_dev, void* stream) {
+  return frame_subtract_background_impl(image_dev, px_type, n_px, background, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int ff_frame_difference(const void* current_dev, const void* prior_dev, int px_type, int64_t n_px, double threshold,
+                        double* out_dev, void* stream) {
+  return frame_difference_impl(current_dev, prior_dev, px_type, n_px, threshold, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int ff_frame_three_difference(const void* prev_dev, const void* curr_dev, const void* next_dev, int px_type,
+                              int64_t n_px, double threshold, double* out_dev, void* stream) {
+  return frame_three_difference_impl(prev_dev, curr_dev, next_dev, px_type, n_px, threshold, out_dev,
+                                     static_cast<cudaStream_t>(stream));
+}
+
+int ff_frame_count_above(const void* frame_dev, int px_type, int64_t n_px, double threshold, int64_t* count_dev,
+                         void* stream) {
+  return frame_count_above_impl(frame_dev, px_type, n_px, threshold, count_dev, static_cast<cudaStream_t>(stream));
+}
+
+int ff_head_images(const void* frames_dev, const void* halo_dev, int64_t n_frames, int height, int width, int bits,
+                   int32_t bg, int32_t bg_halo, int32_t diff_thr, int morphology_size, const double* gauss_weights_host,
+                   int radius, const uint8_t* skip_dev, double* sub_out_dev, double* diff_out_dev, double* opened_out_dev,
+                   double* blurred_out_dev, double* sobel_out_dev, double* gradient_out_dev, uint8_t* state_out_dev,
+                   void* stream) {
+  return head_images_impl(frames_dev, halo_dev, n_frames, height, width, bits, bg, bg_halo, diff_thr, morphology_size,
+                          gauss_weights_host, radius, skip_dev, sub_out_dev, diff_out_dev, opened_out_dev,
+                          blurred_out_dev, sobel_out_dev, gradient_out_dev, state_out_dev,
+                          static_cast<cudaStream_t>(stream));
 }
 
 int ff_host_ctx_create(int device, int64_t chunk_bytes, ff_host_ctx** ctx_out) {

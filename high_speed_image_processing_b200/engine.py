@@ -12,13 +12,14 @@ import ctypes as C
 import math
 import os
 from dataclasses import dataclass, field
-from typing import Optional, Sequence, Union
+from typing import Dict, Optional, Sequence, Union
 
 import numpy as np
 import torch
 
 from . import _cabi
-from ._cabi import FF_DIFF_F32, FF_DIFF_F64, FF_DIFF_NONE, FF_DIFF_U16, FF_METHOD, FF_NO_EXIT
+from ._cabi import (FF_DIFF_F32, FF_DIFF_F64, FF_DIFF_NONE, FF_DIFF_U16, FF_METHOD, FF_NO_EXIT, FF_PX_F64,
+                    FF_PX_U8, FF_PX_U16)
 
 DETECTION_METHODS = tuple(FF_METHOD)  # ("threshold", "gradient", "half_maximum")
 INT32_MAX = 2**31 - 1
@@ -443,6 +444,126 @@ class FlameFrontEngine:
         done.synchronize()
         scalars = ClipScalars.from_frame0_stats(int(bg_host.item()), line_host.numpy())
         return HeadRangeResult(first_frame, track, flags, stop, lines if keep_lines else None, scalars)
+
+    # ------------------------------------------------------------------ frame-level operators (seam B3)
+    _PX_TYPES = {torch.uint8: FF_PX_U8, torch.uint16: FF_PX_U16, torch.float64: FF_PX_F64}
+
+    def _px_type(self, t: torch.Tensor, name: str) -> int:
+        self._check_dev(t, name)
+        if t.dtype not in self._PX_TYPES:
+            raise TypeError(f"{name}: frame-level operators take uint8, uint16 or float64 frames, got {t.dtype}")
+        return self._PX_TYPES[t.dtype]
+
+    def frame_op(self, op: str, frames: Sequence[torch.Tensor], scalar: float) -> torch.Tensor:
+        """Element-wise float64 operators of scripts/process_videos.py on decoded device frames:
+        ``"subtract_background"`` (:670-674, one frame), ``"difference"`` (:677-701, current, prior),
+        ``"three_difference"`` (:704-740, prev, curr, next).  Returns a float64 tensor of the frames' shape."""
+        arity = {"subtract_background": 1, "difference": 2, "three_difference": 3}
+        if op not in arity:
+            raise ValueError(f"unknown frame operator {op!r}")
+        if len(frames) != arity[op]:
+            raise ValueError(f"{op} takes {arity[op]} frame(s)")
+        px = self._px_type(frames[0], "frame")
+        for f in frames[1:]:
+            if self._px_type(f, "frame") != px or f.shape != frames[0].shape:
+                raise ValueError("frames must share dtype and shape")
+        n = frames[0].numel()
+        out = torch.empty(frames[0].shape, dtype=torch.float64, device=self.device)
+        if n == 0:
+            return out
+        st = self._stream()
+        with torch.cuda.device(self.device):
+            if op == "subtract_background":
+                rc = self._lib.ff_frame_subtract_background(frames[0].data_ptr(), px, n, float(scalar), out.data_ptr(), st)
+            elif op == "difference":
+                rc = self._lib.ff_frame_difference(frames[0].data_ptr(), frames[1].data_ptr(), px, n, float(scalar),
+                                                   out.data_ptr(), st)
+            else:
+                rc = self._lib.ff_frame_three_difference(frames[0].data_ptr(), frames[1].data_ptr(),
+                                                         frames[2].data_ptr(), px, n, float(scalar), out.data_ptr(), st)
+        _cabi.check(rc, f"ff_frame_{op}")
+        self.launches += 1
+        return out
+
+    def frame_count_above(self, frame: torch.Tensor, threshold: float) -> int:
+        """``np.sum(frame > threshold)`` of ``is_empty_frame`` (:759) on a decoded device frame."""
+        px = self._px_type(frame, "frame")
+        if frame.numel() == 0:
+            return 0
+        count = torch.empty(1, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.ff_frame_count_above(frame.data_ptr(), px, frame.numel(), float(threshold),
+                                                       count.data_ptr(), self._stream()), "ff_frame_count_above")
+        self.launches += 1
+        return int(count.item())
+
+    HEAD_IMAGES = ("frame_subtracted", "frame_diff", "noise_removed", "blurred", "sobel_output", "gradient_output")
+
+    def head_images(self, frames: torch.Tensor, n_frames: int, height: int, width: int, bits: int, background: int,
+                    *, frame_diff_threshold: float = 5.0, morphology_kernel_size: int = 3,
+                    gaussian_sigma: float = 1.5, halo: Optional[torch.Tensor] = None,
+                    halo_background: Optional[int] = None, skip: Optional[torch.Tensor] = None,
+                    want: Sequence[str] = HEAD_IMAGES) -> Dict[str, torch.Tensor]:
+        """Full-frame intermediates of ``FlameDetector.detect`` (scripts/process_videos.py:380-413) for
+        ``n_frames`` device-resident frames (``ff_head_images``): float64 ``[n,H,W]`` tensors named like
+        the fields of ``FlameDetectionResult`` (:197-217), plus ``"state"`` uint8[n] (0 skipped, 1 all
+        valid, 2 no prior frame: only ``frame_subtracted`` is meaningful)."""
+        from .head import gaussian_weights
+        self._check_dev(frames, "frames")
+        fb = frame_nbytes(height, width, bits)
+        if frames.numel() * frames.element_size() < n_frames * fb:
+            raise ValueError(f"frames must hold at least {n_frames * fb} bytes")
+        unknown = [w for w in want if w not in self.HEAD_IMAGES]
+        if unknown:
+            raise ValueError(f"unknown image(s) {unknown}; options: {', '.join(self.HEAD_IMAGES)}")
+        if frame_diff_threshold < 0:
+            raise ValueError("frame_diff_threshold must be >= 0")
+        if background < 0 or (halo_background is not None and halo_background < 0):
+            raise ValueError("background scalars must be >= 0")
+        if width < 2:
+            raise ValueError("Shape of array too small to calculate a numerical gradient, "
+                             "at least 2 elements are required.")
+        if halo is not None:
+            self._check_dev(halo, "halo")
+        if skip is not None:
+            self._check_dev(skip, "skip")
+            if skip.dtype != torch.uint8 or skip.numel() != n_frames:
+                raise ValueError("skip must be uint8[n_frames]")
+        weights = np.ascontiguousarray(gaussian_weights(gaussian_sigma), dtype=np.float64)
+        out = {name: torch.empty((n_frames, height, width), dtype=torch.float64, device=self.device) for name in want}
+        state = torch.empty(n_frames, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.ff_head_images(
+                frames.data_ptr(), _ptr(halo), n_frames, height, width, bits, int(background),
+                int(background if halo_background is None else halo_background),
+                _clamp_i32(math.ceil(frame_diff_threshold)), int(morphology_kernel_size),
+                weights.ctypes.data_as(C.POINTER(C.c_double)), (weights.size - 1) // 2, _ptr(skip),
+                *(_ptr(out.get(name)) for name in self.HEAD_IMAGES), state.data_ptr(), self._stream()),
+                "ff_head_images")
+        self.launches += 1
+        out["state"] = state
+        return out
+
+    def head_track_lines(self, lines: torch.Tensor, flags: torch.Tensor, first_frame: int, width: int, params,
+                         max_displacement: int, tracker_state=(-1, -1)):
+        """``ff_head_track`` on caller-provided centre-row lines ``float64[n,2,W]`` (Sobel, gradient) and
+        flags ``uint8[n]``: search window (:317-348), candidates (:420-465), exit stop.  Returns
+        ``(track int32[n,5], stop int32[3])`` device tensors."""
+        self._check_dev(lines, "lines")
+        self._check_dev(flags, "flags")
+        n = flags.numel()
+        if lines.dtype != torch.float64 or lines.numel() != n * 2 * width or flags.dtype != torch.uint8:
+            raise ValueError("lines must be float64[n,2,W] and flags uint8[n]")
+        track = torch.empty((n, 5), dtype=torch.int32, device=self.device)
+        stop = torch.empty(3, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.ff_head_track(
+                lines.data_ptr(), flags.data_ptr(), n, first_frame, width, params.edge_margin_px, max_displacement,
+                params.search_window_px, float(params.min_gradient_strength),
+                float(params.sobel_threshold_fraction), params.exit_margin_px, int(tracker_state[0]),
+                int(tracker_state[1]), track.data_ptr(), stop.data_ptr(), self._stream()), "ff_head_track")
+        self.launches += 3
+        return track, stop
 
     def truncate(self, pos: torch.Tensor, first_frame: int, first_exit: torch.Tensor) -> None:
         """Mark frames at/after the (global) first exit frame as dropped (README.md:145-149)."""

@@ -69,6 +69,63 @@ class HeadTrackSummary:
     stop: Optional[Tuple[str, int]] = None       # ("exit" | "velocity_drop", frame)
 
 
+class VelocityBook:
+    """The detector's position / velocity / DDT bookkeeping (scripts/process_videos.py:467-516),
+    one ``update`` per detect() call.  Entries are ``[frame_idx, v_backward1, v_backward2, v_central]``:
+    first-order backward, second-order backward, and the second-order central difference that is
+    filled into the PREVIOUS entry once the next position is known."""
+
+    def __init__(self, frame_rate: float, calibration: float, ddt_velocity_jump_m_s: float):
+        self.frame_rate = frame_rate
+        self.calibration = calibration
+        self.ddt_jump = ddt_velocity_jump_m_s
+        self.history: List[Tuple[int, Optional[int]]] = []
+        self.velocities: List[VelocityEntry] = []
+        self.ddt_frame: Optional[int] = None
+
+    def reset(self) -> None:
+        self.history.clear()
+        self.velocities.clear()
+        self.ddt_frame = None
+
+    def last_detection(self) -> Tuple[int, int]:
+        """(frame, position) of the latest frame with a position, or (-1, -1)."""
+        for f_idx, pos in reversed(self.history):
+            if pos is not None:
+                return f_idx, pos
+        return -1, -1
+
+    def update(self, frame_idx: int, final_position: Optional[int]) -> None:
+        history, vel, calibration = self.history, self.velocities, self.calibration
+        history.append((frame_idx, final_position))
+        if final_position is None or len(history) < 2:
+            return
+        curr_frame, curr_pos = history[-1]
+        prev_frame, prev_pos = history[-2]
+        if prev_pos is None or not self.frame_rate > 0:
+            return
+        dt = (curr_frame - prev_frame) / self.frame_rate
+        if not dt > 0:
+            return
+        v_backward1 = (curr_pos - prev_pos) * calibration / dt
+        v_backward2 = None
+        if len(history) >= 3:
+            _, prev2_pos = history[-3]
+            if prev2_pos is not None:
+                v_backward2 = (3 * curr_pos - 4 * prev_pos + prev2_pos) * calibration / (2 * dt)
+                v_central = (curr_pos - prev2_pos) * calibration / (2 * dt)
+                if len(vel) >= 1:
+                    old = vel[-1]
+                    vel[-1] = [old[0], old[1], old[2], v_central]
+        vel.append([frame_idx, v_backward1, v_backward2, None])
+        if self.ddt_frame is None and len(vel) >= 2:
+            if v_backward1 - vel[-2][1] > self.ddt_jump:
+                self.ddt_frame = frame_idx
+
+    def clear_last_central(self) -> None:
+        _clear_last_central(self.velocities)
+
+
 def finish_head_track(track: np.ndarray, flags: np.ndarray, first_frame: int, width: int, frame_rate: float,
                       calibration: float, offset: float, time_of: Callable[[int], float],
                       params: HeadParams) -> HeadTrackSummary:
@@ -77,8 +134,8 @@ def finish_head_track(track: np.ndarray, flags: np.ndarray, first_frame: int, wi
     ``track`` int32[n,5] = (final, pos_min_gradient, pos_rightmost_sobel, search_start, search_end),
     ``flags`` uint8[n] (0 = frame never reached the detector)."""
     out = HeadTrackSummary()
-    history: List[Tuple[int, Optional[int]]] = []
-    vel = out.velocity_history
+    book = VelocityBook(frame_rate, calibration, params.ddt_velocity_jump_m_s)
+    vel = out.velocity_history = book.velocities
     for i in np.nonzero(flags)[0].tolist():
         frame_idx = first_frame + i
         final, pos_a, pos_b, s0, s1 = (int(v) for v in track[i])
@@ -88,40 +145,19 @@ def finish_head_track(track: np.ndarray, flags: np.ndarray, first_frame: int, wi
         out.per_frame.append({"frame": frame_idx, "final": final_position,
                               "min_gradient": pos_a if pos_a >= 0 else None,
                               "rightmost_sobel": pos_b if pos_b >= 0 else None, "search": [s0, s1]})
-        history.append((frame_idx, final_position))
-        # ---- velocities and DDT (:479-516) ----
-        if final_position is not None and len(history) >= 2:
-            curr_frame, curr_pos = history[-1]
-            prev_frame, prev_pos = history[-2]
-            if prev_pos is not None and frame_rate > 0:
-                dt = (curr_frame - prev_frame) / frame_rate
-                if dt > 0:
-                    v_backward1 = (curr_pos - prev_pos) * calibration / dt
-                    v_backward2 = None
-                    v_central = None
-                    if len(history) >= 3:
-                        _, prev2_pos = history[-3]
-                        if prev2_pos is not None:
-                            v_backward2 = (3 * curr_pos - 4 * prev_pos + prev2_pos) * calibration / (2 * dt)
-                            v_central = (curr_pos - prev2_pos) * calibration / (2 * dt)
-                            if len(vel) >= 1:
-                                old = vel[-1]
-                                vel[-1] = [old[0], old[1], old[2], v_central]
-                    vel.append([frame_idx, v_backward1, v_backward2, None])
-                    if out.ddt_frame is None and len(vel) >= 2:
-                        if v_backward1 - vel[-2][1] > params.ddt_velocity_jump_m_s:
-                            out.ddt_frame = frame_idx
+        book.update(frame_idx, final_position)          # velocities and DDT (:479-516)
+        out.ddt_frame = book.ddt_frame
         velocity = vel[-1][1] if vel else None
         # ---- stop rules (:1486-1509); the stopping frame is not recorded ----
         if final_position is not None and final_position >= width - params.exit_margin_px:
-            _clear_last_central(vel)
+            book.clear_last_central()
             out.stop = ("exit", frame_idx)
             break
         if velocity is not None and len(vel) >= 2:
             prev_v1 = vel[-2][1]
             if prev_v1 is not None and prev_v1 > 100:
                 if (prev_v1 - velocity) / prev_v1 > 0.5:
-                    _clear_last_central(vel)
+                    book.clear_last_central()
                     out.stop = ("velocity_drop", frame_idx)
                     break
         if final_position is not None:

@@ -11,6 +11,11 @@ the reference (scripts/process_videos.py:1441-1516) is replaced by the B200 engi
     [multi-GPU: all-reduce(min) of the exit frame, all-gather of positions]
     -> ff_truncate -> host: Time_s, Position_m, text files         (:1449-1452, :1512, :1561-1619)
 
+The reference's frame-level names (``FlameDetector``, ``FlameDetectorConfig``,
+``FlameDetectionResult``, ``subtract_scalar_background``, ``subtract_prior_frame``,
+``three_frame_difference``, ``is_empty_frame``, ``write_results``) are importable from here as from
+the reference script; they live in ``detector.py`` and run on the GPU frame by frame.
+
 Matplotlib diagnostics (:783-1270) are out of scope and never on this path.
 """
 from __future__ import annotations
@@ -23,6 +28,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
+from .detector import (FlameDetectionResult, FlameDetector, FlameDetectorConfig, is_empty_frame,  # noqa: F401
+                       subtract_prior_frame, subtract_scalar_background, three_frame_difference, write_results)
 from .engine import ClipScalars, DetectionParams, DETECTION_METHODS
 from .head import HeadParams, finish_head_track
 from .photron import MPIVideoProcessor, PhotonVideo, SpatialCalibration, open_video

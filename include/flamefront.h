@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FF_ABI_VERSION 3
+#define FF_ABI_VERSION 4
 
 /* status codes */
 #define FF_OK                 0
@@ -50,6 +50,11 @@ extern "C" {
 #define FF_DIFF_U16   1   /* lossless when diff_thr >= 0: values are integers in [0,65535] */
 #define FF_DIFF_F32   2
 #define FF_DIFF_F64   3   /* the reference's own dtype (float64)                        */
+
+/* element type of a decoded frame handed to the frame-level operators */
+#define FF_PX_U8   0
+#define FF_PX_U16  1
+#define FF_PX_F64  3
 
 #define FF_POS_NONE     (-1)
 #define FF_POS_DROPPED  (-2)
@@ -208,6 +213,46 @@ int ff_head_track(const double* lines_dev, const uint8_t* flags_dev, int64_t n_f
                   int width, int32_t edge_margin_px, int32_t max_displacement_px, int32_t search_window_px,
                   double min_gradient_strength, double sobel_threshold_fraction, int32_t exit_margin_px,
                   int32_t last_frame_in, int32_t last_pos_in, int32_t* out_dev, int32_t* stop_dev, void* stream);
+
+/* ---- frame-level operators (the per-frame seam of scripts/process_videos.py) ----------------------
+ * What a caller gets who uses the reference's frame functions instead of its driver loop.  Inputs
+ * are DECODED frames ([H,W] arrays as PhotonVideo.__getitem__ returns them, src/photron/video.py:559-584)
+ * of px_type FF_PX_U8 / FF_PX_U16 / FF_PX_F64, n_px = H*W elements; outputs are float64 like the
+ * reference's (one IEEE operation per NumPy operation, so values are bit-identical).
+ *   ff_frame_subtract_background  subtract_scalar_background (:670-674): x.astype(f64) - bg; x[x<0] = 0
+ *   ff_frame_difference           subtract_prior_frame (:677-701): d = cur - prior; d[d < thr] = 0
+ *   ff_frame_three_difference     three_frame_difference (:704-740): min(|cur-prev|, |next-cur|), thresholded
+ *   ff_frame_count_above          np.sum(frame > noise_threshold) of is_empty_frame (:759); count_dev int64[1]  */
+int ff_frame_subtract_background(const void* image_dev, int px_type, int64_t n_px, double background,
+                                 double* out_dev, void* stream);
+int ff_frame_difference(const void* current_dev, const void* prior_dev, int px_type, int64_t n_px,
+                        double threshold, double* out_dev, void* stream);
+int ff_frame_three_difference(const void* prev_dev, const void* curr_dev, const void* next_dev, int px_type,
+                              int64_t n_px, double threshold, double* out_dev, void* stream);
+int ff_frame_count_above(const void* frame_dev, int px_type, int64_t n_px, double threshold,
+                         int64_t* count_dev, void* stream);
+
+/* ff_head_images: every full-frame intermediate FlameDetector.detect returns in its
+ * FlameDetectionResult (scripts/process_videos.py:197-217, computed at :380-413), for n_frames frames
+ * stored as in the .mraw file (or a single decoded frame: bits = 16 / 8):
+ *   sub_out       frame_subtracted = max(x - bg, 0)                                  (:380)
+ *   diff_out      frame_diff = sub - prior_sub, values < diff_thr zeroed             (:397-399)
+ *   opened_out    noise_removed = grey_opening(frame_diff, size=(k,k)), k odd <= 7   (:403-404)
+ *   blurred_out   gaussian_filter(noise_removed, sigma)                               (:407)
+ *   sobel_out     sobel(blurred, axis=1)                                              (:410)
+ *   gradient_out  np.gradient(blurred, axis=1)                                        (:413)
+ * each float64[n_frames,H,W], nullable; float64 stages in SciPy's operation order, mode 'reflect'.
+ *   bg / bg_halo        integer background scalar of the frames / of the halo frame (detect() keeps
+ *                       its prior frame as it was subtracted at ITS call, :469); both >= 0
+ *   gauss_weights_host  2*radius+1 float64 taps (scipy _gaussian_kernel1d), HOST pointer
+ *   state_out_dev       uint8[n_frames], nullable: 0 listed in skip_dev (outputs zeroed), 1 all images
+ *                       valid, 2 no prior frame (only sub_out is meaningful; the reference returns None
+ *                       for the others, :386-393)                                                      */
+int ff_head_images(const void* frames_dev, const void* halo_dev, int64_t n_frames, int height, int width,
+                   int bits, int32_t bg, int32_t bg_halo, int32_t diff_thr, int morphology_size,
+                   const double* gauss_weights_host, int radius, const uint8_t* skip_dev,
+                   double* sub_out_dev, double* diff_out_dev, double* opened_out_dev, double* blurred_out_dev,
+                   double* sobel_out_dev, double* gradient_out_dev, uint8_t* state_out_dev, void* stream);
 
 /* ---- host-resident clips: chunked H2D streaming -----------------------------------------------
  * The end-to-end form of stages 2b-4 for a clip that lives in host memory (pinned, or the

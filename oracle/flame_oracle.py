@@ -109,6 +109,15 @@ def frame_difference(current: np.ndarray, prior: np.ndarray, threshold: float) -
     return diff
 
 
+def three_frame_difference(frame_prev: np.ndarray, frame_curr: np.ndarray, frame_next: np.ndarray,
+                           threshold: float = 0.0) -> np.ndarray:
+    """scripts/process_videos.py:704-740."""
+    prev, curr, nxt = (f.astype(np.float64) for f in (frame_prev, frame_curr, frame_next))
+    motion = np.minimum(np.abs(curr - prev), np.abs(nxt - curr))
+    motion[motion < threshold] = 0
+    return motion
+
+
 def background_scalar(frame0: np.ndarray) -> float:
     """scripts/process_videos.py:1357-1358."""
     return float(np.max(frame0))

@@ -42,6 +42,60 @@ def detect_lines_scipy(frame_diff: np.ndarray, kernel_size: int = 3, sigma: floa
     return sobel_output[row, :], gradient_output[row, :]
 
 
+def detect_images_scipy(frame_sub: np.ndarray, prior_sub: Optional[np.ndarray], threshold: float = 5.0,
+                        kernel_size: int = 3, sigma: float = 1.5) -> dict:
+    """Every full-frame intermediate of FlameDetector.detect (:380-413), named like the fields of
+    FlameDetectionResult (:197-217); the ones after ``frame_subtracted`` are None without a prior."""
+    from scipy.ndimage import gaussian_filter, grey_opening, sobel
+    out = {"frame_subtracted": frame_sub, "frame_diff": None, "noise_removed": None, "blurred": None,
+           "sobel_output": None, "gradient_output": None}
+    if prior_sub is None:
+        return out
+    out["frame_diff"] = fo.frame_difference(frame_sub, prior_sub, threshold)
+    out["noise_removed"] = grey_opening(out["frame_diff"], size=(kernel_size, kernel_size))
+    out["blurred"] = gaussian_filter(out["noise_removed"], sigma=sigma)
+    out["sobel_output"] = sobel(out["blurred"], axis=1)
+    out["gradient_output"] = np.gradient(out["blurred"], axis=1)
+    return out
+
+
+class FrameDetectorOracle:
+    """FlameDetector driven frame by frame (:350-537) without the driver loop around it: the
+    restated search bounds / candidate selection / velocity bookkeeping on the SciPy images."""
+
+    def __init__(self, frame_rate: float, calibration: float, cfg: Optional["HeadConfig"] = None,
+                 kernel_size: int = 3):
+        self.cfg = cfg or HeadConfig()
+        self.kernel_size = kernel_size
+        self.frame_rate, self.calibration = frame_rate, calibration
+        self.maxdisp = max_displacement_px(frame_rate, calibration, self.cfg)
+        self.history: List[Tuple[int, Optional[int]]] = []
+        self.velocities: List[list] = []
+        self.ddt_frame: Optional[int] = None
+        self.prior: Optional[np.ndarray] = None
+
+    def detect(self, frame: np.ndarray, frame_idx: int, background: float) -> dict:
+        cfg = self.cfg
+        w = frame.shape[1]
+        sub = fo.subtract_scalar_background(frame, background)
+        last = next(((f, p) for f, p in reversed(self.history) if p is not None), None)
+        if last is None:
+            s0, s1 = cfg.edge_margin_px, w - cfg.edge_margin_px
+        else:
+            lf, lp = last
+            s0, s1 = lp, min(w - cfg.edge_margin_px, lp + self.maxdisp * max(1, frame_idx - lf) + cfg.search_window_px)
+        imgs = detect_images_scipy(sub, self.prior, cfg.frame_diff_threshold, self.kernel_size, cfg.gaussian_sigma)
+        pa = pb = final = None
+        if self.prior is not None:
+            row = frame.shape[0] // 2
+            pa, pb, final = select_position(imgs["sobel_output"][row, :], imgs["gradient_output"][row, :], s0, s1, cfg)
+        self.history.append((frame_idx, final))
+        self.prior = sub
+        self.ddt_frame = velocities_update(self.history, self.velocities, frame_idx, final, self.frame_rate,
+                                           self.calibration, cfg, self.ddt_frame)
+        return {"images": imgs, "final": final, "min_gradient": pa, "rightmost_sobel": pb, "search": (s0, s1)}
+
+
 # --------------------------------------------------------------------------------------
 # layer 2: operation-by-operation restatement on the centre band
 # --------------------------------------------------------------------------------------

@@ -125,6 +125,87 @@ def replay_head_loop(pv, video, cal, off, exit_margin=15):
             "velocity_history": vel, "ddt_frame": det.ddt_frame, "stop": stop_reason}
 
 
+def detector_api_golden(pv, ho) -> dict:
+    """The reference's frame-level API driven directly (no driver loop, no empty-frame skip):
+    FlameDetector.detect with every intermediate image hashed, two configurations, on frames
+    committed as tests/golden/detector_frames.npz; plus the element-wise frame functions."""
+    spec = syn.SyntheticSpec(width=136, height=40, n_frames=20, bits=16, style="nova", t_enter=2.0,
+                             velocity=7.0, tail_length=30.0, curvature_px=3.0, seed=4242, record_rate=100000)
+    frames = syn.render_frames(spec)
+    np.savez_compressed(GOLD / "detector_frames.npz", frames=frames)
+    images = ("frame_subtracted", "frame_diff", "noise_removed", "blurred", "sobel_output", "gradient_output")
+    out = {"frames_sha1": _sha(frames), "shape": list(frames.shape), "frame_rate": spec.record_rate, "runs": []}
+    variants = [
+        {"name": "defaults", "cfg": {}, "calibration": 0.000833333, "order": list(range(20)), "background": None},
+        {"name": "k5_sigma1_thr3.5_gaps", "calibration": 0.002, "background": 37,
+         "cfg": {"morphology_kernel_size": 5, "gaussian_sigma": 1.0, "frame_diff_threshold": 3.5,
+                 "min_gradient_strength": 4.0, "edge_margin_px": 3, "search_window_px": 12,
+                 "sobel_threshold_fraction": 0.25, "use_spline_estimator": False},
+         "order": [0, 2, 3, 5, 6, 7, 8, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19]},
+        {"name": "k1_sigma2", "calibration": 0.000833333, "background": None,
+         "cfg": {"morphology_kernel_size": 1, "gaussian_sigma": 2.0}, "order": list(range(1, 12))},
+    ]
+    for var in variants:
+        cfg = pv.FlameDetectorConfig(**var["cfg"])
+        det = pv.FlameDetector(config=cfg, frame_rate=spec.record_rate, calibration_m_per_px=var["calibration"])
+        bg = float(np.max(frames[0])) if var["background"] is None else float(var["background"])
+        hcfg = ho.HeadConfig(**{k: v for k, v in var["cfg"].items() if k in ho.HeadConfig.__dataclass_fields__})
+        orc = ho.FrameDetectorOracle(spec.record_rate, var["calibration"], hcfg,
+                                     kernel_size=var["cfg"].get("morphology_kernel_size", 3))
+        calls = []
+        for idx in var["order"]:
+            r = det.detect(frame=frames[idx], frame_idx=idx, background_scalar=bg)
+            o = orc.detect(frames[idx], idx, bg)
+            for name in images:
+                a, b = getattr(r, name), o["images"][name]
+                assert (a is None) == (b is None) and (a is None or np.array_equal(a, b)), (var["name"], idx, name)
+            assert (r.final_position, r.pos_min_gradient, r.pos_rightmost_sobel, tuple(r.search_bounds)) == \
+                (o["final"], o["min_gradient"], o["rightmost_sobel"], tuple(o["search"])), (var["name"], idx)
+            calls.append({"frame": idx, "time_s": r.time_s, "final": r.final_position,
+                          "min_gradient": r.pos_min_gradient, "rightmost_sobel": r.pos_rightmost_sobel,
+                          "spline": r.pos_spline_predicted, "search": list(r.search_bounds),
+                          "sha1": {n: (None if getattr(r, n) is None else _sha(getattr(r, n))) for n in images}})
+        vel = [list(e) for e in det.get_velocity_history()]
+        assert vel == orc.velocities and det.ddt_frame == orc.ddt_frame
+        out["runs"].append({"name": var["name"], "cfg": var["cfg"], "calibration": var["calibration"],
+                            "background": bg, "order": var["order"], "calls": calls, "velocity_history": vel,
+                            "ddt_frame": det.ddt_frame, "last_position": det.last_position,
+                            "last_velocities": list(det.last_velocities),
+                            "pre_ddt": len(det.get_pre_ddt_velocities()), "post_ddt": len(det.get_post_ddt_velocities()),
+                            "max_displacement_px": det._max_displacement_px,
+                            "prior_sha1": _sha(det._prior_frame)})
+    # ---- element-wise frame functions ------------------------------------------------------------
+    f5, f6, f7 = frames[5], frames[6], frames[7]
+    sub6 = pv.subtract_scalar_background(f6, 41.5)
+    ops = {
+        "sub_bg_41.5": _sha(sub6),
+        "sub_bg_max0": _sha(pv.subtract_scalar_background(f6, float(np.max(frames[0])))),
+        "prior_raw_thr0": _sha(pv.subtract_prior_frame(f6, f5, threshold=0.0)),
+        "prior_raw_thr7.5": _sha(pv.subtract_prior_frame(f6, f5, threshold=7.5)),
+        "prior_f64": _sha(pv.subtract_prior_frame(sub6, pv.subtract_scalar_background(f5, 41.5), threshold=5.0)),
+        "three_thr0": _sha(pv.three_frame_difference(f5, f6, f7)),
+        "three_thr3": _sha(pv.three_frame_difference(f5, f6, f7, threshold=3.0)),
+        "empty": {f"{thr}/{frac}": bool(pv.is_empty_frame(sub6, noise_threshold=thr, min_signal_fraction=frac))
+                  for thr in (10.0, 50.0, 20.5, 2000.0) for frac in (0.001, 0.0005, 0.05, 0.5)},
+        "empty_raw_defaults": bool(pv.is_empty_frame(f6)),
+        "count_above": {str(thr): int(np.sum(sub6 > thr)) for thr in (10.0, 50.0, 20.5, 2000.0)},
+    }
+    assert ops["sub_bg_41.5"] == _sha(fo.subtract_scalar_background(f6, 41.5))
+    assert ops["prior_raw_thr7.5"] == _sha(fo.frame_difference(f6, f5, 7.5))
+    assert ops["three_thr3"] == _sha(fo.three_frame_difference(f5, f6, f7, 3.0))
+    work = GOLD / "_work"
+    work.mkdir(parents=True, exist_ok=True)
+    table = {"Frame": [39, 40], "Time_s": ["0.003368750", "0.003375000"], "Position_px": [6, 14],
+             "Note": ["a b", 'q"x']}
+    pv.write_results(table, str(work / "wr.txt"))
+    ops["write_results"] = {"columns": [[k, v] for k, v in table.items()],   # JSON objects are key-sorted
+                             "bytes": (work / "wr.txt").read_bytes().decode("latin-1")}
+    out["ops"] = ops
+    out["config_defaults"] = {k: getattr(pv.FlameDetectorConfig(), k) for k in pv.FlameDetectorConfig.__dataclass_fields__}
+    out["result_fields"] = list(pv.FlameDetectionResult.__dataclass_fields__)
+    return out
+
+
 def main() -> None:
     _install_stubs()
     sys.path.insert(0, str(REF / "scripts"))
@@ -217,6 +298,10 @@ def main() -> None:
 
     # ---- HEAD detector replay (f1/f2 rows of SURVEY 8f) ----------------------------------------
     gold["head_replay"] = replay_head_loop(pv, video, 0.000833333, 1.347567)
+
+    # ---- the frame-level API (seam B3) driven directly -------------------------------------------
+    from oracle import head_oracle as ho
+    gold["detector_api"] = detector_api_golden(pv, ho)
 
     # ---- the reference's own driver, end to end (f1 + f2 + f3) -----------------------------------
     # process_video_source (:1277-1629) with only the matplotlib renderers replaced by no-ops;
