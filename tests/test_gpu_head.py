@@ -198,3 +198,32 @@ def test_speculative_tracker_equals_sequential_walk(engine, monkeypatch, case):
     (t3, s3, _), (t4, s4, _) = _track_both_ways(engine, packed, n, h, w, hp, 160000, 0.000833333, monkeypatch,
                                                 tracker_state=(3, 17))
     assert np.array_equal(t3, t4) and np.array_equal(s3, s4)
+
+
+def test_fullsize_c2_head_detector_vs_oracle_on_every_flame_frame(engine):
+    """BASELINE config 2 at full size (1024x128 x 20000) through the HEAD detector: the lead-in must
+    be skipped as empty, and from twelve frames before the flame enters to the stop every detect()
+    output, result row and velocity equals the oracle loop (SciPy images, ~1100 frames)."""
+    spec = syn.config_spec("C2")
+    n, h, w, fb = spec.n_frames, spec.height, spec.width, spec.frame_bytes
+    packed = syn.render_packed_torch(spec, engine.device)
+    hp = HeadParams()
+    cal, off, rate = 0.000833333, 1.347567, spec.record_rate
+    time_of = lambda i: fo.frame_time_absolute(i, spec.start_frame, spec.skip_frame, rate)
+    res = engine.process_head(packed, n, h, w, 12, hp, rate, cal)
+    flags = res.flags.cpu().numpy()
+    got = finish_head_track(res.track.cpu().numpy(), flags, 0, w, rate, cal, off, time_of, hp)
+    assert got.stop is not None and got.stop[0] == "exit" and len(got.rows) > 900
+    a = int(spec.t_enter) - 12                   # the front's edge (sigma 3 px) is still far outside the frame
+    b = min(n, got.stop[1] + 3)
+    assert not flags[:a].any(), "the lead-in holds no frame that reaches the detector"
+    frame0 = fo.frames_from_bytes(packed[:fb].cpu().numpy(), 1, h, w, 12)
+    window = fo.frames_from_bytes(packed[a * fb:b * fb].cpu().numpy(), b - a, h, w, 12)
+    shift = a - 1                                   # oracle index i >= 1  <->  clip frame i + shift
+    want = ho.run_head(np.concatenate([frame0, window]), rate, cal, off, lambda i: time_of(i + shift))
+    assert want.empty >= 1 and want.stop == ("exit", got.stop[1] - shift)
+    assert got.per_frame == [dict(p, frame=p["frame"] + shift) for p in want.per_frame]
+    assert [list(r) for r in got.rows] == [[r[0] + shift] + r[1:] for r in want.rows]
+    assert got.velocity_history == [[e[0] + shift] + e[1:] for e in want.velocity_history]
+    assert got.ddt_frame == (None if want.ddt_frame is None else want.ddt_frame + shift)
+    assert int(res.stop.cpu()[0]) == got.stop[1]
