@@ -211,6 +211,195 @@ __global__ void __launch_bounds__(kHeadThreads) head_band_kernel(const HeadBandP
   }
 }
 
+// ---- fast band kernel: rows that start on an 8-pixel boundary (W % 8 == 0, 4-byte aligned frames) --
+// The general kernel above spends half its instructions on per-pixel address arithmetic and byte
+// loads (ncu: 153 warp instructions per 32 pixels in stage D, issue-bound at 71 % issue slots busy).
+// Here stage D works on aligned groups of 8 pixels - three 32-bit loads per frame for packed
+// 12-bit - written to shared memory as one 16-byte store, and the 3x3 opening runs separably on
+// 16x2 SIMD words (vertical min, horizontal min, vertical max, horizontal max: 3 loads + 2 VMIN
+// per pixel PAIR and pass).  The band buffer therefore starts at the aligned column x_begin - 16
+// (band column j lives at buffer column j + 16 - HALO) and is 288 columns wide.
+constexpr int kBandPad = 16;
+constexpr int kBandLWA = kHeadTileW + 2 * kBandPad;      // 288
+constexpr int kBandGroups = kBandLWA / 8;                // 36 groups of 8 pixels per band row
+constexpr int kBandWords = kBandLWA / 2;                 // 144 16x2 words per band row
+
+template <int BITS>
+__device__ __forceinline__ void load8_global(const uint8_t* __restrict__ base, int64_t q0, int (&v)[8]) {
+  if (BITS == 12) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(base + (q0 >> 1) * 3);
+    decode12x8(__ldg(w), __ldg(w + 1), __ldg(w + 2), v);
+  } else if (BITS == 16) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(base + q0 * 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t u = __ldg(w + k);
+      v[2 * k] = (int)(u & 0xFFFFu);
+      v[2 * k + 1] = (int)(u >> 16);
+    }
+  } else {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(base + q0);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const uint32_t u = __ldg(w + k);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) v[4 * k + b] = (int)((u >> (8 * b)) & 0xFFu);
+    }
+  }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(kHeadThreads) head_band_fast_kernel(const HeadBandParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int tid = threadIdx.x;
+  const int W = p.width, H = p.height;
+  const int R = p.radius;
+  const int HALO = R + 3;
+  const int NB = 2 * HALO + 1;
+  const int off = kBandPad - HALO;          // >= 5: kMaxRadius + 3 = 11 <= kBandPad
+  const int c = H / 2;
+  const int tiles_x = (W + kHeadTileW - 1) / kHeadTileW;
+  const int n_work = __ldg(p.scratch) * tiles_x;
+  const int bg = __ldg(p.bg_dev);
+  uint16_t* bufA = reinterpret_cast<uint16_t*>(smem);                    // [NB][kBandLWA]
+  uint16_t* bufB = bufA + NB * kBandLWA;                                  // [NB][kBandLWA]
+  uint32_t* A32 = reinterpret_cast<uint32_t*>(bufA);
+  uint32_t* B32 = reinterpret_cast<uint32_t*>(bufB);
+  const int LWmax = kHeadTileW + 2 * HALO;
+  double* g0 = reinterpret_cast<double*>(smem + (size_t)2 * NB * kBandLWA * sizeof(uint16_t));   // [3][LW]
+  double* bl = g0 + 3 * LWmax;                                            // [3][LW]
+
+  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+    const int f = __ldg(p.scratch + 4 + work / tiles_x);
+    const int x_begin = (work % tiles_x) * kHeadTileW;
+    const int tw = min(kHeadTileW, W - x_begin);      // multiple of 8
+    const int LW = tw + 2 * HALO;
+    const int groups = (tw + 2 * kBandPad) / 8;
+    const int words = groups * 4;
+    int hf = f - 1;
+    if (p.skip != nullptr)
+      while (hf >= 0 && p.skip[hf]) --hf;
+    const uint8_t* prior = hf >= 0 ? p.frames + (int64_t)hf * p.frame_bytes : p.halo;
+    const uint8_t* cur = p.frames + (int64_t)f * p.frame_bytes;
+
+    // ---- D: thresholded difference, 8 pixels per task; groups outside the image are mirrored below ----
+    for (int t = tid; t < NB * kBandGroups; t += kHeadThreads) {
+      const int i = t / kBandGroups, g = t - i * kBandGroups;
+      const int xg = x_begin - kBandPad + 8 * g;
+      if (g >= groups || xg < 0 || xg + 8 > W) continue;
+      const int64_t q0 = (int64_t)reflect_idx(c - HALO + i, H) * W + xg;
+      int a[8], b[8];
+      load8_global<BITS>(cur, q0, a);
+      load8_global<BITS>(prior, q0, b);
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int d0 = max(a[2 * k] - bg, 0) - max(b[2 * k] - bg, 0);
+        int d1 = max(a[2 * k + 1] - bg, 0) - max(b[2 * k + 1] - bg, 0);
+        if (d0 < p.diff_thr) d0 = 0;
+        if (d1 < p.diff_thr) d1 = 0;
+        o[k] = (uint32_t)d0 | ((uint32_t)d1 << 16);      // diff_thr >= 0 (launcher): 0 <= d <= 65535
+      }
+      *reinterpret_cast<uint4*>(bufA + i * kBandLWA + 8 * g) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();
+    // scipy 'reflect' left of column 0 / right of column W-1: the mirrored pixel is one of this tile's
+    // own (at most 16 columns inside the image, or anywhere in an image narrower than that)
+    if (x_begin < kBandPad || x_begin + tw + kBandPad > W) {
+      for (int t = tid; t < NB * 2 * kBandPad; t += kHeadThreads) {
+        const int i = t / (2 * kBandPad), k = t - i * (2 * kBandPad);
+        const int x = k < kBandPad ? k - kBandPad : W + k - kBandPad;          // 16 columns either side
+        if (x < x_begin - kBandPad || x >= x_begin + tw + kBandPad) continue;    // not this tile's side
+        bufA[i * kBandLWA + x - x_begin + kBandPad] = bufA[i * kBandLWA + reflect_idx(x, W) - x_begin + kBandPad];
+      }
+      __syncthreads();
+    }
+    // ---- 3x3 opening, separable on 16x2 words: min rows, min columns, max rows, max columns ----------
+    // (buffer borders clamp; they lie outside the region the Gaussian reads, like the zeros of the
+    // general kernel).  One warp per band row, lanes over the words of the row.
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      // rows: dst[i] = op(src[i-1], src[i], src[i+1])
+      auto rows_pass = [&](const uint32_t* src, uint32_t* dst, auto op) {
+        for (int i = warp; i < NB; i += kHeadThreads / 32) {
+          const uint32_t* up = src + max(i - 1, 0) * kBandWords;
+          const uint32_t* md = src + i * kBandWords;
+          const uint32_t* dn = src + min(i + 1, NB - 1) * kBandWords;
+          for (int w = lane; w < words; w += 32) dst[i * kBandWords + w] = op(op(up[w], md[w]), dn[w]);
+        }
+      };
+      // columns: neighbours straddle words - (pixel 2w-1, 2w) and (2w+1, 2w+2) via PRMT
+      auto cols_pass = [&](const uint32_t* src, uint32_t* dst, auto op) {
+        for (int i = warp; i < NB; i += kHeadThreads / 32) {
+          const uint32_t* md = src + i * kBandWords;
+          for (int w = lane; w < words; w += 32) {
+            const uint32_t l = md[max(w - 1, 0)], m = md[w], r = md[min(w + 1, words - 1)];
+            dst[i * kBandWords + w] = op(op(__byte_perm(l, m, 0x5432), m), __byte_perm(m, r, 0x5432));
+          }
+        }
+      };
+      auto vmin = [](uint32_t x, uint32_t y) { return __vminu2(x, y); };
+      auto vmax = [](uint32_t x, uint32_t y) { return __vmaxu2(x, y); };
+      rows_pass(A32, B32, vmin);
+      __syncthreads();
+      cols_pass(B32, A32, vmin);
+      __syncthreads();
+      rows_pass(A32, B32, vmax);
+      __syncthreads();
+      cols_pass(B32, A32, vmax);
+      __syncthreads();
+    }
+    // ---- G0 = Gaussian along rows (axis 0) for band rows HALO-1, HALO, HALO+1 ------------------------
+    for (int e = tid; e < 3 * LW; e += kHeadThreads) {
+      const int b = e / LW, j = e - b * LW;
+      double tmp = 0.0;
+      if (j >= 2 && j < LW - 2) {
+        const uint16_t* col = bufA + (HALO - 1 + b) * kBandLWA + j + off;
+        tmp = __dmul_rn((double)col[0], p.w[R]);
+        for (int jj = -R; jj < 0; ++jj) {
+          const double pair = __dadd_rn((double)col[jj * kBandLWA], (double)col[-jj * kBandLWA]);
+          tmp = __dadd_rn(tmp, __dmul_rn(pair, p.w[R + jj]));
+        }
+      }
+      g0[e] = tmp;
+    }
+    __syncthreads();
+    // ---- BL = Gaussian along columns (axis 1), valid cols [HALO-1, LW-HALO+1) -----------------------
+    for (int e = tid; e < 3 * LW; e += kHeadThreads) {
+      const int b = e / LW, j = e - b * LW;
+      double tmp = 0.0;
+      if (j >= HALO - 1 && j < LW - HALO + 1) {
+        const double* g = g0 + b * LW;
+        tmp = __dmul_rn(g[j], p.w[R]);
+        for (int jj = -R; jj < 0; ++jj) tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(g[j + jj], g[j - jj]), p.w[R + jj]));
+      }
+      bl[e] = tmp;
+    }
+    __syncthreads();
+    // ---- Sobel(axis=1) and np.gradient(axis=1) on the centre row --------------------------------------
+    double* out_s = p.lines + ((int64_t)f * 2 + 0) * W;
+    double* out_g = p.lines + ((int64_t)f * 2 + 1) * W;
+    for (int t = tid; t < tw; t += kHeadThreads) {
+      const int j = HALO + t;
+      const int x = x_begin + t;
+      double s3[3];
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const double* v = bl + b * LW;
+        s3[b] = __dadd_rn(__dmul_rn(v[j], 0.0), __dmul_rn(__dsub_rn(v[j - 1], v[j + 1]), -1.0));
+      }
+      out_s[x] = __dadd_rn(__dmul_rn(s3[1], 2.0), __dmul_rn(__dadd_rn(s3[0], s3[2]), 1.0));
+      const double* v = bl + 1 * LW;
+      double g;
+      if (x == 0) g = __ddiv_rn(__dsub_rn(v[j + 1], v[j]), 1.0);
+      else if (x == W - 1) g = __ddiv_rn(__dsub_rn(v[j], v[j - 1]), 1.0);
+      else g = __ddiv_rn(__dsub_rn(v[j + 1], v[j - 1]), 2.0);
+      out_g[x] = g;
+    }
+    __syncthreads();      // the next work item reuses the shared-memory band
+  }
+}
+
 struct HeadTrackParams {
   const double* lines;
   const uint8_t* flags;
@@ -648,7 +837,12 @@ int head_lines_impl(const void* frames, const void* halo, int64_t n_frames, int 
   head_flags_kernel<<<(unsigned)((n_frames + warps - 1) / warps), kHeadThreads, 0, st>>>(p);
   FF_CUDA_TRY(cudaGetLastError());
   const int tiles_x = (width + kHeadTileW - 1) / kHeadTileW;
-  auto launch = [&](auto kern) -> int {
+  const bool fast = (width % 8) == 0 && (p.frame_bytes % 4) == 0 && getenv("FF_BAND_GENERAL") == nullptr &&
+                    (reinterpret_cast<uintptr_t>(frames) % 4) == 0 &&
+                    (halo == nullptr || (reinterpret_cast<uintptr_t>(halo) % 4) == 0);
+  const size_t smem_general = smem;
+  const size_t smem_fast = (size_t)2 * nb * kBandLWA * sizeof(uint16_t) + (size_t)6 * lw * sizeof(double);
+  auto launch = [&](auto kern, size_t smem) -> int {
     if (smem > 48 * 1024) FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kHeadThreads, smem));
@@ -661,10 +855,17 @@ int head_lines_impl(const void* frames, const void* halo, int64_t n_frames, int 
     FF_CUDA_TRY(cudaGetLastError());
     return FF_OK;
   };
+  if (fast) {
+    switch (bits) {
+      case 8: return launch(head_band_fast_kernel<8>, smem_fast);
+      case 12: return launch(head_band_fast_kernel<12>, smem_fast);
+      default: return launch(head_band_fast_kernel<16>, smem_fast);
+    }
+  }
   switch (bits) {
-    case 8: return launch(head_band_kernel<8>);
-    case 12: return launch(head_band_kernel<12>);
-    default: return launch(head_band_kernel<16>);
+    case 8: return launch(head_band_kernel<8>, smem_general);
+    case 12: return launch(head_band_kernel<12>, smem_general);
+    default: return launch(head_band_kernel<16>, smem_general);
   }
 }
 

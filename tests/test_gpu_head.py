@@ -227,3 +227,33 @@ def test_fullsize_c2_head_detector_vs_oracle_on_every_flame_frame(engine):
     assert got.velocity_history == [[e[0] + shift] + e[1:] for e in want.velocity_history]
     assert got.ddt_frame == (None if want.ddt_frame is None else want.ddt_frame + shift)
     assert int(res.stop.cpu()[0]) == got.stop[1]
+
+
+@pytest.mark.parametrize("h,w,bits,sigma", [(64, 512, 12, 1.5), (9, 264, 16, 2.0), (128, 1024, 12, 1.5), (20, 8, 8, 1.0),
+                                            (33, 776, 8, 1.5), (40, 1280, 16, 0.7)])
+def test_fast_band_kernel_equals_general_kernel(engine, monkeypatch, h, w, bits, sigma):
+    """Rows that start on an 8-pixel boundary take head_band_fast_kernel (grouped loads, separable SIMD
+    opening); FF_BAND_GENERAL=1 forces the per-pixel kernel.  Same lines, bit for bit, including
+    skip_frames entries and a sub-range with a halo frame."""
+    spec = syn.SyntheticSpec(width=w, height=h, n_frames=30, bits=bits, style="nova", t_enter=2.0,
+                             velocity=max(1.0, w / 24.0), tail_length=w / 6.0, seed=w + h + bits)
+    frames = syn.render_frames(spec)
+    frames[11] = np.random.default_rng(w).integers(0, spec.max_value + 1, size=(h, w)).astype(frames.dtype)
+    packed = dev(syn.pack_frames(frames, bits), engine)
+    fb = spec.frame_bytes
+    skip = np.zeros(29, dtype=np.uint8)
+    skip[[6, 7, 15]] = 1
+    hp = HeadParams(gaussian_sigma=sigma)
+
+    def run():
+        r = engine.process_head(packed[fb:], 29, h, w, bits, hp, 160000, 0.000833333, frame0=packed[:fb], first_frame=1,
+                                halo=packed[:fb], skip=dev(skip, engine), keep_lines=True)
+        fl = r.flags.cpu().numpy()
+        return fl, r.lines.cpu().numpy()[fl == 1], r.track.cpu().numpy()
+
+    fast = run()
+    monkeypatch.setenv("FF_BAND_GENERAL", "1")
+    general = run()
+    assert (fast[0] == 1).sum() > 8
+    for a, b in zip(fast, general):
+        assert np.array_equal(a, b)
