@@ -26,7 +26,7 @@ FF_POS_NONE = -1
 FF_POS_DROPPED = -2
 FF_NO_EXIT = 2147483647
 FF_PX_U8, FF_PX_U16, FF_PX_F64 = 0, 1, 3
-FF_ABI_VERSION = 4
+FF_ABI_VERSION = 5
 
 
 class FlameFrontLibraryError(RuntimeError):
@@ -70,8 +70,9 @@ SIGNATURES = {
     "ff_exchange_destroy": (_int, [_vp]),
     "ff_head_lines": (_int, [_vp, _vp, _i64, _int, _int, _int, _vp, _vp, _i64, _i32, C.POINTER(C.c_double), _int, _vp,
                              _vp, _vp, _vp, _vp]),
+    "ff_head_track_scratch_len": (_int, [_i64, C.POINTER(_i64)]),
     "ff_head_track": (_int, [_vp, _vp, _i64, _i64, _int, _i32, _i32, _i32, C.c_double, C.c_double, _i32, _i32, _i32,
-                             _vp, _vp, _vp]),
+                             _vp, _vp, _vp, _vp]),
     "ff_frame_subtract_background": (_int, [_vp, _int, _i64, C.c_double, _vp, _vp]),
     "ff_frame_difference": (_int, [_vp, _vp, _int, _i64, C.c_double, _vp, _vp]),
     "ff_frame_three_difference": (_int, [_vp, _vp, _vp, _int, _i64, C.c_double, _vp, _vp]),

@@ -31,7 +31,8 @@ int truncate_impl(int32_t*, int64_t, int64_t, const int32_t*, cudaStream_t);
 int head_lines_impl(const void*, const void*, int64_t, int, int, int, const int32_t*, const int32_t*, int64_t, int32_t,
                     const double*, int, const uint8_t*, double*, uint8_t*, int32_t*, cudaStream_t);
 int head_track_impl(const double*, const uint8_t*, int64_t, int64_t, int, int32_t, int32_t, int32_t, double, double,
-                    int32_t, int32_t, int32_t, int32_t*, int32_t*, cudaStream_t);
+                    int32_t, int32_t, int32_t, int32_t*, int32_t*, int32_t*, cudaStream_t);
+int64_t head_track_scratch_len(int64_t);
 int frame_subtract_background_impl(const void*, int, int64_t, double, double*, cudaStream_t);
 int frame_difference_impl(const void*, const void*, int, int64_t, double, double*, cudaStream_t);
 int frame_three_difference_impl(const void*, const void*, const void*, int, int64_t, double, double*, cudaStream_t);
@@ -320,13 +321,21 @@ int ff_head_lines(const void* frames_dev, const void* halo_dev, int64_t n_frames
                          static_cast<cudaStream_t>(stream));
 }
 
+int ff_head_track_scratch_len(int64_t n_frames, int64_t* n_elems) {
+  if (n_elems == nullptr || n_frames <= 0) return FF_ERR_INVALID;
+  *n_elems = head_track_scratch_len(n_frames);
+  return FF_OK;
+}
+
 int ff_head_track(const double* lines_dev, const uint8_t* flags_dev, int64_t n_frames, int64_t first_frame, int width,
                   int32_t edge_margin_px, int32_t max_displacement_px, int32_t search_window_px,
                   double min_gradient_strength, double sobel_threshold_fraction, int32_t exit_margin_px,
-                  int32_t last_frame_in, int32_t last_pos_in, int32_t* out_dev, int32_t* stop_dev, void* stream) {
+                  int32_t last_frame_in, int32_t last_pos_in, int32_t* out_dev, int32_t* stop_dev,
+                  int32_t* scratch_dev, void* stream) {
   return head_track_impl(lines_dev, flags_dev, n_frames, first_frame, width, edge_margin_px, max_displacement_px,
                          search_window_px, min_gradient_strength, sobel_threshold_fraction, exit_margin_px,
-                         last_frame_in, last_pos_in, out_dev, stop_dev, static_cast<cudaStream_t>(stream));
+                         last_frame_in, last_pos_in, out_dev, stop_dev, scratch_dev,
+                         static_cast<cudaStream_t>(stream));
 }
 
 int ff_frame_subtract_background(const void* image_dev, int px_type, int64_t n_px, double background,

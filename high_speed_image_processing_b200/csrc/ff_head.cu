@@ -411,6 +411,9 @@ struct HeadTrackParams {
   int last_frame_in, last_pos_in;  // tracker state carried in from an earlier range (-1 = none)
   int32_t* out;                    // [n][5]: final, min_gradient, rightmost_sobel, search_start, search_end
   int32_t* stop;                   // [3]: exit frame (global) or FF_NO_EXIT, last frame, last pos
+  int32_t* seg;                    // [n_seg][8] per-segment states of the chained speculation, or nullptr
+  int32_t* seg_hdr;                // [0] first segment whose speculative walk ends with a detection / carried state
+  int32_t* out2;                   // [n][5] rows re-computed by head_track_fixup_kernel
 };
 
 // Monotone map from the bits of a non-NaN double to an unsigned integer (-0.0 == +0.0): the
@@ -526,6 +529,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_track_generic_kernel(const 
 // (they sit in L2 after head_band_kernel).
 constexpr int kSegFrames = 32;               // frames per segment = lanes of the validating warp
 constexpr int kSpecWarpsPerCta = 8;
+constexpr int kSegInts = 8;                  // int32 per segment in the chained-speculation scratch
+constexpr int kMaxRepair = 16;               // frames a segment re-runs from its guess before it gives up
 
 struct TrackState { int last_f, last_p; };
 struct FrameResult { int final_pos, pos_a, pos_b, s0, s1; };
@@ -681,26 +686,138 @@ __global__ void __launch_bounds__(kSpecWarpsPerCta * 32) head_track_spec_kernel(
       o[0] = r.final_pos; o[1] = r.pos_a; o[2] = r.pos_b; o[3] = r.s0; o[4] = r.s1;
     }
   }
+  if (p.seg != nullptr && lane == 0) {       // E1: where this walk ended (segment 0: from the true state)
+    int32_t* e = p.seg + (int64_t)seg * kSegInts;
+    e[0] = st.last_f;
+    e[1] = st.last_p;
+    e[4] = 0;                                // frames repaired by the fix-up pass
+    e[5] = p.n_frames;                       // exit frame inside this segment (fix-up pass)
+    if (st.last_p >= 0) atomicMin(p.seg_hdr, seg);      // first segment that ends with a state
+  }
 }
 
-__global__ void __launch_bounds__(256) head_track_commit_kernel(const HeadTrackParams p) {
-  __shared__ int s_exit_f;          // range-local index of the exit frame, or n_frames
-  const int tid = threadIdx.x, lane = tid & 31;
+// ---- chained speculation --------------------------------------------------------------------------
+// A walk started from "nothing detected yet" differs from the true walk only until it has locked onto
+// the front - typically its first active frame.  head_track_fixup_kernel repairs exactly those frames
+// for ALL segments at once: segment s guesses its true start state G_s = the end state of the nearest
+// earlier speculative walk that ended with a state (detection or carried-in), re-runs its leading
+// active frames from G_s until its state meets the speculation's, writes the repaired rows (saving
+// the speculation's in out2) and records where it ended (E2) and the first exit frame it saw.  The
+// guess is right for every segment up to the first one whose repaired walk did NOT end in the state
+// its successors guessed (or that gave up after kMaxRepair frames) - found for all segments in
+// parallel by head_track_resolve_kernel, which then needs no sequential work at all unless such a
+// segment exists before the exit frame; from there it puts the speculation's rows back and falls
+// back to validating segment by segment.
+//   seg[s] = { E1.f, E1.p, E2.f, E2.p, n_fixed (0: not re-run), exit frame in s or n_frames, G.f, G.p }
+__global__ void __launch_bounds__(kSpecWarpsPerCta * 32) head_track_fixup_kernel(const HeadTrackParams p) {
+  const int lane = threadIdx.x & 31;
+  const int seg = blockIdx.x * kSpecWarpsPerCta + (threadIdx.x >> 5);
+  const int f_lo = seg * kSegFrames;
+  if (f_lo >= p.n_frames) return;
   const unsigned fullmask = 0xFFFFFFFFu;
   const int W = p.width;
-  if (tid < 32) {
-    TrackState cur;
-    cur.last_f = p.last_frame_in;
-    cur.last_p = p.last_pos_in;
-    int exit_f = p.n_frames;
-    const int n_seg = (p.n_frames + kSegFrames - 1) / kSegFrames;
-    const bool vec_flags = (reinterpret_cast<uintptr_t>(p.flags) & 15u) == 0;
-    for (int seg0 = 0; seg0 < n_seg && exit_f == p.n_frames; seg0 += 32) {
+  const int fme = f_lo + lane;
+  const int flme = fme < p.n_frames ? (int)p.flags[fme] : 0;
+  const unsigned act_all = __ballot_sync(fullmask, flme != 0);
+  if (!act_all) return;
+  int32_t* e = p.seg + (int64_t)seg * kSegInts;
+  // G: nearest earlier segment whose speculative walk ended with a state (none before seg_hdr[0])
+  TrackState cur;
+  cur.last_f = -1;
+  cur.last_p = -1;
+  const int first_with_state = __ldcg(p.seg_hdr);
+  for (int t0 = seg - 1; t0 >= first_with_state; t0 -= 32) {
+    const int t = t0 - lane;
+    const int lp = t >= 0 ? __ldcg(p.seg + (int64_t)t * kSegInts + 1) : -1;
+    const unsigned m = __ballot_sync(fullmask, lp >= 0);
+    if (m) {
+      const int l = __ffs((int)m) - 1;               // lowest lane = nearest segment
+      cur.last_p = __shfl_sync(fullmask, lp, l);
+      cur.last_f = __ldcg(p.seg + (int64_t)(t0 - l) * kSegInts + 0);
+      break;
+    }
+  }
+  int my_final = flme != 0 ? __ldcg(p.out + (int64_t)fme * 5) : -1;      // the speculation's result
+  int n_fixed = 0;
+  // Segment 0 started from the true state; without a state before, the speculation IS the walk; and a
+  // guess that is itself an exit state means the walk has ended before this segment if the guess holds.
+  if (seg != 0 && cur.last_p >= 0 && cur.last_p < W - p.exit_margin) {
+    const TrackState guess = cur;
+    const int spec_final = my_final;
+    TrackState spec;
+    spec.last_f = -1;
+    spec.last_p = -1;
+    unsigned act = act_all;
+    bool exit_hit = false;
+    while (act && n_fixed < kMaxRepair && !(spec.last_f == cur.last_f && spec.last_p == cur.last_p)) {
+      const int l = __ffs((int)act) - 1;
+      act &= act - 1;
+      const int f = f_lo + l;
+      const int fl = __shfl_sync(fullmask, flme, l);
+      const FrameResult r = track_frame(p, f, fl, cur, lane);
+      const int sf = __shfl_sync(fullmask, spec_final, l);
+      if (sf >= 0) {
+        spec.last_f = (int)(p.first_frame + f);
+        spec.last_p = sf;
+      }
+      if (r.final_pos >= 0) {
+        cur.last_f = (int)(p.first_frame + f);
+        cur.last_p = r.final_pos;
+      }
+      if (lane < 5) {                        // keep the speculation's row, then replace it
+        int32_t* o = p.out + (int64_t)f * 5 + lane;
+        p.out2[(int64_t)f * 5 + lane] = *o;
+        *o = lane == 0 ? r.final_pos : lane == 1 ? r.pos_a : lane == 2 ? r.pos_b : lane == 3 ? r.s0 : r.s1;
+      }
+      if (lane == l) my_final = r.final_pos;
+      ++n_fixed;
+      if (r.final_pos >= 0 && r.final_pos >= W - p.exit_margin) {      // the walk ends here if the guess holds
+        exit_hit = true;
+        break;
+      }
+    }
+    if (lane == 0) {
+      const bool met = spec.last_f == cur.last_f && spec.last_p == cur.last_p;
+      const bool own = e[1] >= 0;
+      if (met || exit_hit) {                 // from here on the walks coincide (or nothing follows): they end alike
+        e[2] = own ? e[0] : guess.last_f;
+        e[3] = own ? e[1] : guess.last_p;
+      } else if (!act) {                     // every active frame re-run
+        e[2] = cur.last_f;
+        e[3] = cur.last_p;
+      } else {                               // gave up after kMaxRepair frames: the segment is not resolved
+        e[2] = -2;
+        e[3] = -2;
+      }
+      e[6] = guess.last_f;
+      e[7] = guess.last_p;
+    }
+  }
+  const unsigned ext = __ballot_sync(fullmask, my_final >= 0 && my_final >= W - p.exit_margin);      // :1488-1494
+  if (lane == 0) {
+    e[4] = n_fixed;
+    e[5] = ext ? f_lo + __ffs((int)ext) - 1 : p.n_frames;
+  }
+}
+
+struct WalkEnd { int exit_f; TrackState cur; };
+
+// Validation of the speculative walks one segment after the other, by ONE warp, from segment
+// `seg_begin` on with the true state `cur`: re-run the first active frame(s) of a segment until the
+// state equals the state the speculation had at the same point; the rest of the segment stands.
+// Returns the range-local exit frame (or n_frames) and the state at the end / at the exit.
+__device__ WalkEnd commit_walk(const HeadTrackParams& p, int seg_begin, TrackState cur, int lane) {
+  const unsigned fullmask = 0xFFFFFFFFu;
+  const int W = p.width;
+  int exit_f = p.n_frames;
+  const int n_seg = (p.n_frames + kSegFrames - 1) / kSegFrames;
+  const bool vec_flags = (reinterpret_cast<uintptr_t>(p.flags) & 15u) == 0;
+  for (int seg0 = seg_begin & ~31; seg0 < n_seg && exit_f == p.n_frames; seg0 += 32) {
     // lane L summarises segment seg0 + L: bit j of m_act = frame j reached the detector, bit j of
     // m_one = it has a difference image (flag 1).  One round of loads per 1024 frames keeps the
     // long empty stretches of a clip off the sequential path.
     unsigned m_act = 0, m_one = 0;
-    {
+    if (seg0 + lane >= seg_begin) {
       const int fs = (seg0 + lane) * kSegFrames;
       if (vec_flags && fs + kSegFrames <= p.n_frames) {
         const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(p.flags + fs));
@@ -779,7 +896,108 @@ __global__ void __launch_bounds__(256) head_track_commit_kernel(const HeadTrackP
         cur.last_p = __shfl_sync(fullmask, spec_final, ll);
       }
     }   // busy segments of this group
-    }   // groups of 32 segments
+  }   // groups of 32 segments
+  WalkEnd w;
+  w.exit_f = exit_f;
+  w.cur = cur;
+  return w;
+}
+
+// frames after the exit frame were never reached by the reference loop (:1494)
+__device__ __forceinline__ void clear_after_exit(const HeadTrackParams& p, int exit_f) {
+  const int64_t first_dead = (int64_t)exit_f + 1;
+  for (int64_t i = first_dead * 5 + threadIdx.x; i < (int64_t)p.n_frames * 5; i += blockDim.x) p.out[i] = -1;
+}
+
+__global__ void __launch_bounds__(256) head_track_commit_kernel(const HeadTrackParams p) {
+  __shared__ int s_exit_f;          // range-local index of the exit frame, or n_frames
+  if (threadIdx.x < 32) {
+    TrackState cur;
+    cur.last_f = p.last_frame_in;
+    cur.last_p = p.last_pos_in;
+    const WalkEnd w = commit_walk(p, 0, cur, threadIdx.x);
+    if (threadIdx.x == 0) {
+      s_exit_f = w.exit_f;
+      p.stop[0] = w.exit_f == p.n_frames ? FF_NO_EXIT : (int)(p.first_frame + w.exit_f);
+      p.stop[1] = w.cur.last_f;
+      p.stop[2] = w.cur.last_p;
+    }
+  }
+  __syncthreads();
+  clear_after_exit(p, s_exit_f);
+}
+
+// Chained speculation, final step: everything in parallel unless a repaired walk missed its guess.
+__global__ void __launch_bounds__(256) head_track_resolve_kernel(const HeadTrackParams p) {
+  __shared__ int s_u, s_exit_f, s_last_seg;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned fullmask = 0xFFFFFFFFu;
+  const int n_seg = (p.n_frames + kSegFrames - 1) / kSegFrames;
+  if (tid == 0) {
+    s_u = n_seg;
+    s_exit_f = p.n_frames;
+    s_last_seg = -1;
+  }
+  __syncthreads();
+  // ---- first segment whose repaired walk did not end in the state its successors guessed -------------
+  for (int sg = tid; sg < n_seg; sg += blockDim.x) {
+    const int4 lo = __ldcg(reinterpret_cast<const int4*>(p.seg + (int64_t)sg * kSegInts));
+    const int4 hi = __ldcg(reinterpret_cast<const int4*>(p.seg + (int64_t)sg * kSegInts) + 1);
+    if (hi.x > 0) {                               // re-run from a guess (hi.z, hi.w)
+      const bool own = lo.y >= 0;                 // the speculative walk ended with a state: later guesses use E1
+      const int tf = own ? lo.x : hi.z, tp = own ? lo.y : hi.w;
+      if (lo.z != tf || lo.w != tp) atomicMin(&s_u, sg);
+    }
+  }
+  __syncthreads();
+  const int u = s_u;                              // the rows of segments 0..u-1 are the true walk's
+  // ---- exit frame and last state among them -----------------------------------------------------------
+  for (int sg = tid; sg < u; sg += blockDim.x) {
+    const int4 lo = __ldcg(reinterpret_cast<const int4*>(p.seg + (int64_t)sg * kSegInts));
+    const int4 hi = __ldcg(reinterpret_cast<const int4*>(p.seg + (int64_t)sg * kSegInts) + 1);
+    if (hi.y < p.n_frames) atomicMin(&s_exit_f, hi.y);
+    if ((hi.x > 0 ? lo.w : lo.y) >= 0) atomicMax(&s_last_seg, sg);
+  }
+  __syncthreads();
+  int exit_f = s_exit_f;
+  const bool fallback = exit_f == p.n_frames && u < n_seg;
+  if (fallback) {
+    // a guess missed before any exit: segments from u on get the speculation's rows back ...
+    for (int sg = u + warp; sg < n_seg; sg += blockDim.x / 32) {
+      const int n_fixed = p.seg[(int64_t)sg * kSegInts + 4];
+      if (n_fixed == 0) continue;
+      const int fme = sg * kSegFrames + lane;
+      const int flme = fme < p.n_frames ? (int)p.flags[fme] : 0;
+      const unsigned act = __ballot_sync(fullmask, flme != 0);
+      if (flme != 0 && __popc(act & ((1u << lane) - 1u)) < n_fixed) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) p.out[(int64_t)fme * 5 + k] = p.out2[(int64_t)fme * 5 + k];
+      }
+    }
+    __syncthreads();
+  }
+  if (warp == 0) {
+    TrackState cur;
+    cur.last_f = p.last_frame_in;
+    cur.last_p = p.last_pos_in;
+    if (exit_f < p.n_frames) {
+      cur.last_f = (int)(p.first_frame + exit_f);
+      cur.last_p = p.out[(int64_t)exit_f * 5];
+    } else if (!fallback) {
+      const int ls = s_last_seg;
+      if (ls >= 0) {
+        const int32_t* e = p.seg + (int64_t)ls * kSegInts;
+        const bool ran = e[4] > 0;
+        cur.last_f = ran ? e[2] : e[0];
+        cur.last_p = ran ? e[3] : e[1];
+      }
+    } else {                                      // ... and are validated one after the other from the state
+      cur.last_f = p.seg[(int64_t)u * kSegInts + 6];          // segment u guessed (right, as all before it hold)
+      cur.last_p = p.seg[(int64_t)u * kSegInts + 7];
+      const WalkEnd w = commit_walk(p, u, cur, lane);
+      exit_f = w.exit_f;
+      cur = w.cur;
+    }
     if (lane == 0) {
       s_exit_f = exit_f;
       p.stop[0] = exit_f == p.n_frames ? FF_NO_EXIT : (int)(p.first_frame + exit_f);
@@ -788,12 +1006,14 @@ __global__ void __launch_bounds__(256) head_track_commit_kernel(const HeadTrackP
     }
   }
   __syncthreads();
-  // frames after the exit frame were never reached by the reference loop (:1494)
-  const int64_t first_dead = (int64_t)s_exit_f + 1;
-  for (int64_t i = first_dead * 5 + tid; i < (int64_t)p.n_frames * 5; i += blockDim.x) p.out[i] = -1;
+  clear_after_exit(p, s_exit_f);
 }
 
 }  // namespace
+
+int64_t head_track_scratch_len(int64_t n_frames) {
+  return ((5 * n_frames + 3) & ~(int64_t)3) + kSegInts * ((n_frames + kSegFrames - 1) / kSegFrames) + 8;
+}
 
 int head_lines_impl(const void* frames, const void* halo, int64_t n_frames, int height, int width, int bits,
                     const int32_t* bg_dev, const int32_t* partial, int64_t min_signal_count, int32_t diff_thr,
@@ -872,7 +1092,8 @@ int head_lines_impl(const void* frames, const void* halo, int64_t n_frames, int 
 int head_track_impl(const double* lines, const uint8_t* flags, int64_t n_frames, int64_t first_frame, int width,
                     int32_t edge_margin_px, int32_t max_displacement_px, int32_t search_window_px,
                     double min_gradient_strength, double sobel_threshold_fraction, int32_t exit_margin_px,
-                    int32_t last_frame_in, int32_t last_pos_in, int32_t* out, int32_t* stop, cudaStream_t st) {
+                    int32_t last_frame_in, int32_t last_pos_in, int32_t* out, int32_t* stop, int32_t* scratch,
+                    cudaStream_t st) {
   if (lines == nullptr || flags == nullptr || out == nullptr || stop == nullptr) return FF_ERR_INVALID;
   if (n_frames <= 0 || width < 2 || n_frames > 0x7FFFFFFF || first_frame < 0) return FF_ERR_INVALID;
   FF_CUDA_TRY(cudaMemsetAsync(out, 0xFF, sizeof(int32_t) * 5 * (size_t)n_frames, st));
@@ -894,11 +1115,27 @@ int head_track_impl(const double* lines, const uint8_t* flags, int64_t n_frames,
   p.stop = stop;
   if (getenv("FF_TRACK_SEQUENTIAL") == nullptr) {       // default: speculative parallel walk
     const int64_t n_seg = (n_frames + kSegFrames - 1) / kSegFrames;
+    const unsigned seg_ctas = (unsigned)((n_seg + kSpecWarpsPerCta - 1) / kSpecWarpsPerCta);
+    const bool chained = scratch != nullptr && getenv("FF_TRACK_UNCHAINED") == nullptr;
+    if (chained) {
+      if (reinterpret_cast<uintptr_t>(scratch) % 16 != 0) return FF_ERR_ALIGNMENT;
+      const int64_t rows = (5 * n_frames + 3) & ~(int64_t)3;          // segment records start 16-byte aligned
+      p.out2 = scratch;
+      p.seg = scratch + rows;
+      p.seg_hdr = p.seg + kSegInts * n_seg;
+      FF_CUDA_TRY(cudaMemsetAsync(p.seg_hdr, 0x7F, 4 * sizeof(int32_t), st));
+    }
     head_track_fullwidth_kernel<<<(unsigned)((n_frames + kSpecWarpsPerCta - 1) / kSpecWarpsPerCta), kSpecWarpsPerCta * 32, 0, st>>>(p);
     FF_CUDA_TRY(cudaGetLastError());
-    head_track_spec_kernel<<<(unsigned)((n_seg + kSpecWarpsPerCta - 1) / kSpecWarpsPerCta), kSpecWarpsPerCta * 32, 0, st>>>(p);
+    head_track_spec_kernel<<<seg_ctas, kSpecWarpsPerCta * 32, 0, st>>>(p);
     FF_CUDA_TRY(cudaGetLastError());
-    head_track_commit_kernel<<<1, 256, 0, st>>>(p);
+    if (chained) {
+      head_track_fixup_kernel<<<seg_ctas, kSpecWarpsPerCta * 32, 0, st>>>(p);
+      FF_CUDA_TRY(cudaGetLastError());
+      head_track_resolve_kernel<<<1, 256, 0, st>>>(p);
+    } else {
+      head_track_commit_kernel<<<1, 256, 0, st>>>(p);
+    }
     FF_CUDA_TRY(cudaGetLastError());
     return FF_OK;
   }

@@ -438,8 +438,8 @@ class FlameFrontEngine:
                 max_displacement_px(frame_rate, calibration, params), params.search_window_px,
                 float(params.min_gradient_strength), float(params.sobel_threshold_fraction),
                 params.exit_margin_px, int(tracker_state[0]), int(tracker_state[1]), track.data_ptr(),
-                stop.data_ptr(), st), "ff_head_track")
-        self.launches += 6      # stream, flags, band, full-width, speculative walk, commit
+                stop.data_ptr(), self._track_scratch(n_frames).data_ptr(), st), "ff_head_track")
+        self.launches += 7      # stream, flags, band, full-width, speculative walk, fix-up, resolve
         done, bg_host, line_host = fetch
         done.synchronize()
         scalars = ClipScalars.from_frame0_stats(int(bg_host.item()), line_host.numpy())
@@ -561,9 +561,17 @@ class FlameFrontEngine:
                 lines.data_ptr(), flags.data_ptr(), n, first_frame, width, params.edge_margin_px, max_displacement,
                 params.search_window_px, float(params.min_gradient_strength),
                 float(params.sobel_threshold_fraction), params.exit_margin_px, int(tracker_state[0]),
-                int(tracker_state[1]), track.data_ptr(), stop.data_ptr(), self._stream()), "ff_head_track")
-        self.launches += 3
+                int(tracker_state[1]), track.data_ptr(), stop.data_ptr(), self._track_scratch(n).data_ptr(),
+                self._stream()), "ff_head_track")
+        self.launches += 4
         return track, stop
+
+    def _track_scratch(self, n_frames: int) -> torch.Tensor:
+        """Scratch of ``ff_head_track`` (second result table + per-segment states of the chained
+        speculation); fully written before it is read, so it needs no initialisation."""
+        n_elems = C.c_int64(0)
+        _cabi.check(self._lib.ff_head_track_scratch_len(n_frames, C.byref(n_elems)), "ff_head_track_scratch_len")
+        return torch.empty(n_elems.value, dtype=torch.int32, device=self.device)
 
     def truncate(self, pos: torch.Tensor, first_frame: int, first_exit: torch.Tensor) -> None:
         """Mark frames at/after the (global) first exit frame as dropped (README.md:145-149)."""

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FF_ABI_VERSION 4
+#define FF_ABI_VERSION 5
 
 /* status codes */
 #define FF_OK                 0
@@ -204,15 +204,21 @@ int ff_exchange_destroy(ff_exchange* x);
  *   last_frame_in/last_pos_in  tracker state carried in (-1/-1 = no detection yet)
  *   out_dev   int32[n_frames,5]: final, pos_min_gradient, pos_rightmost_sobel, search_start,
  *             search_end; all -1 for frames that were not processed or lie after the exit frame
- *   stop_dev  int32[3]: exit frame (global index) or FF_NO_EXIT, last detection frame, last position */
+ *   stop_dev  int32[3]: exit frame (global index) or FF_NO_EXIT, last detection frame, last position
+ *   scratch_dev  int32[ff_head_track_scratch_len(n_frames)] or NULL.  The walk over the frames is
+ *             sequential only through (last frame, last position); it runs as speculative walks of
+ *             32-frame segments.  With scratch the segments' start states are chained and checked in
+ *             parallel; without it one warp validates the segments one after the other.  Same results. */
 int ff_head_lines(const void* frames_dev, const void* halo_dev, int64_t n_frames, int height, int width,
                   int bits, const int32_t* bg_dev, const int32_t* partial_dev, int64_t min_signal_count,
                   int32_t diff_thr, const double* gauss_weights_host, int radius, const uint8_t* skip_dev,
                   double* lines_out_dev, uint8_t* flags_out_dev, int32_t* scratch_dev, void* stream);
+int ff_head_track_scratch_len(int64_t n_frames, int64_t* n_elems);
 int ff_head_track(const double* lines_dev, const uint8_t* flags_dev, int64_t n_frames, int64_t first_frame,
                   int width, int32_t edge_margin_px, int32_t max_displacement_px, int32_t search_window_px,
                   double min_gradient_strength, double sobel_threshold_fraction, int32_t exit_margin_px,
-                  int32_t last_frame_in, int32_t last_pos_in, int32_t* out_dev, int32_t* stop_dev, void* stream);
+                  int32_t last_frame_in, int32_t last_pos_in, int32_t* out_dev, int32_t* stop_dev,
+                  int32_t* scratch_dev, void* stream);
 
 /* ---- frame-level operators (the per-frame seam of scripts/process_videos.py) ----------------------
  * What a caller gets who uses the reference's frame functions instead of its driver loop.  Inputs

@@ -149,18 +149,28 @@ def test_head_with_skip_frames_and_no_detection(engine):
 
 
 def _track_both_ways(engine, packed, n, h, w, hp, rate, cal, monkeypatch, **kw):
-    """(speculative, sequential) tracker outputs on the same lines."""
-    monkeypatch.delenv("FF_TRACK_SEQUENTIAL", raising=False)
-    spec_res = engine.process_head(packed, n, h, w, 12, hp, rate, cal, **kw)
-    spec_out = (spec_res.track.cpu().numpy(), spec_res.stop.cpu().numpy(), spec_res.flags.cpu().numpy())
+    """(speculative, sequential) tracker outputs on the same lines.  The speculative tracker is run in
+    both of its forms - chained guesses checked in parallel (default) and segment-by-segment
+    validation (FF_TRACK_UNCHAINED=1) - which must agree before either is compared."""
+    def run():
+        r = engine.process_head(packed, n, h, w, 12, hp, rate, cal, **kw)
+        return r.track.cpu().numpy(), r.stop.cpu().numpy(), r.flags.cpu().numpy()
+
+    for var in ("FF_TRACK_SEQUENTIAL", "FF_TRACK_UNCHAINED"):
+        monkeypatch.delenv(var, raising=False)
+    spec_out = run()
+    monkeypatch.setenv("FF_TRACK_UNCHAINED", "1")
+    unchained = run()
+    monkeypatch.delenv("FF_TRACK_UNCHAINED", raising=False)
+    for a, b in zip(spec_out, unchained):
+        assert np.array_equal(a, b), "chained and unchained speculation disagree"
     monkeypatch.setenv("FF_TRACK_SEQUENTIAL", "1")
-    seq_res = engine.process_head(packed, n, h, w, 12, hp, rate, cal, **kw)
-    seq_out = (seq_res.track.cpu().numpy(), seq_res.stop.cpu().numpy(), seq_res.flags.cpu().numpy())
+    seq_out = run()
     monkeypatch.delenv("FF_TRACK_SEQUENTIAL", raising=False)
     return spec_out, seq_out
 
 
-@pytest.mark.parametrize("case", ["long_flame", "slow_no_exit", "noise", "late_start"])
+@pytest.mark.parametrize("case", ["long_flame", "slow_no_exit", "noise", "late_start", "noise_gaps", "two_fronts"])
 def test_speculative_tracker_equals_sequential_walk(engine, monkeypatch, case):
     """The speculative parallel tracker (32 segments walked at once, then validated in order) must
     reproduce the sequential walk exactly - several batches of 1024 frames, segments that do not
@@ -178,6 +188,20 @@ def test_speculative_tracker_equals_sequential_walk(engine, monkeypatch, case):
         spec = syn.SyntheticSpec(width=256, height=16, n_frames=2600, style="mini", t_enter=2300.0, velocity=1.1,
                                  seed=23)
         frames = syn.render_frames(spec)
+    elif case == "two_fronts":      # a second, brighter front far ahead appears and vanishes: guesses miss
+        spec = syn.SyntheticSpec(width=1024, height=16, n_frames=1200, style="mini", t_enter=30.0, velocity=0.6,
+                                 seed=24)
+        frames = syn.render_frames(spec)
+        for i in range(200, 1100, 37):
+            x = 400 + (i * 7) % 500
+            frames[i:i + 3, :, x:x + 12] = np.minimum(frames[i:i + 3, :, x:x + 12].astype(np.int64) + 3000, 4095)
+    elif case == "noise_gaps":      # erratic blobs with empty stretches: walks fall back to "nothing" often
+        frames = rng.integers(30, 60, size=(1400, 16, 256)).astype(np.uint16)
+        for i in range(1, len(frames)):
+            if (i // 9) % 3 == 1:
+                continue
+            x = int(rng.integers(0, 236))
+            frames[i, :, x:x + int(rng.integers(3, 20))] += int(rng.integers(200, 3500))
     else:                           # bright random blobs: every frame non-empty, erratic detections
         frames = rng.integers(30, 60, size=(1300, 16, 256)).astype(np.uint16)
         for i in range(1, len(frames)):
@@ -185,7 +209,7 @@ def test_speculative_tracker_equals_sequential_walk(engine, monkeypatch, case):
             frames[i, :, x:x + int(rng.integers(4, 25))] += int(rng.integers(300, 3000))
     n, h, w = frames.shape
     packed = dev(syn.pack_frames(frames, 12), engine)
-    hp = HeadParams(exit_margin_px=15 if case != "noise" else 1)
+    hp = HeadParams(exit_margin_px=15 if not case.startswith("noise") else 1)
     (t1, s1, f1), (t2, s2, f2) = _track_both_ways(engine, packed, n, h, w, hp, 160000, 0.000833333, monkeypatch)
     assert np.array_equal(f1, f2)
     assert np.array_equal(s1, s2), (s1, s2)
