@@ -381,17 +381,15 @@ class FlameFrontEngine:
         return RangeResult(first_frame, pos, counts, first_exit, diff, profiles, decoded, scalars)
 
     # ------------------------------------------------------------------ HEAD-parity detector
-    def process_head(self, frames: torch.Tensor, n_frames: int, height: int, width: int, bits: int,
-                     params, frame_rate: float, calibration: float, *, frame0: Optional[torch.Tensor] = None,
-                     first_frame: int = 0, halo: Optional[torch.Tensor] = None,
-                     skip: Optional[torch.Tensor] = None, keep_lines: bool = False,
-                     tracker_state=(-1, -1)) -> "HeadRangeResult":
-        """The detector the reference runs at HEAD (scripts/process_videos.py:350-465) on a
-        device-resident frame range: streaming kernel (above-noise counts) -> ``ff_head_lines``
-        (difference, 3x3 opening, Gaussian, Sobel / gradient on the centre band, float64 in
-        SciPy's operation order) -> ``ff_head_track`` (velocity-constrained search window,
-        candidate selection, exit stop).  ``params`` is a ``head.HeadParams``."""
-        from .head import gaussian_weights, max_displacement_px
+    def head_lines(self, frames: torch.Tensor, n_frames: int, height: int, width: int, bits: int, params, *,
+                   frame0: Optional[torch.Tensor] = None, first_frame: int = 0,
+                   halo: Optional[torch.Tensor] = None, skip: Optional[torch.Tensor] = None):
+        """The image part of the HEAD detector on a device-resident frame range - everything that
+        shards by frame range: streaming kernel (above-noise counts) -> ``ff_head_lines``
+        (difference, 3x3 opening, Gaussian, Sobel / gradient on the centre band, float64 in SciPy's
+        operation order).  Returns ``(lines float64[n,2,W], flags uint8[n], pending)``; pass
+        ``pending`` to :meth:`head_scalars` after the remaining launches to get the ``ClipScalars``."""
+        from .head import gaussian_weights
         self._check_dev(frames, "frames")
         fb = frame_nbytes(height, width, bits)
         if frames.dtype != torch.uint8 or frames.numel() < n_frames * fb:
@@ -410,7 +408,7 @@ class FlameFrontEngine:
                 raise ValueError("frame0 (the clip's first frame) is required for a sub-range")
             frame0 = frames[:fb]
         bg_dev, line_dev = self.background(frame0, height, width, bits)
-        fetch = self._fetch_frame0_stats_async(bg_dev, line_dev)
+        pending = self._fetch_frame0_stats_async(bg_dev, line_dev)
         diff_thr = _clamp_i32(math.ceil(params.frame_diff_threshold))
         n_elems, tiles = C.c_int64(0), C.c_int(0)
         _cabi.check(self._lib.ff_partial_len(n_frames, height, width, bits, C.byref(n_elems), C.byref(tiles)),
@@ -418,8 +416,6 @@ class FlameFrontEngine:
         partial = torch.empty(max(1, n_elems.value), dtype=torch.int32, device=self.device)
         lines = torch.empty((n_frames, 2, width), dtype=torch.float64, device=self.device)
         flags = torch.empty(n_frames, dtype=torch.uint8, device=self.device)
-        track = torch.empty((n_frames, 5), dtype=torch.int32, device=self.device)
-        stop = torch.empty(3, dtype=torch.int32, device=self.device)
         scratch = torch.empty(n_frames + 4, dtype=torch.int32, device=self.device)
         weights = np.ascontiguousarray(gaussian_weights(params.gaussian_sigma), dtype=np.float64)
         radius = (weights.size - 1) // 2
@@ -433,17 +429,32 @@ class FlameFrontEngine:
                 partial.data_ptr(), min_signal_count(height * width, params.min_signal_fraction), diff_thr,
                 weights.ctypes.data_as(C.POINTER(C.c_double)), radius, _ptr(skip), lines.data_ptr(),
                 flags.data_ptr(), scratch.data_ptr(), st), "ff_head_lines")
-            _cabi.check(self._lib.ff_head_track(
-                lines.data_ptr(), flags.data_ptr(), n_frames, first_frame, width, params.edge_margin_px,
-                max_displacement_px(frame_rate, calibration, params), params.search_window_px,
-                float(params.min_gradient_strength), float(params.sobel_threshold_fraction),
-                params.exit_margin_px, int(tracker_state[0]), int(tracker_state[1]), track.data_ptr(),
-                stop.data_ptr(), self._track_scratch(n_frames).data_ptr(), st), "ff_head_track")
-        self.launches += 7      # stream, flags, band, full-width, speculative walk, fix-up, resolve
-        done, bg_host, line_host = fetch
+        self.launches += 3      # stream, flags, band
+        return lines, flags, pending
+
+    @staticmethod
+    def head_scalars(pending) -> ClipScalars:
+        """The clip's float64 frame-0 statistics once the side-stream copies of :meth:`head_lines` landed."""
+        done, bg_host, line_host = pending
         done.synchronize()
-        scalars = ClipScalars.from_frame0_stats(int(bg_host.item()), line_host.numpy())
-        return HeadRangeResult(first_frame, track, flags, stop, lines if keep_lines else None, scalars)
+        return ClipScalars.from_frame0_stats(int(bg_host.item()), line_host.numpy())
+
+    def process_head(self, frames: torch.Tensor, n_frames: int, height: int, width: int, bits: int,
+                     params, frame_rate: float, calibration: float, *, frame0: Optional[torch.Tensor] = None,
+                     first_frame: int = 0, halo: Optional[torch.Tensor] = None,
+                     skip: Optional[torch.Tensor] = None, keep_lines: bool = False,
+                     tracker_state=(-1, -1)) -> "HeadRangeResult":
+        """The detector the reference runs at HEAD (scripts/process_videos.py:350-465) on a
+        device-resident frame range: :meth:`head_lines` (the image pipeline) -> ``ff_head_track``
+        (velocity-constrained search window, candidate selection, exit stop; :meth:`head_track_lines`).
+        ``params`` is a ``head.HeadParams``."""
+        from .head import max_displacement_px
+        lines, flags, pending = self.head_lines(frames, n_frames, height, width, bits, params, frame0=frame0,
+                                                first_frame=first_frame, halo=halo, skip=skip)
+        track, stop = self.head_track_lines(lines, flags, first_frame, width, params,
+                                            max_displacement_px(frame_rate, calibration, params), tracker_state)
+        return HeadRangeResult(first_frame, track, flags, stop, lines if keep_lines else None,
+                               self.head_scalars(pending))
 
     # ------------------------------------------------------------------ frame-level operators (seam B3)
     _PX_TYPES = {torch.uint8: FF_PX_U8, torch.uint16: FF_PX_U16, torch.float64: FF_PX_F64}

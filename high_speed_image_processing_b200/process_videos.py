@@ -183,10 +183,7 @@ def process_video(video: PhotonVideo, config: VideoSourceConfig, calibration: fl
     if n == 0:
         raise ValueError("video has no frames")
     if config.detection_method == "head":
-        if exchange is not None and exchange.size > 1:
-            raise ValueError("detection_method='head' tracks sequentially over the clip: shard by whole "
-                             "videos (process_collection), not by frame range")
-        return _process_video_head(video, config, calibration, offset, eng)
+        return _process_video_head(video, config, calibration, offset, eng, exchange)
     params = config.detection_params()
 
     # per-clip scalars from frame 0 (every rank reads frame 0 itself: 1 frame of H2D)
@@ -264,24 +261,73 @@ def process_video(video: PhotonVideo, config: VideoSourceConfig, calibration: fl
 
 
 def _process_video_head(video: PhotonVideo, config: VideoSourceConfig, calibration: float, offset: float,
-                        eng) -> VideoResult:
-    """HEAD-parity mode: the reference loop :1441-1516 with ``FlameDetector.detect`` on the GPU."""
+                        eng, exchange=None) -> VideoResult:
+    """HEAD-parity mode: the reference loop :1441-1516 with ``FlameDetector.detect`` on the GPU.
+
+    With an ``exchange`` over several ranks the clip is split into contiguous frame ranges like the
+    other methods: every rank uploads its range (+ one halo frame) and runs the image pipeline on it
+    (``engine.head_lines`` - all of the HBM and PCIe traffic); the search, sequential only through
+    (last frame, last position), runs range after range: a rank receives that 3-int state from its
+    predecessor, walks its range (``ff_head_track``, ~0.1 ms) and passes the state on; one
+    all-gather of the int32 result rows finishes the clip.  Results are identical on every rank."""
     import torch
+    import torch.distributed as dist
     from ._cabi import FF_NO_EXIT
-    from .engine import min_signal_count
+    from .head import max_displacement_px
 
     hp = config.head_params
     n, (h, w), bits = len(video), video.frame_shape, video.storage_bits
-    frames_dev = eng.upload(video.raw_frames(0, n))
-    skip_dev = skip_np = None
+    skip_np = None
     if config.skip_frames:
         skip_np = np.zeros(n, dtype=np.uint8)
         for s in config.skip_frames:
             if 0 <= s < n:
                 skip_np[s] = 1
-        skip_dev = torch.from_numpy(skip_np).to(eng.device)
-    res = eng.process_head(frames_dev, n, h, w, bits, hp, video.frame_rate, calibration, skip=skip_dev)
-    track, flags = res.track.cpu().numpy(), res.flags.cpu().numpy()
+    multi = exchange is not None and exchange.size > 1
+    if not multi:
+        frames_dev = eng.upload(video.raw_frames(0, n))
+        skip_dev = None if skip_np is None else torch.from_numpy(skip_np).to(eng.device)
+        res = eng.process_head(frames_dev, n, h, w, bits, hp, video.frame_rate, calibration, skip=skip_dev)
+        track, flags, scalars = res.track.cpu().numpy(), res.flags.cpu().numpy(), res.scalars
+    else:
+        a, b = exchange.my_range(n)
+        rank, size, group = exchange.rank, exchange.size, exchange.group
+        frame0 = eng.upload(video.raw_frames(0, 1))
+        state = torch.tensor([FF_NO_EXIT, -1, -1], dtype=torch.int32, device=eng.device)
+        cap = exchange.block_cap(n)
+        block = torch.full((cap, 6), -1, dtype=torch.int32, device=eng.device)   # 5 result columns + flag
+        block[:, 5] = 0
+        pending = None
+        if b > a:
+            halo_idx = a - 1
+            if skip_np is not None:
+                while halo_idx >= 0 and skip_np[halo_idx]:
+                    halo_idx -= 1
+            halo_dev = eng.upload(video.raw_frames(halo_idx, halo_idx + 1)) if halo_idx >= 0 else None
+            skip_dev = None if skip_np is None else torch.from_numpy(skip_np[a:b].copy()).to(eng.device)
+            lines, flags_dev, pending = eng.head_lines(eng.upload(video.raw_frames(a, b)), b - a, h, w, bits, hp,
+                                                       frame0=frame0, first_frame=a, halo=halo_dev, skip=skip_dev)
+            block[:b - a, 5] = flags_dev
+        else:
+            _, _, pending = eng.head_lines(frame0, 1, h, w, bits, hp)      # this rank only needs the clip scalars
+        if rank > 0:
+            dist.recv(state, src=dist.get_global_rank(group, rank - 1) if group is not None else rank - 1, group=group)
+        exit_before, last_f, last_p = (int(v) for v in state.tolist())
+        if b > a and exit_before == FF_NO_EXIT:      # the walk has not ended before this range
+            track_dev, state = eng.head_track_lines(lines, flags_dev, a, w, hp,
+                                                    max_displacement_px(video.frame_rate, calibration, hp),
+                                                    (last_f, last_p))
+            block[:b - a, :5] = track_dev
+        if rank + 1 < size:
+            dist.send(state, dst=dist.get_global_rank(group, rank + 1) if group is not None else rank + 1, group=group)
+        gathered = torch.empty((size, cap, 6), dtype=torch.int32, device=eng.device)
+        dist.all_gather_into_tensor(gathered, block, group=group)
+        gathered = gathered.cpu().numpy()
+        from .sharding import contiguous_range
+        parts = [gathered[r, :hi - lo] for r in range(size) for lo, hi in [contiguous_range(n, r, size)]]
+        rows_all = np.concatenate(parts)
+        track, flags = np.ascontiguousarray(rows_all[:, :5]), rows_all[:, 5].astype(np.uint8)
+        scalars = eng.head_scalars(pending)
     time_of = video.get_absolute_time if config.use_absolute_time else video.get_time
     summary = finish_head_track(track, flags, 0, w, video.frame_rate, calibration, offset, time_of, hp)
     pos = np.full(n, -1, dtype=np.int32)
@@ -292,7 +338,7 @@ def _process_video_head(video: PhotonVideo, config: VideoSourceConfig, calibrati
     processed = np.ones(n, dtype=bool) if skip_np is None else skip_np == 0
     empty_frames = int(np.count_nonzero((flags[:stop_frame] == 0) & processed[:stop_frame]))
     first_exit = summary.stop[1] if summary.stop and summary.stop[0] == "exit" else None
-    return VideoResult(res.scalars, pos, np.zeros(n, dtype=np.int32), first_exit, list(summary.rows), empty_frames,
+    return VideoResult(scalars, pos, np.zeros(n, dtype=np.int32), first_exit, list(summary.rows), empty_frames,
                        summary.velocity_history, summary.ddt_frame, summary.stop)
 
 

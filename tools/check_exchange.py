@@ -110,6 +110,28 @@ def main() -> None:
             report["ok"] = False
             print(f"[rank {rank}] MISMATCH process_video residency={residency}", flush=True)
     report["process_video_sharded"] = "host+device residency vs oracle rows"
+    # ---- the HEAD detector, range-sharded: image pipeline per rank, tracker state handed rank to rank ----
+    from oracle import head_oracle as ho
+    hcfg = VideoSourceConfig(name="t")
+    hcfg.detection_method = "head"
+    for label, hspec in (("exit", syn.SyntheticSpec(width=512, height=64, n_frames=301, style="nova", t_enter=15.0,
+                                                    velocity=2.5, seed=5)),
+                         ("no_exit", syn.SyntheticSpec(width=512, height=32, n_frames=157, style="mini", t_enter=90.0,
+                                                       velocity=1.5, seed=6))):
+        hframes = syn.render_frames(hspec)
+        if rank == 0:
+            syn.write_clip(root[0], f"head-{label}", hspec, frames=hframes)
+        dist.barrier()
+        with open_video(f"{root[0]}/head-{label}.cihx") as video:
+            res = process_video(video, hcfg, 0.000833333, 1.347567, engine=eng, exchange=ex)
+            want_h = ho.run_head(hframes, video.frame_rate, 0.000833333, 1.347567, video.get_absolute_time)
+        same = ([list(r) for r in res.rows] == want_h.rows and res.velocity_history == want_h.velocity_history
+                and res.ddt_frame == want_h.ddt_frame and res.stop == want_h.stop and len(want_h.rows) > 20)
+        if not same:
+            report["ok"] = False
+            print(f"[rank {rank}] MISMATCH head sharded {label}: {res.stop} vs {want_h.stop}, "
+                  f"{len(res.rows)} vs {len(want_h.rows)} rows", flush=True)
+    report["head_sharded"] = "rows, velocities, DDT frame and stop vs the oracle loop (exit / no exit)"
     ex.close()
     dist.barrier()
     if rank == 0:
