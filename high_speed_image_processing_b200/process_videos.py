@@ -16,7 +16,8 @@ The reference's frame-level names (``FlameDetector``, ``FlameDetectorConfig``,
 ``three_frame_difference``, ``is_empty_frame``, ``write_results``) are importable from here as from
 the reference script; they live in ``detector.py`` and run on the GPU frame by frame.
 
-Matplotlib diagnostics (:783-1270) are out of scope and never on this path.
+Matplotlib diagnostics (:783-1270) live in ``diagnostics.py`` (optional, off this path;
+``process_video_source(..., diagnostics=True)``).
 """
 from __future__ import annotations
 
@@ -420,8 +421,14 @@ def write_head_outputs(res: "VideoResult", out_dir, stem: str) -> List[str]:
 # driver (reference: scripts/process_videos.py:1277-1629, :1633-1703)
 # --------------------------------------------------------------------------------------
 def process_video_source(config: VideoSourceConfig, processor: Optional[MPIVideoProcessor] = None,
-                         engine=None, exchange=None, verbose: bool = True) -> Dict[str, VideoResult]:
-    """Process every ``*.cihx`` under ``config.video_path`` and write the result files."""
+                         engine=None, exchange=None, verbose: bool = True,
+                         diagnostics: bool = False) -> Dict[str, VideoResult]:
+    """Process every ``*.cihx`` under ``config.video_path`` and write the result files.
+
+    ``diagnostics=True`` additionally renders, on the root rank and after the timed work, the
+    figures the reference driver draws for every recording (stacked sequences and one 12-panel
+    figure per frame that reaches the detector, :1385-1418, :1474-1480) into
+    ``<output_dir>/<stem>-frames/`` - needs Matplotlib (``diagnostics.py``)."""
     is_root = (processor is None or processor.is_root) and (exchange is None or exchange.rank == 0)
     say = print if (verbose and is_root) else (lambda *a, **k: None)
     say(f"\n{'=' * 60}\nProcessing: {config.name}\nVideo path: {config.video_path}")
@@ -461,6 +468,12 @@ def process_video_source(config: VideoSourceConfig, processor: Optional[MPIVideo
                 else:
                     path = write_position_file(res.rows, out_dir / f"{cihx_file.stem}-flame-position.txt")
                     say(f"  All results: {path} ({len(res.rows)} points)")
+            if diagnostics and is_root and config.output_dir:
+                from .diagnostics import render_video_diagnostics
+                n_fig = render_video_diagnostics(video, config.name, cihx_file.stem, cal,
+                                                 Path(config.output_dir) / f"{cihx_file.stem}-frames",
+                                                 skip_frames=config.skip_frames, engine=engine)
+                say(f"  Diagnostics: {n_fig} frame figures in {cihx_file.stem}-frames/")
             results[cihx_file.name] = res
         finally:
             video.close()
