@@ -434,6 +434,50 @@ def own_arm(args) -> None:
         except Exception as exc:                                               # never fail the GPU line over it
             cpu["all_cores"] = {"error": repr(exc)}
 
+    # ---------------- the detector the reference executes at HEAD, same clip (rank 0, N=1 only) -------
+    head = None
+    if rank == 0 and world == 1 and not args.no_head:
+        from high_speed_image_processing_b200.head import HeadParams, finish_head_track
+        hp = HeadParams()
+        cal_h, off_h, rate_h = 0.000833333, 1.347567, float(spec.record_rate)
+        for _ in range(3):
+            hres = eng.process_head(packed, fpr, h, w, 12, hp, rate_h, cal_h)
+        torch.cuda.synchronize()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(args.steps):
+            hres = eng.process_head(packed, fpr, h, w, 12, hp, rate_h, cal_h)
+        h1.record()
+        torch.cuda.synchronize()
+        head_ms = h0.elapsed_time(h1) / args.steps
+        time_of = lambda i: (spec.start_frame + i * spec.skip_frame) / spec.record_rate      # noqa: E731
+        got = finish_head_track(hres.track.cpu().numpy(), hres.flags.cpu().numpy(), 0, w, rate_h, cal_h, off_h,
+                                time_of, hp)
+        head = {"what": "FlameDetector parity path (3x3 opening, Gaussian, Sobel/gradient in float64, windowed "
+                        "tracker) on the same clip, device-resident, steps back to back",
+                "value": fpr / (head_ms * 1e-3), "unit": UNIT, "ms_per_clip": head_ms, "rows": len(got.rows),
+                "stop": list(got.stop) if got.stop else None}
+        if not args.no_cpu_baseline:
+            # the oracle loop (the reference's SciPy calls) on frame 0 + a window that starts in the empty
+            # lead-in and runs into the flame; its rows double as a checker of the GPU rows
+            from oracle import flame_oracle as fo
+            from oracle import head_oracle as ho
+            n_lead, n_flame = 600, 60
+            a0 = int(spec.t_enter) - n_lead
+            win = fo.frames_from_bytes(packed[a0 * fb:(a0 + n_lead + n_flame) * fb].cpu().numpy(), n_lead + n_flame,
+                                       h, w, 12)
+            f0np = fo.frames_from_bytes(frame0.cpu().numpy(), 1, h, w, 12)
+            shift = a0 - 1
+            t_cpu = time.perf_counter()
+            want = ho.run_head(np.concatenate([f0np, win]), rate_h, cal_h, off_h, lambda i: time_of(i + shift))
+            t_cpu = time.perf_counter() - t_cpu
+            mine = [list(r) for r in got.rows if r[0] < a0 + n_lead + n_flame]
+            assert mine == [[r[0] + shift] + r[1:] for r in want.rows], "GPU HEAD rows differ from the oracle loop"
+            head["cpu_baseline"] = {"value": (n_lead + n_flame) / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"{n_lead} lead-in + {n_flame} flame frames in {t_cpu:.1f} s "
+                                              f"(the clip holds ~{FLAME_FRAMES} flame frames in {total}), serial",
+                                    "rows_checked": len(mine)}
+
     if rank == 0:
         peaks_path = REPO / "MEASURED_PEAKS.json"
         if peaks_path.exists():
@@ -464,6 +508,7 @@ def own_arm(args) -> None:
                     "h2d_peak_how": "pinned copy of the same buffer, all ranks concurrently, slowest rank",
                     "frac_of_h2d_peak": (h2d / e2e_sec / 1e9) / h2d_peak if h2d_peak else None,
                     "launches_per_step": launches_e2e, "pageable_source": pageable},
+            "head_detector": head,
             "gpu_launches": launches,
             "clocks": clocks,
             "result": {"first_exit_frame": first_exit, "detections": int(det.size)},
@@ -487,6 +532,7 @@ def main() -> None:
     ap.add_argument("--sample-frames", type=int, default=4000, help="CPU baseline sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-source end-to-end leg")
+    ap.add_argument("--no-head", action="store_true", help="skip the HEAD-detector leg (N=1 only)")
     ap.add_argument("--clock-period-ms", type=int, default=100, help="nvidia-smi sampling period (0 = off)")
     ap.add_argument("--exchange", choices=["auto", "peer", "gathered"], default="auto",
                     help="multi-GPU block transport: peer memory over NVLink (CUDA IPC) or one NCCL all-gather")
