@@ -170,7 +170,8 @@ def _track_both_ways(engine, packed, n, h, w, hp, rate, cal, monkeypatch, **kw):
     return spec_out, seq_out
 
 
-@pytest.mark.parametrize("case", ["long_flame", "slow_no_exit", "noise", "late_start", "noise_gaps", "two_fronts"])
+@pytest.mark.parametrize("case", ["long_flame", "slow_no_exit", "noise", "late_start", "noise_gaps", "two_fronts",
+                                  "two_fronts_exit", "exit_then_noise"])
 def test_speculative_tracker_equals_sequential_walk(engine, monkeypatch, case):
     """The speculative parallel tracker (32 segments walked at once, then validated in order) must
     reproduce the sequential walk exactly - several batches of 1024 frames, segments that do not
@@ -195,6 +196,20 @@ def test_speculative_tracker_equals_sequential_walk(engine, monkeypatch, case):
         for i in range(200, 1100, 37):
             x = 400 + (i * 7) % 500
             frames[i:i + 3, :, x:x + 12] = np.minimum(frames[i:i + 3, :, x:x + 12].astype(np.int64) + 3000, 4095)
+    elif case == "two_fronts_exit":  # missed guesses first, then the front leaves the domain
+        spec = syn.SyntheticSpec(width=1024, height=16, n_frames=1200, style="mini", t_enter=30.0, velocity=1.0,
+                                 seed=25)
+        frames = syn.render_frames(spec)
+        for i in range(150, 700, 41):
+            x = 300 + (i * 11) % 600
+            frames[i:i + 3, :, x:x + 12] = np.minimum(frames[i:i + 3, :, x:x + 12].astype(np.int64) + 3000, 4095)
+    elif case == "exit_then_noise":  # clean walk to the exit; erratic blobs afterwards must not matter
+        spec = syn.SyntheticSpec(width=512, height=16, n_frames=900, style="mini", t_enter=20.0, velocity=1.3,
+                                 seed=26)
+        frames = syn.render_frames(spec)
+        for i in range(spec.exit_frame(15) + 5, 900):
+            x = int(rng.integers(0, 480))
+            frames[i, :, x:x + int(rng.integers(4, 25))] = 3500
     elif case == "noise_gaps":      # erratic blobs with empty stretches: walks fall back to "nothing" often
         frames = rng.integers(30, 60, size=(1400, 16, 256)).astype(np.uint16)
         for i in range(1, len(frames)):
@@ -218,6 +233,8 @@ def test_speculative_tracker_equals_sequential_walk(engine, monkeypatch, case):
         assert (f1 == 1).sum() > 2048 and s1[0] != 2**31 - 1
     if case == "slow_no_exit":
         assert s1[0] == 2**31 - 1 and (t1[:, 0] >= 0).sum() > 100
+    if case in ("two_fronts_exit", "exit_then_noise"):
+        assert s1[0] != 2**31 - 1 and (t1[s1[0] + 1:] == -1).all()
     # carried-in tracker state (a range that continues an earlier one)
     (t3, s3, _), (t4, s4, _) = _track_both_ways(engine, packed, n, h, w, hp, 160000, 0.000833333, monkeypatch,
                                                 tracker_state=(3, 17))
