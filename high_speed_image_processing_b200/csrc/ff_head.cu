@@ -81,6 +81,65 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
   return i < n ? i : period - 1 - i;
 }
 
+// The float64 stages shared by both band kernels.  `band` holds the opened difference image as uint16,
+// band row i / band column j at band[i * stride + j + col0]; rows HALO-1-R .. HALO+1+R and columns
+// [2, LW-2) must be valid.  G0 = Gaussian along rows (axis 0) for band rows HALO-1, HALO, HALO+1; BL =
+// Gaussian along columns (axis 1), valid columns [HALO-1, LW-HALO+1); then Sobel(axis=1) and
+// np.gradient(axis=1) of the centre row.  scipy NI_Correlate1D order: centre tap first, then symmetric
+// pairs outermost -> innermost, explicit round-to-nearest mul/add (no FMA).  Ends with a CTA barrier.
+__device__ __forceinline__ void band_float_stages(const HeadBandParams& p, const uint16_t* band, int stride, int col0,
+                                                  int LW, int tw, int x_begin, int f, double* g0, double* bl) {
+  const int tid = threadIdx.x;
+  const int R = p.radius, HALO = R + 3, W = p.width;
+  for (int e = tid; e < 3 * LW; e += kHeadThreads) {
+    const int b = e / LW, j = e - b * LW;
+    double tmp = 0.0;
+    if (j >= 2 && j < LW - 2) {
+      const uint16_t* col = band + (HALO - 1 + b) * stride + j + col0;
+      tmp = __dmul_rn((double)col[0], p.w[R]);
+      for (int jj = -R; jj < 0; ++jj) {
+        const double pair = __dadd_rn((double)col[jj * stride], (double)col[-jj * stride]);
+        tmp = __dadd_rn(tmp, __dmul_rn(pair, p.w[R + jj]));
+      }
+    }
+    g0[e] = tmp;
+  }
+  __syncthreads();
+  for (int e = tid; e < 3 * LW; e += kHeadThreads) {
+    const int b = e / LW, j = e - b * LW;
+    double tmp = 0.0;
+    if (j >= HALO - 1 && j < LW - HALO + 1) {
+      const double* g = g0 + b * LW;
+      tmp = __dmul_rn(g[j], p.w[R]);
+      for (int jj = -R; jj < 0; ++jj) tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(g[j + jj], g[j - jj]), p.w[R + jj]));
+    }
+    bl[e] = tmp;
+  }
+  __syncthreads();
+  double* out_s = p.lines + ((int64_t)f * 2 + 0) * W;
+  double* out_g = p.lines + ((int64_t)f * 2 + 1) * W;
+  for (int t = tid; t < tw; t += kHeadThreads) {
+    const int j = HALO + t;
+    const int x = x_begin + t;
+    double s3[3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const double* v = bl + b * LW;
+      // correlate1d([-1,0,1]): tmp = in[0]*0; tmp += (in[-1] - in[+1]) * (-1)
+      s3[b] = __dadd_rn(__dmul_rn(v[j], 0.0), __dmul_rn(__dsub_rn(v[j - 1], v[j + 1]), -1.0));
+    }
+    // correlate1d([1,2,1]) along rows: tmp = in[0]*2; tmp += (in[-1] + in[+1]) * 1
+    out_s[x] = __dadd_rn(__dmul_rn(s3[1], 2.0), __dmul_rn(__dadd_rn(s3[0], s3[2]), 1.0));
+    const double* v = bl + 1 * LW;
+    double g;
+    if (x == 0) g = __ddiv_rn(__dsub_rn(v[j + 1], v[j]), 1.0);
+    else if (x == W - 1) g = __ddiv_rn(__dsub_rn(v[j], v[j - 1]), 1.0);
+    else g = __ddiv_rn(__dsub_rn(v[j + 1], v[j - 1]), 2.0);
+    out_g[x] = g;
+  }
+  __syncthreads();      // the next work item reuses the shared-memory band
+}
+
 template <int BITS>
 __global__ void __launch_bounds__(kHeadThreads) head_band_kernel(const HeadBandParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -157,57 +216,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_band_kernel(const HeadBandP
     }
   }
   __syncthreads();
-  // ---- G0 = Gaussian along rows (axis 0) for band rows HALO-1, HALO, HALO+1 ------------------------
-  for (int e = tid; e < 3 * LW; e += kHeadThreads) {
-    const int b = e / LW, j = e - b * LW;
-    double tmp = 0.0;
-    if (j >= 2 && j < LW - 2) {
-      const int row = HALO - 1 + b;
-      tmp = __dmul_rn((double)bufA[row * LW + j], p.w[R]);
-      for (int jj = -R; jj < 0; ++jj) {
-        const double pair = __dadd_rn((double)bufA[(row + jj) * LW + j], (double)bufA[(row - jj) * LW + j]);
-        tmp = __dadd_rn(tmp, __dmul_rn(pair, p.w[R + jj]));
-      }
-    }
-    g0[e] = tmp;
-  }
-  __syncthreads();
-  // ---- BL = Gaussian along columns (axis 1), valid cols [HALO-1, LW-HALO+1) -----------------------
-  for (int e = tid; e < 3 * LW; e += kHeadThreads) {
-    const int b = e / LW, j = e - b * LW;
-    double tmp = 0.0;
-    if (j >= HALO - 1 && j < LW - HALO + 1) {
-      const double* g = g0 + b * LW;
-      tmp = __dmul_rn(g[j], p.w[R]);
-      for (int jj = -R; jj < 0; ++jj) tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(g[j + jj], g[j - jj]), p.w[R + jj]));
-    }
-    bl[e] = tmp;
-  }
-  __syncthreads();
-  // ---- Sobel(axis=1) and np.gradient(axis=1) on the centre row --------------------------------------
-  double* out_s = p.lines + ((int64_t)f * 2 + 0) * W;
-  double* out_g = p.lines + ((int64_t)f * 2 + 1) * W;
-  for (int t = tid; t < tw; t += kHeadThreads) {
-    const int j = HALO + t;
-    const int x = x_begin + t;
-    double s3[3];
-#pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      const double* v = bl + b * LW;
-      // correlate1d([-1,0,1]): tmp = in[0]*0; tmp += (in[-1] - in[+1]) * (-1)
-      const double t0 = __dmul_rn(v[j], 0.0);
-      s3[b] = __dadd_rn(t0, __dmul_rn(__dsub_rn(v[j - 1], v[j + 1]), -1.0));
-    }
-    // correlate1d([1,2,1]) along rows: tmp = in[0]*2; tmp += (in[-1] + in[+1]) * 1
-    out_s[x] = __dadd_rn(__dmul_rn(s3[1], 2.0), __dmul_rn(__dadd_rn(s3[0], s3[2]), 1.0));
-    const double* v = bl + 1 * LW;
-    double g;
-    if (x == 0) g = __ddiv_rn(__dsub_rn(v[j + 1], v[j]), 1.0);
-    else if (x == W - 1) g = __ddiv_rn(__dsub_rn(v[j], v[j - 1]), 1.0);
-    else g = __ddiv_rn(__dsub_rn(v[j + 1], v[j - 1]), 2.0);
-    out_g[x] = g;
-  }
-  __syncthreads();      // the next work item reuses the shared-memory band
+  band_float_stages(p, bufA, LW, 0, LW, tw, x_begin, f, g0, bl);
   }
 }
 
@@ -349,54 +358,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_band_fast_kernel(const Head
       cols_pass(B32, A32, vmax);
       __syncthreads();
     }
-    // ---- G0 = Gaussian along rows (axis 0) for band rows HALO-1, HALO, HALO+1 ------------------------
-    for (int e = tid; e < 3 * LW; e += kHeadThreads) {
-      const int b = e / LW, j = e - b * LW;
-      double tmp = 0.0;
-      if (j >= 2 && j < LW - 2) {
-        const uint16_t* col = bufA + (HALO - 1 + b) * kBandLWA + j + off;
-        tmp = __dmul_rn((double)col[0], p.w[R]);
-        for (int jj = -R; jj < 0; ++jj) {
-          const double pair = __dadd_rn((double)col[jj * kBandLWA], (double)col[-jj * kBandLWA]);
-          tmp = __dadd_rn(tmp, __dmul_rn(pair, p.w[R + jj]));
-        }
-      }
-      g0[e] = tmp;
-    }
-    __syncthreads();
-    // ---- BL = Gaussian along columns (axis 1), valid cols [HALO-1, LW-HALO+1) -----------------------
-    for (int e = tid; e < 3 * LW; e += kHeadThreads) {
-      const int b = e / LW, j = e - b * LW;
-      double tmp = 0.0;
-      if (j >= HALO - 1 && j < LW - HALO + 1) {
-        const double* g = g0 + b * LW;
-        tmp = __dmul_rn(g[j], p.w[R]);
-        for (int jj = -R; jj < 0; ++jj) tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(g[j + jj], g[j - jj]), p.w[R + jj]));
-      }
-      bl[e] = tmp;
-    }
-    __syncthreads();
-    // ---- Sobel(axis=1) and np.gradient(axis=1) on the centre row --------------------------------------
-    double* out_s = p.lines + ((int64_t)f * 2 + 0) * W;
-    double* out_g = p.lines + ((int64_t)f * 2 + 1) * W;
-    for (int t = tid; t < tw; t += kHeadThreads) {
-      const int j = HALO + t;
-      const int x = x_begin + t;
-      double s3[3];
-#pragma unroll
-      for (int b = 0; b < 3; ++b) {
-        const double* v = bl + b * LW;
-        s3[b] = __dadd_rn(__dmul_rn(v[j], 0.0), __dmul_rn(__dsub_rn(v[j - 1], v[j + 1]), -1.0));
-      }
-      out_s[x] = __dadd_rn(__dmul_rn(s3[1], 2.0), __dmul_rn(__dadd_rn(s3[0], s3[2]), 1.0));
-      const double* v = bl + 1 * LW;
-      double g;
-      if (x == 0) g = __ddiv_rn(__dsub_rn(v[j + 1], v[j]), 1.0);
-      else if (x == W - 1) g = __ddiv_rn(__dsub_rn(v[j], v[j - 1]), 1.0);
-      else g = __ddiv_rn(__dsub_rn(v[j + 1], v[j - 1]), 2.0);
-      out_g[x] = g;
-    }
-    __syncthreads();      // the next work item reuses the shared-memory band
+    band_float_stages(p, bufA, kBandLWA, off, LW, tw, x_begin, f, g0, bl);
   }
 }
 
