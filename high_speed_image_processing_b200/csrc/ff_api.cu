@@ -33,6 +33,7 @@ int head_lines_impl(const void*, const void*, int64_t, int, int, int, const int3
 int head_track_impl(const double*, const uint8_t*, int64_t, int64_t, int, int32_t, int32_t, int32_t, double, double,
                     int32_t, int32_t, int32_t, int32_t*, int32_t*, int32_t*, cudaStream_t);
 int64_t head_track_scratch_len(int64_t);
+void stream_copy(uint8_t* dst, const uint8_t* src, size_t n);      // ff_hostcopy.cpp
 int frame_subtract_background_impl(const void*, int, int64_t, double, double*, cudaStream_t);
 int frame_difference_impl(const void*, const void*, int, int64_t, double, double*, cudaStream_t);
 int frame_three_difference_impl(const void*, const void*, const void*, int, int64_t, double, double*, cudaStream_t);
@@ -91,7 +92,7 @@ class CopyPool {
       if (i >= n_parts_) break;
       const size_t a = i * part_;
       const size_t n = a + part_ <= bytes_ ? part_ : bytes_ - a;
-      std::memcpy(dst_ + a, src_ + a, n);
+      stream_copy(dst_ + a, src_ + a, n);
       ++mine;
     }
     if (mine) {
