@@ -317,11 +317,12 @@ class FlameDetector:
                                         self._max_displacement_px, self._book.last_detection())
         final, pos_a, pos_b, s0, s1 = (int(v) for v in track[0].tolist())
 
+        host_stack = imgs["stack"][:, 0].cpu().numpy() if self._intermediates == "host" else None   # one copy
+
         def image(name: str):
             if not keep or (name != "frame_subtracted" and not has_prior):
                 return None
-            t = imgs[name][0]
-            return t if self._intermediates == "device" else t.cpu().numpy()
+            return imgs[name][0] if host_stack is None else host_stack[want.index(name)]
 
         pos_spline_predicted = self.predict_with_spline(frame_idx) if cfg.use_spline_estimator else None
         final_position = final if final >= 0 else None

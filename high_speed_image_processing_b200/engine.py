@@ -518,7 +518,8 @@ class FlameFrontEngine:
         """Full-frame intermediates of ``FlameDetector.detect`` (scripts/process_videos.py:380-413) for
         ``n_frames`` device-resident frames (``ff_head_images``): float64 ``[n,H,W]`` tensors named like
         the fields of ``FlameDetectionResult`` (:197-217), plus ``"state"`` uint8[n] (0 skipped, 1 all
-        valid, 2 no prior frame: only ``frame_subtracted`` is meaningful)."""
+        valid, 2 no prior frame: only ``frame_subtracted`` is meaningful) and ``"stack"``, the one
+        tensor ``[len(want), n, H, W]`` they are views of."""
         from .head import gaussian_weights
         self._check_dev(frames, "frames")
         fb = frame_nbytes(height, width, bits)
@@ -541,7 +542,10 @@ class FlameFrontEngine:
             if skip.dtype != torch.uint8 or skip.numel() != n_frames:
                 raise ValueError("skip must be uint8[n_frames]")
         weights = np.ascontiguousarray(gaussian_weights(gaussian_sigma), dtype=np.float64)
-        out = {name: torch.empty((n_frames, height, width), dtype=torch.float64, device=self.device) for name in want}
+        # one allocation for all requested images (``out["stack"]``, [len(want), n, H, W]): a caller that wants
+        # them on the host needs a single device-to-host copy
+        stack = torch.empty((len(want), n_frames, height, width), dtype=torch.float64, device=self.device)
+        out = {name: stack[i] for i, name in enumerate(want)}
         state = torch.empty(n_frames, dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
             _cabi.check(self._lib.ff_head_images(
@@ -553,6 +557,7 @@ class FlameFrontEngine:
                 "ff_head_images")
         self.launches += 1
         out["state"] = state
+        out["stack"] = stack
         return out
 
     def head_track_lines(self, lines: torch.Tensor, flags: torch.Tensor, first_frame: int, width: int, params,

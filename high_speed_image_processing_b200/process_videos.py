@@ -321,9 +321,9 @@ def _process_video_head(video: PhotonVideo, config: VideoSourceConfig, calibrati
             block[:b - a, :5] = track_dev
         if rank + 1 < size:
             dist.send(state, dst=dist.get_global_rank(group, rank + 1) if group is not None else rank + 1, group=group)
-        gathered = torch.empty((size, cap, 6), dtype=torch.int32, device=eng.device)
+        gathered = torch.empty((size * cap, 6), dtype=torch.int32, device=eng.device)
         dist.all_gather_into_tensor(gathered, block, group=group)
-        gathered = gathered.cpu().numpy()
+        gathered = gathered.view(size, cap, 6).cpu().numpy()
         from .sharding import contiguous_range
         parts = [gathered[r, :hi - lo] for r in range(size) for lo, hi in [contiguous_range(n, r, size)]]
         rows_all = np.concatenate(parts)

@@ -275,7 +275,7 @@ def test_head_images_on_a_packed_range(engine, bits):
         prior = sub
     # without a halo the first frame has no prior: state 2, only frame_subtracted is meaningful
     few = engine.head_images(packed, 3, 24, 160, bits, bg, want=("frame_subtracted", "sobel_output"))
-    assert sorted(few) == ["frame_subtracted", "sobel_output", "state"]
+    assert sorted(few) == ["frame_subtracted", "sobel_output", "stack", "state"]
     assert few["state"].cpu().tolist() == [2, 1, 1]
     assert np.array_equal(few["frame_subtracted"][0].cpu().numpy(), fo.subtract_scalar_background(frames[0], bg))
     assert not few["sobel_output"][0].any()

@@ -190,3 +190,104 @@ def test_collection_sharded_by_video(tmp_path):
                                                     0.5, float(i), n)
     load = [sum(lengths[int(k)] for k, v in r0["res"].items() if v[5] == r) for r in (0, 1)]
     assert abs(load[0] - load[1]) <= max(lengths)                   # size-balanced
+
+
+# ---- the HEAD detector, range-sharded: image work per rank, tracker state handed rank to rank ----------
+class _OracleHeadEngine:
+    """CPU stand-in for the three engine calls of ``process_videos._process_video_head`` (the CUDA
+    kernels need a GPU): the oracle's SciPy lines and its candidate selection, same tensor layouts."""
+    device = torch.device("cpu")
+
+    def upload(self, raw):
+        return torch.from_numpy(np.ascontiguousarray(raw).reshape(-1).copy())
+
+    def head_lines(self, frames, n, h, w, bits, hp, *, frame0=None, first_frame=0, halo=None, skip=None):
+        from oracle import head_oracle as ho
+        dec = fo.frames_from_bytes(frames.numpy(), n, h, w, bits)
+        f0 = dec[0] if frame0 is None else fo.frames_from_bytes(frame0.numpy(), 1, h, w, bits)[0]
+        bg = fo.background_scalar(f0)
+        prior = None if halo is None else fo.subtract_scalar_background(fo.frames_from_bytes(halo.numpy(), 1, h, w, bits)[0], bg)
+        lines = torch.zeros((n, 2, w), dtype=torch.float64)
+        flags = torch.zeros(n, dtype=torch.uint8)
+        for i in range(n):
+            sub = fo.subtract_scalar_background(dec[i], bg)
+            if not fo.is_empty_frame(sub, fo.empty_noise_threshold(bg), hp.min_signal_fraction):
+                if prior is None:
+                    flags[i] = 2
+                else:
+                    s, g = ho.detect_lines_scipy(fo.frame_difference(sub, prior, hp.frame_diff_threshold))
+                    lines[i, 0], lines[i, 1], flags[i] = torch.from_numpy(s.copy()), torch.from_numpy(g.copy()), 1
+            prior = sub
+        return lines, flags, None
+
+    @staticmethod
+    def head_scalars(pending):
+        return None
+
+    def head_track_lines(self, lines, flags, first_frame, width, hp, max_displacement, tracker_state=(-1, -1)):
+        from oracle import head_oracle as ho
+        cfg = ho.HeadConfig()
+        last_f, last_p = tracker_state
+        track = torch.full((flags.numel(), 5), -1, dtype=torch.int32)
+        stop = torch.tensor([FF_NO_EXIT, last_f, last_p], dtype=torch.int32)
+        for i in range(flags.numel()):
+            if flags[i] == 0:
+                continue
+            gf = first_frame + i
+            if last_p < 0:
+                s0, s1 = cfg.edge_margin_px, width - cfg.edge_margin_px
+            else:
+                s0, s1 = last_p, min(width - cfg.edge_margin_px, last_p + max_displacement * max(1, gf - last_f) + cfg.search_window_px)
+            pa = pb = final = None
+            if flags[i] == 1:
+                pa, pb, final = ho.select_position(lines[i, 0].numpy(), lines[i, 1].numpy(), s0, s1, cfg)
+            track[i] = torch.tensor([-1 if v is None else v for v in (final, pa, pb)] + [s0, s1], dtype=torch.int32)
+            if final is not None:
+                last_f, last_p = gf, final
+                if final >= width - cfg.exit_margin_px:
+                    stop[0] = gf
+                    break
+        stop[1], stop[2] = last_f, last_p
+        return track, stop
+
+
+def _head_worker(rank, size, port, n_frames, velocity, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        from high_speed_image_processing_b200.photron import open_video
+        from high_speed_image_processing_b200.process_videos import VideoSourceConfig, _process_video_head
+        spec = syn.SyntheticSpec(width=160, height=12, n_frames=n_frames, style="nova", t_enter=5.0, velocity=velocity,
+                                 tail_length=30.0, curvature_px=1.0, seed=13, bits=16)
+        clip_dir = os.path.join(out_dir, f"clip{rank}")
+        syn.write_clip(clip_dir, "run-1-", spec)
+        cfg = VideoSourceConfig(name="t")
+        cfg.detection_method = "head"
+        with open_video(os.path.join(clip_dir, "run-1-.cihx")) as video:
+            res = _process_video_head(video, cfg, 0.000833333, 1.347567, _OracleHeadEngine(), RangeExchange())
+        import pickle
+        with open(os.path.join(out_dir, f"r{rank}.pkl"), "wb") as f:
+            pickle.dump({"rows": [list(r) for r in res.rows], "vel": res.velocity_history, "stop": res.stop,
+                         "ddt": res.ddt_frame, "first_exit": res.first_exit}, f)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("size,n_frames,velocity", [(2, 61, 3.5), (3, 64, 3.5), (3, 50, 1.2)])
+def test_head_detector_range_sharded_equals_oracle_loop(tmp_path, size, n_frames, velocity):
+    """State hand-over between ranks (send/recv), an exit inside an early rank's range (later ranks must
+    not track), no exit at all, and the all-gather / de-padding of the result rows."""
+    import pickle
+    from oracle import head_oracle as ho
+    mp.spawn(_head_worker, args=(size, _free_port(), n_frames, velocity, str(tmp_path)), nprocs=size, join=True)
+    spec = syn.SyntheticSpec(width=160, height=12, n_frames=n_frames, style="nova", t_enter=5.0, velocity=velocity,
+                             tail_length=30.0, curvature_px=1.0, seed=13, bits=16)
+    time_of = lambda i: fo.frame_time_absolute(i, spec.start_frame, spec.skip_frame, spec.record_rate)  # noqa: E731
+    want = ho.run_head(syn.render_frames(spec), spec.record_rate, 0.000833333, 1.347567, time_of)
+    assert len(want.rows) > 15 and (want.stop is not None) == (velocity > 2)
+    for r in range(size):
+        got = pickle.load(open(tmp_path / f"r{r}.pkl", "rb"))
+        assert got["rows"] == want.rows and got["vel"] == want.velocity_history
+        assert got["stop"] == want.stop and got["ddt"] == want.ddt_frame
+        assert got["first_exit"] == (want.stop[1] if want.stop and want.stop[0] == "exit" else None)
