@@ -261,20 +261,78 @@ def process_video(video: PhotonVideo, config: VideoSourceConfig, calibration: fl
                        empty_frames)
 
 
+def _head_chunk_frames(frame_bytes: int) -> int:
+    """Frames per upload of the HEAD path: bounded device memory whatever the recording's size
+    (FF_HEAD_CHUNK_MB, default 2048 MiB of stored bytes; the float64 line buffers add 16 W bytes per frame)."""
+    mb = int(os.environ.get("FF_HEAD_CHUNK_MB", "2048"))
+    return max(2, (mb << 20) // max(1, frame_bytes))
+
+
+def _head_walk_range(eng, video: PhotonVideo, hp: HeadParams, calibration: float, a: int, b: int,
+                     skip_np: Optional[np.ndarray], frame0_dev, state: Tuple[int, int, int],
+                     stopped=None):
+    """Frames [a, b) of a recording through the HEAD detector in chunks: upload (+ the halo frame, the
+    latest non-skipped frame before the chunk), image pipeline, tracker with the state carried from
+    chunk to chunk.  Nothing is uploaded past the chunk in which the walk ends - on the exit frame
+    (:1488-1494), or where ``stopped(track, flags)`` (the host-side stop rules) says so.
+    ``state`` = (exit frame or FF_NO_EXIT, last detection frame, last position) on entry;
+    returns ``(track int32[b-a,5], flags uint8[b-a], state, pending scalars)``."""
+    import torch
+    from ._cabi import FF_NO_EXIT
+    from .head import max_displacement_px
+    n, (h, w), bits = len(video), video.frame_shape, video.storage_bits
+    fb = video.raw_frames(0, 1).size
+    track = np.full((b - a, 5), -1, dtype=np.int32)
+    flags = np.zeros(b - a, dtype=np.uint8)
+    pending = None
+    step = _head_chunk_frames(fb)
+    prev_dev, prev_hi = None, -1
+    for c0 in range(a, b, step):
+        if state[0] != FF_NO_EXIT:
+            break
+        c1 = min(b, c0 + step)
+        halo_idx = c0 - 1
+        if skip_np is not None:
+            while halo_idx >= 0 and skip_np[halo_idx]:
+                halo_idx -= 1
+        if halo_idx < 0:
+            halo_dev = None
+        elif prev_dev is not None and halo_idx == prev_hi - 1:
+            halo_dev = prev_dev[-fb:].clone()                    # last frame of the previous chunk, already here
+        else:
+            halo_dev = eng.upload(video.raw_frames(halo_idx, halo_idx + 1))
+        prev_dev = None                                          # release the previous chunk before the next upload
+        frames_dev = eng.upload(video.raw_frames(c0, c1))
+        skip_dev = None if skip_np is None else torch.from_numpy(skip_np[c0:c1].copy()).to(eng.device)
+        lines, flags_dev, pend = eng.head_lines(frames_dev, c1 - c0, h, w, bits, hp, frame0=frame0_dev,
+                                                first_frame=c0, halo=halo_dev, skip=skip_dev)
+        pending = pending or pend
+        track_dev, stop_dev = eng.head_track_lines(lines, flags_dev, c0, w, hp,
+                                                   max_displacement_px(video.frame_rate, calibration, hp),
+                                                   (state[1], state[2]))
+        track[c0 - a:c1 - a] = track_dev.cpu().numpy()
+        flags[c0 - a:c1 - a] = flags_dev.cpu().numpy()
+        state = tuple(int(v) for v in stop_dev.tolist())
+        prev_dev, prev_hi = frames_dev, c1
+        if stopped is not None and stopped(track[:c1 - a], flags[:c1 - a]):
+            break
+    return track, flags, state, pending
+
+
 def _process_video_head(video: PhotonVideo, config: VideoSourceConfig, calibration: float, offset: float,
                         eng, exchange=None) -> VideoResult:
     """HEAD-parity mode: the reference loop :1441-1516 with ``FlameDetector.detect`` on the GPU.
 
-    With an ``exchange`` over several ranks the clip is split into contiguous frame ranges like the
-    other methods: every rank uploads its range (+ one halo frame) and runs the image pipeline on it
-    (``engine.head_lines`` - all of the HBM and PCIe traffic); the search, sequential only through
-    (last frame, last position), runs range after range: a rank receives that 3-int state from its
-    predecessor, walks its range (``ff_head_track``, ~0.1 ms) and passes the state on; one
+    The recording goes through the device in bounded chunks (``_head_walk_range``), and nothing is
+    uploaded past the chunk in which the walk stops.  With an ``exchange`` over several ranks the clip
+    is split into contiguous frame ranges like the other methods: every rank runs the image pipeline on
+    its range (``engine.head_lines`` - all of the HBM and PCIe traffic); the search, sequential only
+    through (last frame, last position), runs range after range: a rank receives that 3-int state from
+    its predecessor, walks its range (``ff_head_track``, ~0.1 ms) and passes the state on; one
     all-gather of the int32 result rows finishes the clip.  Results are identical on every rank."""
     import torch
     import torch.distributed as dist
     from ._cabi import FF_NO_EXIT
-    from .head import max_displacement_px
 
     hp = config.head_params
     n, (h, w), bits = len(video), video.frame_shape, video.storage_bits
@@ -284,53 +342,46 @@ def _process_video_head(video: PhotonVideo, config: VideoSourceConfig, calibrati
         for s in config.skip_frames:
             if 0 <= s < n:
                 skip_np[s] = 1
+    time_of = video.get_absolute_time if config.use_absolute_time else video.get_time
+
+    def finish(track, flags):
+        return finish_head_track(track, flags, 0, w, video.frame_rate, calibration, offset, time_of, hp)
+
+    frame0 = eng.upload(video.raw_frames(0, 1))
+    start = (FF_NO_EXIT, -1, -1)
     multi = exchange is not None and exchange.size > 1
     if not multi:
-        frames_dev = eng.upload(video.raw_frames(0, n))
-        skip_dev = None if skip_np is None else torch.from_numpy(skip_np).to(eng.device)
-        res = eng.process_head(frames_dev, n, h, w, bits, hp, video.frame_rate, calibration, skip=skip_dev)
-        track, flags, scalars = res.track.cpu().numpy(), res.flags.cpu().numpy(), res.scalars
+        # the host-side stop rules (exit, velocity drop: :1486-1509) end the uploads as well
+        track, flags, _, pending = _head_walk_range(eng, video, hp, calibration, 0, n, skip_np, frame0, start,
+                                                    stopped=lambda t, f: finish(t, f).stop is not None)
     else:
         a, b = exchange.my_range(n)
         rank, size, group = exchange.rank, exchange.size, exchange.group
-        frame0 = eng.upload(video.raw_frames(0, 1))
-        state = torch.tensor([FF_NO_EXIT, -1, -1], dtype=torch.int32, device=eng.device)
-        cap = exchange.block_cap(n)
-        block = torch.full((cap, 6), -1, dtype=torch.int32, device=eng.device)   # 5 result columns + flag
-        block[:, 5] = 0
-        pending = None
-        if b > a:
-            halo_idx = a - 1
-            if skip_np is not None:
-                while halo_idx >= 0 and skip_np[halo_idx]:
-                    halo_idx -= 1
-            halo_dev = eng.upload(video.raw_frames(halo_idx, halo_idx + 1)) if halo_idx >= 0 else None
-            skip_dev = None if skip_np is None else torch.from_numpy(skip_np[a:b].copy()).to(eng.device)
-            lines, flags_dev, pending = eng.head_lines(eng.upload(video.raw_frames(a, b)), b - a, h, w, bits, hp,
-                                                       frame0=frame0, first_frame=a, halo=halo_dev, skip=skip_dev)
-            block[:b - a, 5] = flags_dev
-        else:
-            _, _, pending = eng.head_lines(frame0, 1, h, w, bits, hp)      # this rank only needs the clip scalars
+        peer = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+        state = torch.tensor(start, dtype=torch.int32, device=eng.device)
         if rank > 0:
-            dist.recv(state, src=dist.get_global_rank(group, rank - 1) if group is not None else rank - 1, group=group)
-        exit_before, last_f, last_p = (int(v) for v in state.tolist())
-        if b > a and exit_before == FF_NO_EXIT:      # the walk has not ended before this range
-            track_dev, state = eng.head_track_lines(lines, flags_dev, a, w, hp,
-                                                    max_displacement_px(video.frame_rate, calibration, hp),
-                                                    (last_f, last_p))
-            block[:b - a, :5] = track_dev
+            dist.recv(state, src=peer(rank - 1), group=group)
+        track, flags, after, pending = _head_walk_range(eng, video, hp, calibration, a, b, skip_np, frame0,
+                                                        tuple(int(v) for v in state.tolist()))
         if rank + 1 < size:
-            dist.send(state, dst=dist.get_global_rank(group, rank + 1) if group is not None else rank + 1, group=group)
+            dist.send(torch.tensor(after, dtype=torch.int32, device=eng.device), dst=peer(rank + 1), group=group)
+        cap = exchange.block_cap(n)
+        block = torch.full((cap, 6), -1, dtype=torch.int32, device=eng.device)      # 5 result columns + flag
+        block[:, 5] = 0
+        if b > a:
+            block[:b - a, :5] = torch.from_numpy(track).to(eng.device)
+            block[:b - a, 5] = torch.from_numpy(flags.astype(np.int32)).to(eng.device)
         gathered = torch.empty((size * cap, 6), dtype=torch.int32, device=eng.device)
         dist.all_gather_into_tensor(gathered, block, group=group)
         gathered = gathered.view(size, cap, 6).cpu().numpy()
         from .sharding import contiguous_range
-        parts = [gathered[r, :hi - lo] for r in range(size) for lo, hi in [contiguous_range(n, r, size)]]
-        rows_all = np.concatenate(parts)
+        rows_all = np.concatenate([gathered[r, :hi - lo] for r in range(size)
+                                   for lo, hi in [contiguous_range(n, r, size)]])
         track, flags = np.ascontiguousarray(rows_all[:, :5]), rows_all[:, 5].astype(np.uint8)
-        scalars = eng.head_scalars(pending)
-    time_of = video.get_absolute_time if config.use_absolute_time else video.get_time
-    summary = finish_head_track(track, flags, 0, w, video.frame_rate, calibration, offset, time_of, hp)
+        if pending is None:              # this rank uploaded nothing: it still reports the clip's scalars
+            _, _, pending = eng.head_lines(frame0, 1, h, w, bits, hp)
+    scalars = eng.head_scalars(pending)
+    summary = finish(track, flags)
     pos = np.full(n, -1, dtype=np.int32)
     for frame_idx, _, px, _, _ in summary.rows:
         pos[frame_idx] = px

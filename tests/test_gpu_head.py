@@ -105,9 +105,14 @@ def test_reference_golden_replay(engine, clip_small, golden):
     assert got.velocity_history == hr["velocity_history"] and list(got.stop) == hr["stop"]
 
 
-def test_driver_writes_the_reference_files_byte_for_byte(tmp_path, clip_small, golden):
+@pytest.mark.parametrize("chunk_mb", [None, "0"])
+def test_driver_writes_the_reference_files_byte_for_byte(tmp_path, clip_small, golden, monkeypatch, chunk_mb):
     """process_video_source(detection_method='head') on the same recordings the reference's own
-    driver processed (oracle/make_golden.py): every output file must be identical."""
+    driver processed (oracle/make_golden.py): every output file must be identical - with the clip
+    uploaded at once and (FF_HEAD_CHUNK_MB=0) in 2-frame chunks, tracker state and halo frame carried
+    from chunk to chunk and no upload past the exit."""
+    if chunk_mb is not None:
+        monkeypatch.setenv("FF_HEAD_CHUNK_MB", chunk_mb)
     vdir = tmp_path / "Nova-Video-Files"
     vdir.mkdir()
     for stem in ("run-3-", "run-5-_C001H001S0001"):
@@ -298,3 +303,33 @@ def test_fast_band_kernel_equals_general_kernel(engine, monkeypatch, h, w, bits,
     assert (fast[0] == 1).sum() > 8
     for a, b in zip(fast, general):
         assert np.array_equal(a, b)
+
+
+def test_chunked_head_walk_with_skip_frames_stops_uploading_at_the_exit(engine, tmp_path, monkeypatch):
+    """Chunk boundaries next to skip_frames entries (the halo is the latest non-skipped frame), and the
+    upload counter: frames after the chunk that holds the exit never reach the device."""
+    from high_speed_image_processing_b200.photron import open_video
+    from high_speed_image_processing_b200.process_videos import process_video
+    spec = syn.SyntheticSpec(width=256, height=16, n_frames=400, style="mini", t_enter=10.0, velocity=2.0, seed=31)
+    frames = syn.render_frames(spec)
+    syn.write_clip(tmp_path, "run-1-", spec, frames=frames)
+    cfg = VideoSourceConfig(name="t")
+    cfg.detection_method = "head"
+    cfg.skip_frames = [15, 16, 31, 32, 33, 64]
+    uploaded = []
+    real_upload = engine.upload
+    monkeypatch.setattr(engine, "upload", lambda host: (uploaded.append(np.asarray(host).size), real_upload(host))[1])
+    results = {}
+    for mb in ("2048", "0"):
+        monkeypatch.setenv("FF_HEAD_CHUNK_MB", mb)
+        del uploaded[:]
+        with open_video(str(tmp_path / "run-1-.cihx")) as video:
+            results[mb] = process_video(video, cfg, 0.000833333, 1.347567, engine=engine)
+        results[mb + "_bytes"] = sum(uploaded)
+    one, many = results["2048"], results["0"]
+    assert one.rows == many.rows and one.velocity_history == many.velocity_history and one.stop == many.stop
+    assert one.stop[0] == "exit" and len(one.rows) > 50 and np.array_equal(one.pos_px, many.pos_px)
+    assert one.empty_frames == many.empty_frames
+    fb = spec.frame_bytes
+    assert results["2048_bytes"] >= 400 * fb                       # one chunk: the whole clip
+    assert results["0_bytes"] < (one.stop[1] + 8) * fb * 1.6       # 2-frame chunks (+ halos): nothing past the exit
