@@ -149,3 +149,28 @@ def test_float_time_and_position_expressions():
     assert f"{fo.frame_time_absolute(39, 500, 1, 160000):.9f}" == "0.003368750"          # README.md:95
     assert f"{fo.position_m(6, 0.000833333, 1.347567):.9f}" == "1.352566998"
     assert math.isclose(fo.position_m(14, 0.000833333, 1.347567), 1.359233662, rel_tol=1e-9)
+
+
+# ---- velocity / DDT bookkeeping of the frame-level detector -----------------------------------------
+@settings(max_examples=120, deadline=None)
+@given(st.lists(st.tuples(st.integers(1, 4), st.one_of(st.none(), st.integers(0, 1023))), min_size=1, max_size=40),
+       st.sampled_from([0.0, 1000.0, 160000.0]), st.sampled_from([0.000833333, 0.002, 0.0]),
+       st.sampled_from([50.0, 1250.0]))
+def test_velocity_book_equals_the_oracle_update(steps, frame_rate, calibration, ddt_jump):
+    """head.VelocityBook (used by FlameDetector.detect and by the whole-clip HEAD path) against the
+    oracle's restatement of scripts/process_videos.py:474-516 on arbitrary detection sequences with
+    gaps, missing positions, zero frame rate / calibration."""
+    from high_speed_image_processing_b200.head import VelocityBook
+    from oracle import head_oracle as ho
+    cfg = ho.HeadConfig(ddt_velocity_jump_m_s=ddt_jump)
+    book = VelocityBook(frame_rate, calibration, ddt_jump)
+    history, vel, ddt = [], [], None
+    frame = 0
+    for gap, pos in steps:
+        frame += gap
+        book.update(frame, pos)
+        history.append((frame, pos))
+        ddt = ho.velocities_update(history, vel, frame, pos, frame_rate, calibration, cfg, ddt)
+        assert book.velocities == vel and book.ddt_frame == ddt and book.history == history
+    last = next(((f, p) for f, p in reversed(history) if p is not None), (-1, -1))
+    assert book.last_detection() == last
