@@ -1075,7 +1075,9 @@ int head_track_impl(const double* lines, const uint8_t* flags, int64_t n_frames,
   p.last_pos_in = last_pos_in;
   p.out = out;
   p.stop = stop;
-  if (getenv("FF_TRACK_SEQUENTIAL") == nullptr) {       // default: speculative parallel walk
+  // one segment's worth of frames (e.g. FlameDetector.detect: a single frame) gains nothing from
+  // speculation: one launch of the plain walk instead of four
+  if (getenv("FF_TRACK_SEQUENTIAL") == nullptr && n_frames > kSegFrames) {       // speculative parallel walk
     const int64_t n_seg = (n_frames + kSegFrames - 1) / kSegFrames;
     const unsigned seg_ctas = (unsigned)((n_seg + kSpecWarpsPerCta - 1) / kSpecWarpsPerCta);
     const bool chained = scratch != nullptr && getenv("FF_TRACK_UNCHAINED") == nullptr;
