@@ -702,8 +702,9 @@ __global__ void __launch_bounds__(kSpecWarpsPerCta * 32) head_track_fixup_kernel
   int my_final = flme != 0 ? __ldcg(p.out + (int64_t)fme * 5) : -1;      // the speculation's result
   int n_fixed = 0;
   // Segment 0 started from the true state; without a state before, the speculation IS the walk; and a
-  // guess that is itself an exit state means the walk has ended before this segment if the guess holds.
-  if (seg != 0 && cur.last_p >= 0 && cur.last_p < W - p.exit_margin) {
+  // guess that is an exit detection of THIS range means the walk has ended before this segment if the
+  // guess holds (a carried-in state stops nothing, whatever its position).
+  if (seg != 0 && cur.last_p >= 0 && (cur.last_p < W - p.exit_margin || cur.last_f < p.first_frame)) {
     const TrackState guess = cur;
     const int spec_final = my_final;
     TrackState spec;

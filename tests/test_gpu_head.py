@@ -244,6 +244,12 @@ def test_speculative_tracker_equals_sequential_walk(engine, monkeypatch, case):
     (t3, s3, _), (t4, s4, _) = _track_both_ways(engine, packed, n, h, w, hp, 160000, 0.000833333, monkeypatch,
                                                 tracker_state=(3, 17))
     assert np.array_equal(t3, t4) and np.array_equal(s3, s4)
+    # ... also one that lies in the exit zone (detected before this range: it must not end the walk)
+    fb = h * w * 3 // 2
+    (t5, s5, _), (t6, s6, _) = _track_both_ways(engine, packed[fb:], n - 1, h, w, hp, 160000, 0.000833333, monkeypatch,
+                                                frame0=packed[:fb], halo=packed[:fb], first_frame=1000,
+                                                tracker_state=(990, w - 2))
+    assert np.array_equal(t5, t6) and np.array_equal(s5, s6)
 
 
 def test_fullsize_c2_head_detector_vs_oracle_on_every_flame_frame(engine):
