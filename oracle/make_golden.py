@@ -330,6 +330,34 @@ def main() -> None:
     gold["driver_outputs"] = outs
     gold["driver_config"] = {"calibration": 0.001, "position_offset": 0.25}
 
+    # ---- the reference's driver on the other storage depths (16-bit little-endian, 8-bit) -----------
+    # The recordings are regenerated by the test from the same SyntheticSpec (sha1 of the frames kept
+    # here), so only the reference's output files are committed.
+    depth_runs = {}
+    for bits_d in (16, 8):
+        dspec = syn.SyntheticSpec(width=192, height=24, n_frames=90, bits=bits_d, style="mini", t_enter=6.0,
+                                  velocity=2.5, curvature_px=2.0, seed=500 + bits_d, record_rate=100000,
+                                  start_frame=0)
+        dframes = syn.render_frames(dspec)
+        ddir = work / f"depth{bits_d}" / "Mini-Video-Files"
+        syn.write_clip(ddir, f"run-2-_{bits_d}bit", dspec, frames=dframes)
+        dc = pv.VideoSourceConfig(name="Mini")
+        dc.enabled = True
+        dc.calibration = 0.000869565
+        dc.position_offset = 0.050237
+        dc.video_path = str(ddir)
+        dc.output_dir = str(work / f"depth{bits_d}" / "out")
+        with contextlib.redirect_stdout(io.StringIO()):
+            pv.process_video_source(dc, None)
+        files = {q.name: q.read_text() for q in sorted((work / f"depth{bits_d}" / "out").glob("*.txt"))}
+        assert files, f"{bits_d}-bit: the reference wrote no result file"
+        depth_runs[str(bits_d)] = {"spec": {k: getattr(dspec, k) for k in ("width", "height", "n_frames", "bits", "style",
+                                                                          "t_enter", "velocity", "curvature_px", "seed",
+                                                                          "record_rate", "start_frame")},
+                                   "frames_sha1": _sha(dframes), "stem": f"run-2-_{bits_d}bit",
+                                   "calibration": 0.000869565, "position_offset": 0.050237, "outputs": files}
+    gold["driver_other_depths"] = depth_runs
+
     # ---- FileCalibration / VideoSourceConfig ----------------------------------------------------
     rules = [
         pv.FileCalibration(calibration=0.000833333, position_offset=1.0159, files=["run-1-"]),

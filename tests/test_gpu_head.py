@@ -339,3 +339,27 @@ def test_chunked_head_walk_with_skip_frames_stops_uploading_at_the_exit(engine, 
     fb = spec.frame_bytes
     assert results["2048_bytes"] >= 400 * fb                       # one chunk: the whole clip
     assert results["0_bytes"] < (one.stop[1] + 8) * fb * 1.6       # 2-frame chunks (+ halos): nothing past the exit
+
+
+@pytest.mark.parametrize("bits", [16, 8])
+def test_driver_files_on_16bit_and_8bit_recordings_match_the_reference(tmp_path, golden, bits):
+    """The reference's own driver was run on 16-bit and 8-bit recordings (oracle/make_golden.py,
+    `driver_other_depths`); the recordings are regenerated here from the same spec (frame sha1
+    checked) and every result file must come out byte for byte."""
+    import hashlib
+    g = golden["driver_other_depths"][str(bits)]
+    spec = syn.SyntheticSpec(**g["spec"])
+    frames = syn.render_frames(spec)
+    assert hashlib.sha1(np.ascontiguousarray(frames).tobytes()).hexdigest() == g["frames_sha1"]
+    vdir = tmp_path / "Mini-Video-Files"
+    syn.write_clip(vdir, g["stem"], spec, frames=frames)
+    cfg = VideoSourceConfig(name="Mini")
+    cfg.enabled = True
+    cfg.detection_method = "head"
+    cfg.calibration = g["calibration"]
+    cfg.position_offset = g["position_offset"]
+    cfg.video_path = str(vdir)
+    cfg.output_dir = str(tmp_path / "out")
+    process_video_source(cfg, None, verbose=False)
+    produced = {p.name: p.read_text() for p in (tmp_path / "out").glob("*.txt")}
+    assert produced == g["outputs"]
