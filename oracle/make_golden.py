@@ -330,6 +330,25 @@ def main() -> None:
     gold["driver_outputs"] = outs
     gold["driver_config"] = {"calibration": 0.001, "position_offset": 0.25}
 
+    # ---- ... and with skip_frames (:1443-1445: skipped frames are not processed and do not become the
+    # prior frame), on the small recording ---------------------------------------------------------
+    sdir = work / "driver_skip" / "Nova-Video-Files"
+    syn.write_clip(sdir, "run-3-", spec, frames=frames)
+    scfg = pv.VideoSourceConfig(name="Nova")
+    scfg.enabled = True
+    scfg.calibration = 0.000833333
+    scfg.position_offset = 1.347567
+    scfg.skip_frames = [21, 22, 30, 41, 42, 43]
+    scfg.video_path = str(sdir)
+    scfg.output_dir = str(work / "driver_skip" / "out")
+    with contextlib.redirect_stdout(io.StringIO()):
+        pv.process_video_source(scfg, None)
+    gold["driver_outputs_skip"] = {"skip_frames": scfg.skip_frames,
+                                   "outputs": {q.name: q.read_text()
+                                               for q in sorted((work / "driver_skip" / "out").glob("*.txt"))}}
+    assert gold["driver_outputs_skip"]["outputs"] and \
+        gold["driver_outputs_skip"]["outputs"]["run-3--flame-position.txt"] != outs["run-3--flame-position.txt"]
+
     # ---- the reference's driver on the other storage depths (16-bit little-endian, 8-bit) -----------
     # The recordings are regenerated by the test from the same SyntheticSpec (sha1 of the frames kept
     # here), so only the reference's output files are committed.

@@ -363,3 +363,28 @@ def test_driver_files_on_16bit_and_8bit_recordings_match_the_reference(tmp_path,
     process_video_source(cfg, None, verbose=False)
     produced = {p.name: p.read_text() for p in (tmp_path / "out").glob("*.txt")}
     assert produced == g["outputs"]
+
+
+@pytest.mark.parametrize("chunk_mb", [None, "0"])
+def test_driver_files_with_skip_frames_match_the_reference(tmp_path, clip_small, golden, monkeypatch, chunk_mb):
+    """skip_frames in the reference's driver (:1443-1445): skipped frames neither reach the detector nor
+    become the prior frame.  Same recording, same list, byte-identical result files - also when the
+    clip goes through the device in 2-frame chunks (the halo must skip over them)."""
+    if chunk_mb is not None:
+        monkeypatch.setenv("FF_HEAD_CHUNK_MB", chunk_mb)
+    g = golden["driver_outputs_skip"]
+    vdir = tmp_path / "Nova-Video-Files"
+    vdir.mkdir()
+    (vdir / "run-3-.cihx").write_bytes(clip_small["cihx"])
+    (vdir / "run-3-.mraw").write_bytes(clip_small["packed"].tobytes())
+    cfg = VideoSourceConfig(name="Nova")
+    cfg.enabled = True
+    cfg.detection_method = "head"
+    cfg.calibration = 0.000833333
+    cfg.position_offset = 1.347567
+    cfg.skip_frames = list(g["skip_frames"])
+    cfg.video_path = str(vdir)
+    cfg.output_dir = str(tmp_path / "out")
+    process_video_source(cfg, None, verbose=False)
+    produced = {p.name: p.read_text() for p in (tmp_path / "out").glob("*.txt")}
+    assert produced == g["outputs"]
