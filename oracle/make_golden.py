@@ -349,6 +349,40 @@ def main() -> None:
     assert gold["driver_outputs_skip"]["outputs"] and \
         gold["driver_outputs_skip"]["outputs"]["run-3--flame-position.txt"] != outs["run-3--flame-position.txt"]
 
+    # ---- ... on recordings with a DDT event (velocity jump > 1250 m/s: pre-/post-DDT files, :506-516) and
+    # with a front that slows to under half its speed (the velocity-drop stop, :1499-1509).  A recording
+    # is two constant-velocity pieces of the synthetic generator spliced at a frame; the test rebuilds it.
+    def spliced(kind, va, vb, splice, n_frames_e):
+        base = dict(width=256, height=16, bits=12, style="mini", curvature_px=1.0, seed=700, record_rate=160000,
+                    start_frame=0, n_frames=n_frames_e)
+        sa = syn.SyntheticSpec(t_enter=5.0, velocity=va, **base)
+        xb = sa.front_position(float(splice))
+        sb = syn.SyntheticSpec(t_enter=splice - xb / vb, velocity=vb, **base)
+        fr = np.concatenate([syn.render_frames(sa, 0, splice), syn.render_frames(sb, splice, n_frames_e)])
+        edir = work / f"event_{kind}" / "Nova-Video-Files"
+        syn.write_clip(edir, "run-3-", sa, frames=fr)
+        ec = pv.VideoSourceConfig(name="Nova")
+        ec.enabled = True
+        ec.calibration = 0.000833333
+        ec.position_offset = 1.347567
+        ec.video_path = str(edir)
+        ec.output_dir = str(work / f"event_{kind}" / "out")
+        log = io.StringIO()
+        with contextlib.redirect_stdout(log):
+            pv.process_video_source(ec, None)
+        files = {q.name: q.read_text() for q in sorted((work / f"event_{kind}" / "out").glob("*.txt"))}
+        spec_keys = ("width", "height", "n_frames", "bits", "style", "t_enter", "velocity", "curvature_px", "seed",
+                     "record_rate", "start_frame")
+        return {"spec_a": {k: getattr(sa, k) for k in spec_keys}, "spec_b": {k: getattr(sb, k) for k in spec_keys},
+                "splice": splice, "frames_sha1": _sha(fr), "outputs": files,
+                "log_mentions": [w for w in ("DDT", "velocity", "exited") if w.lower() in log.getvalue().lower()]}
+    events = {"ddt": spliced("ddt", 2.0, 20.0, 40, 70), "velocity_drop": spliced("velocity_drop", 10.0, 1.0, 20, 70)}
+    assert any("post-DDT" in k for k in events["ddt"]["outputs"]), list(events["ddt"]["outputs"])
+    vd_rows = [ln for ln in events["velocity_drop"]["outputs"]["run-3--flame-position.txt"].splitlines()
+               if ln and not ln.startswith("#")]
+    assert int(vd_rows[-1].split()[0]) < 30, "the velocity-drop recording must stop at the deceleration"
+    gold["driver_events"] = events
+
     # ---- the reference's driver on the other storage depths (16-bit little-endian, 8-bit) -----------
     # The recordings are regenerated by the test from the same SyntheticSpec (sha1 of the frames kept
     # here), so only the reference's output files are committed.

@@ -388,3 +388,32 @@ def test_driver_files_with_skip_frames_match_the_reference(tmp_path, clip_small,
     process_video_source(cfg, None, verbose=False)
     produced = {p.name: p.read_text() for p in (tmp_path / "out").glob("*.txt")}
     assert produced == g["outputs"]
+
+
+@pytest.mark.parametrize("event", ["ddt", "velocity_drop"])
+def test_driver_files_on_ddt_and_velocity_drop_recordings_match_the_reference(tmp_path, golden, event):
+    """Recordings on which the reference's driver saw a DDT event (velocity jump > 1250 m/s: pre- and
+    post-DDT files, :506-516) and a front slowing to under half its speed (the velocity-drop stop,
+    :1499-1509): two constant-velocity pieces of the synthetic generator spliced at a frame, rebuilt
+    here (frame sha1 checked); every result file byte for byte."""
+    import hashlib
+    g = golden["driver_events"][event]
+    sa, sb = syn.SyntheticSpec(**g["spec_a"]), syn.SyntheticSpec(**g["spec_b"])
+    frames = np.concatenate([syn.render_frames(sa, 0, g["splice"]), syn.render_frames(sb, g["splice"], sa.n_frames)])
+    assert hashlib.sha1(np.ascontiguousarray(frames).tobytes()).hexdigest() == g["frames_sha1"]
+    vdir = tmp_path / "Nova-Video-Files"
+    syn.write_clip(vdir, "run-3-", sa, frames=frames)
+    cfg = VideoSourceConfig(name="Nova")
+    cfg.enabled = True
+    cfg.detection_method = "head"
+    cfg.calibration = 0.000833333
+    cfg.position_offset = 1.347567
+    cfg.video_path = str(vdir)
+    cfg.output_dir = str(tmp_path / "out")
+    res = process_video_source(cfg, None, verbose=False)["run-3-.cihx"]
+    produced = {p.name: p.read_text() for p in (tmp_path / "out").glob("*.txt")}
+    assert produced == g["outputs"]
+    if event == "ddt":
+        assert res.ddt_frame is not None and any("post-DDT" in k for k in produced) and res.stop[0] == "exit"
+    else:
+        assert res.stop[0] == "velocity_drop" and res.first_exit is None
