@@ -349,6 +349,23 @@ def main() -> None:
     assert gold["driver_outputs_skip"]["outputs"] and \
         gold["driver_outputs_skip"]["outputs"]["run-3--flame-position.txt"] != outs["run-3--flame-position.txt"]
 
+    # ---- ... with trigger-relative time (use_absolute_time = False, trigger_frame set: :1449-1452) --------
+    tdir = work / "driver_trigger" / "Nova-Video-Files"
+    syn.write_clip(tdir, "run-3-", spec, frames=frames)
+    tcfg = pv.VideoSourceConfig(name="Nova")
+    tcfg.enabled = True
+    tcfg.calibration = 0.000833333
+    tcfg.position_offset = 1.347567
+    tcfg.use_absolute_time = False
+    tcfg.trigger_frame = 12
+    tcfg.video_path = str(tdir)
+    tcfg.output_dir = str(work / "driver_trigger" / "out")
+    with contextlib.redirect_stdout(io.StringIO()):
+        pv.process_video_source(tcfg, None)
+    gold["driver_outputs_trigger"] = {"trigger_frame": 12, "outputs": {
+        q.name: q.read_text() for q in sorted((work / "driver_trigger" / "out").glob("*.txt"))}}
+    assert gold["driver_outputs_trigger"]["outputs"]["run-3--flame-position.txt"] != outs["run-3--flame-position.txt"]
+
     # ---- ... on recordings with a DDT event (velocity jump > 1250 m/s: pre-/post-DDT files, :506-516) and
     # with a front that slows to under half its speed (the velocity-drop stop, :1499-1509).  A recording
     # is two constant-velocity pieces of the synthetic generator spliced at a frame; the test rebuilds it.

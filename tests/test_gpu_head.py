@@ -417,3 +417,25 @@ def test_driver_files_on_ddt_and_velocity_drop_recordings_match_the_reference(tm
         assert res.ddt_frame is not None and any("post-DDT" in k for k in produced) and res.stop[0] == "exit"
     else:
         assert res.stop[0] == "velocity_drop" and res.first_exit is None
+
+
+def test_driver_files_with_trigger_relative_time_match_the_reference(tmp_path, clip_small, golden):
+    """use_absolute_time = False with a trigger frame (:1449-1452): the Time_s column is
+    (frame - trigger) / rate, negative before the trigger."""
+    g = golden["driver_outputs_trigger"]
+    vdir = tmp_path / "Nova-Video-Files"
+    vdir.mkdir()
+    (vdir / "run-3-.cihx").write_bytes(clip_small["cihx"])
+    (vdir / "run-3-.mraw").write_bytes(clip_small["packed"].tobytes())
+    cfg = VideoSourceConfig(name="Nova")
+    cfg.enabled = True
+    cfg.detection_method = "head"
+    cfg.calibration = 0.000833333
+    cfg.position_offset = 1.347567
+    cfg.use_absolute_time = False
+    cfg.trigger_frame = g["trigger_frame"]
+    cfg.video_path = str(vdir)
+    cfg.output_dir = str(tmp_path / "out")
+    process_video_source(cfg, None, verbose=False)
+    produced = {p.name: p.read_text() for p in (tmp_path / "out").glob("*.txt")}
+    assert produced == g["outputs"]
