@@ -14,7 +14,7 @@
 // head_track_*      - the sequential part (:317-348, :420-465): velocity-constrained search
 //     window from the last detected position, arg-min gradient / rightmost Sobel, max of the
 //     candidates, stop at the exit frame (:1488-1494) - run as a speculative parallel walk
-//     (full-width answers for every frame, 32-frame segments walked at once, validated in
+//     (full-width answers for every frame, 16-frame segments walked at once, validated in
 //     order); head_track_generic_kernel is the plain sequential walk kept as its cross-check.
 #include <climits>
 #include <cstdlib>
@@ -489,10 +489,11 @@ __global__ void __launch_bounds__(kHeadThreads) head_track_generic_kernel(const 
 // does, validation simply degrades into the sequential walk.  Results are bit-identical to the
 // sequential kernel either way (tests run both).  Lines are read straight from global memory
 // (they sit in L2 after head_band_kernel).
-constexpr int kSegFrames = 32;               // frames per segment = lanes of the validating warp
+constexpr int kSegFrames = 16;               // frames per segment (<= 32: one lane per frame); a speculative
+                                             // walk is a latency chain of this many frames
 constexpr int kSpecWarpsPerCta = 8;
 constexpr int kSegInts = 8;                  // int32 per segment in the chained-speculation scratch
-constexpr int kMaxRepair = 16;               // frames a segment re-runs from its guess before it gives up
+constexpr int kMaxRepair = 8;                // frames a segment re-runs from its guess before it gives up
 
 struct TrackState { int last_f, last_p; };
 struct FrameResult { int final_pos, pos_a, pos_b, s0, s1; };
@@ -620,7 +621,7 @@ __global__ void __launch_bounds__(kSpecWarpsPerCta * 32) head_track_spec_kernel(
   if (f_lo >= p.n_frames) return;
   const unsigned fullmask = 0xFFFFFFFFu;
   const int fme = f_lo + lane;
-  const int flme = fme < p.n_frames ? (int)p.flags[fme] : 0;
+  const int flme = (lane < kSegFrames && fme < p.n_frames) ? (int)p.flags[fme] : 0;
   unsigned act = __ballot_sync(fullmask, flme != 0);
   TrackState st;
   st.last_f = seg == 0 ? p.last_frame_in : -1;
@@ -679,7 +680,7 @@ __global__ void __launch_bounds__(kSpecWarpsPerCta * 32) head_track_fixup_kernel
   const unsigned fullmask = 0xFFFFFFFFu;
   const int W = p.width;
   const int fme = f_lo + lane;
-  const int flme = fme < p.n_frames ? (int)p.flags[fme] : 0;
+  const int flme = (lane < kSegFrames && fme < p.n_frames) ? (int)p.flags[fme] : 0;
   const unsigned act_all = __ballot_sync(fullmask, flme != 0);
   if (!act_all) return;
   int32_t* e = p.seg + (int64_t)seg * kSegInts;
@@ -777,17 +778,22 @@ __device__ WalkEnd commit_walk(const HeadTrackParams& p, int seg_begin, TrackSta
   const bool vec_flags = (reinterpret_cast<uintptr_t>(p.flags) & 15u) == 0;
   for (int seg0 = seg_begin & ~31; seg0 < n_seg && exit_f == p.n_frames; seg0 += 32) {
     // lane L summarises segment seg0 + L: bit j of m_act = frame j reached the detector, bit j of
-    // m_one = it has a difference image (flag 1).  One round of loads per 1024 frames keeps the
+    // m_one = it has a difference image (flag 1).  One round of loads per 32 segments keeps the
     // long empty stretches of a clip off the sequential path.
     unsigned m_act = 0, m_one = 0;
     if (seg0 + lane >= seg_begin) {
       const int fs = (seg0 + lane) * kSegFrames;
       if (vec_flags && fs + kSegFrames <= p.n_frames) {
+        static_assert(kSegFrames == 16 || kSegFrames == 32, "flag masks are read as one or two 16-byte pieces");
+        uint32_t w8[8] = {};
         const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(p.flags + fs));
-        const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(p.flags + fs) + 1);
-        const uint32_t w8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        w8[0] = v0.x; w8[1] = v0.y; w8[2] = v0.z; w8[3] = v0.w;
+        if (kSegFrames == 32) {
+          const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(p.flags + fs) + 1);
+          w8[4] = v1.x; w8[5] = v1.y; w8[6] = v1.z; w8[7] = v1.w;
+        }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < kSegFrames; ++j) {
           const uint32_t fl = (w8[j >> 2] >> (8 * (j & 3))) & 0xFFu;
           if (fl != 0) m_act |= 1u << j;
           if (fl == 1) m_one |= 1u << j;
@@ -930,7 +936,7 @@ __global__ void __launch_bounds__(256) head_track_resolve_kernel(const HeadTrack
       const int n_fixed = p.seg[(int64_t)sg * kSegInts + 4];
       if (n_fixed == 0) continue;
       const int fme = sg * kSegFrames + lane;
-      const int flme = fme < p.n_frames ? (int)p.flags[fme] : 0;
+      const int flme = (lane < kSegFrames && fme < p.n_frames) ? (int)p.flags[fme] : 0;
       const unsigned act = __ballot_sync(fullmask, flme != 0);
       if (flme != 0 && __popc(act & ((1u << lane) - 1u)) < n_fixed) {
 #pragma unroll

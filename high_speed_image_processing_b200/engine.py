@@ -579,7 +579,7 @@ class FlameFrontEngine:
                 float(params.sobel_threshold_fraction), params.exit_margin_px, int(tracker_state[0]),
                 int(tracker_state[1]), track.data_ptr(), stop.data_ptr(), self._track_scratch(n).data_ptr(),
                 self._stream()), "ff_head_track")
-        self.launches += 4 if n > 32 else 1      # full-width, speculative walk, fix-up, resolve | one plain walk
+        self.launches += 4 if n > 16 else 1      # full-width, speculative walk, fix-up, resolve | one plain walk
         return track, stop
 
     def _track_scratch(self, n_frames: int) -> torch.Tensor:

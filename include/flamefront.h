@@ -207,7 +207,7 @@ int ff_exchange_destroy(ff_exchange* x);
  *   stop_dev  int32[3]: exit frame (global index) or FF_NO_EXIT, last detection frame, last position
  *   scratch_dev  int32[ff_head_track_scratch_len(n_frames)] or NULL.  The walk over the frames is
  *             sequential only through (last frame, last position); it runs as speculative walks of
- *             32-frame segments.  With scratch the segments' start states are chained and checked in
+ *             16-frame segments.  With scratch the segments' start states are chained and checked in
  *             parallel; without it one warp validates the segments one after the other.  Same results. */
 int ff_head_lines(const void* frames_dev, const void* halo_dev, int64_t n_frames, int height, int width,
                   int bits, const int32_t* bg_dev, const int32_t* partial_dev, int64_t min_signal_count,
