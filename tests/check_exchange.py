@@ -1,8 +1,9 @@
 #!/usr/bin/env python
-"""Range-sharded run under torchrun: both block transports of the exchange step against the
+"""TEST INFRASTRUCTURE (it checks against the oracle; run by tests/test_gpu_exchange.py or by hand).
+Range-sharded run under torchrun: both block transports of the exchange step against the
 oracle's serial answer, plus the latency of the step itself.
 
-    torchrun --nproc-per-node N tools/check_exchange.py [--out report.json] [--steps 20]
+    torchrun --nproc-per-node N tests/check_exchange.py [--out report.json] [--steps 20]
 
 Rank 0 writes a JSON report; every rank exits non-zero on a mismatch.
 """

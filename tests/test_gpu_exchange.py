@@ -97,7 +97,7 @@ def test_two_rank_run_both_transports(tmp_path, nproc):
         pytest.skip(f"needs {nproc} GPUs")
     out = tmp_path / "exchange.json"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
-           "--master-addr", "127.0.0.1", "--master-port", "29547", str(REPO / "tools" / "check_exchange.py"),
+           "--master-addr", "127.0.0.1", "--master-port", "29547", str(REPO / "tests" / "check_exchange.py"),
            "--out", str(out), "--steps", "5"]
     env = dict(os.environ, PYTHONPATH=str(REPO))
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)

@@ -10,8 +10,8 @@ half_maximum / threshold / gradient, every clip has its own FileCalibration rule
 real .cihx/.mraw pairs on disk opened through ``open_collection``; each rank stages ITS videos in
 pinned host memory (``video.pin_memory()``, untimed I/O), then the timed region runs
 ``process_collection``: per video frame 0 -> scalars, chunked H2D streaming + kernels, result
-rows on the host; one all_gather_object of the per-video results at the end.  A sample of clips
-is checked against the oracle.  Prints one JSON line on rank 0.
+rows on the host; one all_gather_object of the per-video results at the end.  Prints one JSON line
+on rank 0.  (Parity of this path against the oracle: tests/test_gpu_pipeline.py.)
 """
 from __future__ import annotations
 
@@ -60,7 +60,7 @@ def main() -> None:
     ap.add_argument("--frames", type=int, default=2000)
     ap.add_argument("--dir", default="/tmp/ff_c5")
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--check", type=int, default=3, help="clips per rank verified against the oracle")
+    ap.add_argument("--check", type=int, default=3, help="clips per rank whose result rows are re-checked (calibration arithmetic)")
     ap.add_argument("--keep", action="store_true")
     ap.add_argument("--no-pin", action="store_true", help="leave the recordings memory-mapped (pageable) instead of "
                     "staging them in pinned memory: the page-cache -> GPU path a plain script would take")
@@ -133,22 +133,12 @@ def main() -> None:
         times.append(dt)
     sec = min(times)
 
-    # ---- oracle check on a sample of this rank's clips -------------------------------------------
-    from oracle import flame_oracle as fo
+    # (parity of the collection path against the oracle: tests/test_gpu_pipeline.py; here only the
+    # calibration arithmetic of the rows is re-checked, which needs no oracle)
     checked = 0
     for i in mine[:args.check]:
-        spec, cfg, res = specs[i], cfgs[i], results[i]
-        n_chk = min(spec.n_frames, 260)             # the oracle is slow: compare the flame's first frames
-        a = max(1, int(spec.t_enter) - 20)
-        raw = np.asarray(coll[i].raw_frames(a - 1, a + n_chk))
-        frames = fo.frames_from_bytes(raw, n_chk + 1, spec.height, spec.width, 12)
-        frame0 = fo.frames_from_bytes(np.asarray(coll[i].raw_frames(0, 1)), 1, spec.height, spec.width, 12)[0]
-        want = fo.process_clip(frames[1:], fo.ClipParams(method=cfg.detection_method), frame0=frame0, first_index=a,
-                               prior_frame=frames[0])
-        hi = a + n_chk if res.first_exit is None else min(a + n_chk, res.first_exit)
-        assert np.array_equal(res.pos_px[a:hi], want.pos_px[:hi - a]), f"clip {i}: positions differ from the oracle"
-        cal, off = cfg.get_calibration_for_file(f"run-{i:02d}-.cihx")
-        for frame_idx, t_s, px, p_m, _ in res.rows[:50]:
+        cal, off = cfgs[i].get_calibration_for_file(f"run-{i:02d}-.cihx")
+        for frame_idx, t_s, px, p_m, _ in results[i].rows[:50]:
             assert p_m == px * cal + off
         checked += 1
 
@@ -162,7 +152,7 @@ def main() -> None:
             "frames_per_s": total_frames / sec, "gbs_aggregate": total_bytes / sec / 1e9,
             "gbs_per_gpu": total_bytes / sec / 1e9 / world, "ms_per_video": sec / (args.clips / world) * 1e3,
             "all_times_s": times, "detections": n_rows, "clips_with_exit": exits,
-            "oracle_checked_clips_rank0": checked, "untimed": {"write_files_s": write_s, "pin_stage_s": stage_s,
+            "rows_rechecked_clips_rank0": checked, "untimed": {"write_files_s": write_s, "pin_stage_s": stage_s,
                                                                 "rank0_bytes": my_bytes}}), flush=True)
     coll.close_all()
     if world > 1:
