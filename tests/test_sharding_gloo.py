@@ -210,6 +210,8 @@ class _OracleHeadEngine:
         lines = torch.zeros((n, 2, w), dtype=torch.float64)
         flags = torch.zeros(n, dtype=torch.uint8)
         for i in range(n):
+            if skip is not None and int(skip[i]):      # :1443-1445: neither processed nor kept as the prior frame
+                continue
             sub = fo.subtract_scalar_background(dec[i], bg)
             if not fo.is_empty_frame(sub, fo.empty_noise_threshold(bg), hp.min_signal_fraction):
                 if prior is None:
