@@ -34,7 +34,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-from ._cabi import FF_NO_EXIT, FF_POS_DROPPED
+from ._cabi import FF_NO_EXIT
 
 BLOCK_HEADER = 4        # int32 words in front of a range block's arrays (csrc/ff_exchange.cu: kHdr)
 
