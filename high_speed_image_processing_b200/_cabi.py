@@ -26,7 +26,8 @@ FF_POS_NONE = -1
 FF_POS_DROPPED = -2
 FF_NO_EXIT = 2147483647
 FF_PX_U8, FF_PX_U16, FF_PX_F64 = 0, 1, 3
-FF_ABI_VERSION = 5
+FF_HOOK_WAIT, FF_HOOK_PUBLISH = 1, 2
+FF_ABI_VERSION = 6
 
 
 class FlameFrontLibraryError(RuntimeError):
@@ -44,6 +45,43 @@ class FlameFrontError(RuntimeError):
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
 _int = C.c_int
 
+
+class RangeHooks(C.Structure):
+    """``ff_range_hooks``: ties one rank's range to its peers (filled by ``ff_exchange_begin``)."""
+    _fields_ = [("table_dev", _vp), ("epoch", _i32), ("world", _i32), ("rank", _i32), ("flags", _i32),
+                ("spin_limit", _i64), ("exit_word_dev", _vp)]
+
+
+class RangeArgs(C.Structure):
+    """``ff_range_args`` of ``ff_process_range``."""
+    _fields_ = [("frames_dev", _vp), ("halo_dev", _vp), ("frame0_dev", _vp),
+                ("n_frames", _i64), ("first_frame", _i64),
+                ("height", _i32), ("width", _i32), ("bits", _i32),
+                ("method", _i32), ("use_frame_diff", _i32), ("min_run_px", _i32), ("exit_margin_px", _i32),
+                ("diff_thr", _i32), ("grad2_bound", _i32), ("empty_thr", _i32), ("threshold_floor", _i32),
+                ("min_signal_count", _i64),
+                ("skip_dev", _vp), ("scalars_dev", _vp), ("centerline_dev", _vp),
+                ("pos_out_dev", _vp), ("count_out_dev", _vp), ("first_exit_dev", _vp),
+                ("init_first_exit", _i32), ("truncate", _i32),
+                ("diff_out_dev", _vp), ("diff_dtype", _i32), ("reserved", _i32),
+                ("decoded_out_dev", _vp), ("profile_out_dev", _vp), ("partial_dev", _vp),
+                ("workspace_dev", _vp), ("hooks", C.POINTER(RangeHooks))]
+
+
+class HostArgs(C.Structure):
+    """``ff_host_args`` of ``ff_process_host_range``."""
+    _fields_ = [("frames_host", _vp), ("halo_host", _vp), ("n_frames", _i64), ("first_frame", _i64),
+                ("height", _i32), ("width", _i32), ("bits", _i32), ("bg", _i32), ("empty_thr", _i32),
+                ("method", _i32), ("use_frame_diff", _i32), ("diff_thr", _i32), ("threshold_floor", _i32),
+                ("grad2_bound", _i32), ("min_run_px", _i32), ("exit_margin_px", _i32),
+                ("min_signal_count", _i64), ("skip_host", _vp),
+                ("pos_out_host", _vp), ("count_out_host", _vp),
+                ("pos_block_dev", _vp), ("count_block_dev", _vp), ("first_exit_block_dev", _vp),
+                ("hooks", C.POINTER(RangeHooks)),
+                ("frames_done_out", C.POINTER(_i64)), ("first_exit_out", C.POINTER(_i32)),
+                ("bytes_uploaded_out", C.POINTER(_i64))]
+
+
 # name -> (restype, argtypes); must list every function declared in include/flamefront.h
 SIGNATURES = {
     "ff_abi_version": (_int, []),
@@ -58,13 +96,18 @@ SIGNATURES = {
     "ff_detect": (_int, [_vp, _vp, _i64, _i64, _int, _int, _int, _vp, _vp, _i64, _int, _int, _i32, _i32, _i32,
                          _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ff_truncate": (_int, [_vp, _i64, _i64, _vp, _vp]),
+    "ff_process_range_plan": (_int, [_i64, _int, _int, _int, _int, _int, _int, C.POINTER(_i64), C.POINTER(_i64),
+                                     C.POINTER(_int)]),
+    "ff_process_range": (_int, [C.POINTER(RangeArgs), _vp]),
     "ff_range_block_len": (_int, [_i64, C.POINTER(_i64)]),
     "ff_merge_ranges": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp, _vp]),
     "ff_exchange_create": (_int, [_int, _int, _int, _i64, C.POINTER(_vp)]),
     "ff_exchange_handle_bytes": (_int, []),
     "ff_exchange_get_handle": (_int, [_vp, _vp]),
     "ff_exchange_open_peers": (_int, [_vp, _vp]),
-    "ff_exchange_begin": (_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp]),
+    "ff_exchange_begin": (_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(RangeHooks)]),
+    "ff_exchange_acquire": (_int, [_vp, _vp]),
+    "ff_exchange_publish": (_int, [_vp, _vp]),
     "ff_exchange_finish": (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "ff_exchange_status": (_int, [_vp, C.POINTER(_i32), _vp]),
     "ff_exchange_destroy": (_int, [_vp]),
@@ -81,9 +124,11 @@ SIGNATURES = {
                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ff_host_ctx_create": (_int, [_int, _i64, C.POINTER(_vp)]),
     "ff_host_ctx_destroy": (_int, [_vp]),
+    "ff_host_ctx_set_copy_threads": (_int, [_vp, _int]),
     "ff_host_upload": (_int, [_vp, _vp, _vp, _i64]),
     "ff_process_host": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _int, _int, _i32, _i32, _i64, _int, _int, _i32,
                                _i32, _i32, _i32, _i32, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_i32)]),
+    "ff_process_host_range": (_int, [_vp, C.POINTER(HostArgs)]),
 }
 
 _lib: Optional[C.CDLL] = None

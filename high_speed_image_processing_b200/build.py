@@ -17,9 +17,10 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_DIR = PKG_DIR / "lib"
 LIB_PATH = LIB_DIR / "libflamefront.so"
-SOURCES = ["ff_stream.cu", "ff_detect.cu", "ff_head.cu", "ff_frameops.cu", "ff_exchange.cu", "ff_api.cu",
+SOURCES = ["ff_stream.cu", "ff_detect.cu", "ff_range.cu", "ff_head.cu", "ff_frameops.cu", "ff_exchange.cu", "ff_api.cu",
            "ff_hostcopy.cpp"]       # .cpp: host-only, handed to g++ by nvcc
-HEADERS = [CSRC / "ff_common.cuh", PKG_DIR.parent / "include" / "flamefront.h"]
+HEADERS = [CSRC / "ff_common.cuh", CSRC / "ff_detect_core.cuh", CSRC / "ff_internal.h",
+           PKG_DIR.parent / "include" / "flamefront.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

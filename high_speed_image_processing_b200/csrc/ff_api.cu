@@ -1,16 +1,18 @@
 // C-ABI entry points of libflamefront.so (declared in include/flamefront.h) and the
 // host-resident streaming driver (ff_process_host).
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <thread>
 #include <vector>
 
-#include "ff_common.cuh"
+#include "ff_internal.h"
 
 namespace ff {
 
@@ -20,14 +22,6 @@ void set_cuda_error(cudaError_t e, const char* where) {
   std::snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
 
-int stream_frames_impl(const void*, const void*, int64_t, int, int, int, const int32_t*, int32_t, int32_t,
-                       const uint8_t*, int32_t*, void*, int, uint16_t*, cudaStream_t);
-int unpack_impl(const void*, void*, int64_t, int, int, int, cudaStream_t);
-int detect_impl(const void*, const void*, int64_t, int64_t, int, int, int, const int32_t*, const int32_t*, int64_t,
-                int, int, int32_t, int32_t, int32_t, int32_t, int32_t, const uint8_t*, int32_t*, int32_t*, int32_t*,
-                int32_t*, cudaStream_t);
-int background_impl(const void*, int, int, int, int32_t*, uint16_t*, cudaStream_t);
-int truncate_impl(int32_t*, int64_t, int64_t, const int32_t*, cudaStream_t);
 int head_lines_impl(const void*, const void*, int64_t, int, int, int, const int32_t*, const int32_t*, int64_t, int32_t,
                     const double*, int, const uint8_t*, double*, uint8_t*, int32_t*, cudaStream_t);
 int head_track_impl(const double*, const uint8_t*, int64_t, int64_t, int, int32_t, int32_t, int32_t, double, double,
@@ -66,60 +60,67 @@ class CopyPool {
   }
   // Blocking: returns when dst[0, bytes) is filled.  The caller takes part in the copy.
   void copy(uint8_t* dst, const uint8_t* src, size_t bytes) {
-    const size_t part = 2u << 20;
+    // Every job carries its own counters: a worker that wakes up late for job N still holds job N
+    // (whose parts are all taken) and can neither copy a part of job N+1 nor count towards it.
+    auto job = std::make_shared<Job>();
+    job->dst = dst;
+    job->src = src;
+    job->bytes = bytes;
+    job->part = 2u << 20;
+    job->n_parts = (bytes + job->part - 1) / job->part;
     {
       std::lock_guard<std::mutex> g(m_);
-      dst_ = dst;
-      src_ = src;
-      bytes_ = bytes;
-      part_ = part;
-      n_parts_ = (bytes + part - 1) / part;
-      next_.store(0);
-      done_ = 0;
+      current_ = job;
       ++gen_;
     }
     cv_job_.notify_all();
-    work();
+    work(*job);
     std::unique_lock<std::mutex> lk(m_);
-    cv_done_.wait(lk, [this] { return done_ == n_parts_; });
+    cv_done_.wait(lk, [&] { return job->done >= job->n_parts; });
   }
 
  private:
-  void work() {
+  struct Job {
+    uint8_t* dst = nullptr;
+    const uint8_t* src = nullptr;
+    size_t bytes = 0, part = 0, n_parts = 0;
+    std::atomic<size_t> next{0};
+    size_t done = 0;          // guarded by m_
+  };
+  void work(Job& j) {
     size_t mine = 0;
     for (;;) {
-      const size_t i = next_.fetch_add(1);
-      if (i >= n_parts_) break;
-      const size_t a = i * part_;
-      const size_t n = a + part_ <= bytes_ ? part_ : bytes_ - a;
-      stream_copy(dst_ + a, src_ + a, n);
+      const size_t i = j.next.fetch_add(1);
+      if (i >= j.n_parts) break;
+      const size_t a = i * j.part;
+      const size_t n = a + j.part <= j.bytes ? j.part : j.bytes - a;
+      stream_copy(j.dst + a, j.src + a, n);
       ++mine;
     }
     if (mine) {
       std::lock_guard<std::mutex> g(m_);
-      done_ += mine;
-      if (done_ == n_parts_) cv_done_.notify_all();
+      j.done += mine;
+      if (j.done >= j.n_parts) cv_done_.notify_all();
     }
   }
   void loop() {
     uint64_t seen = 0;
     for (;;) {
+      std::shared_ptr<Job> job;
       {
         std::unique_lock<std::mutex> lk(m_);
         cv_job_.wait(lk, [&] { return stop_ || gen_ != seen; });
         if (stop_) return;
         seen = gen_;
+        job = current_;
       }
-      work();
+      work(*job);
     }
   }
   std::vector<std::thread> workers_;
   std::mutex m_;
   std::condition_variable cv_job_, cv_done_;
-  uint8_t* dst_ = nullptr;
-  const uint8_t* src_ = nullptr;
-  size_t bytes_ = 0, part_ = 0, n_parts_ = 0, done_ = 0;
-  std::atomic<size_t> next_{0};
+  std::shared_ptr<Job> current_;
   uint64_t gen_ = 0;
   bool stop_ = false;
 };
@@ -140,8 +141,12 @@ struct ff_host_ctx {
   int32_t* cnt_dev = nullptr;
   uint8_t* skip_dev = nullptr;
   int64_t frames_cap = 0;
-  int32_t* scalars_dev = nullptr;   // [0] bg, [1] first_exit
-  int32_t* scalars_host = nullptr;  // pinned: [0] bg, [1] init value, [2..3] per-buffer first_exit readback
+  int32_t* scalars_dev = nullptr;   // int32[32]: [0..15] clip-scalar block ([0] bg), [16] first_exit
+  int32_t* scalars_host = nullptr;  // pinned: [0] bg, [1] final first_exit, [2..3] per-buffer first_exit readback,
+                                    // [4..5] per-buffer readback of the clip-global exit word (range-sharded runs)
+  void* ws = nullptr;               // ff_process_range workspace for one chunk (kept zero-filled)
+  int64_t ws_bytes = 0;
+  int copy_threads = -1;            // -1: FF_HOST_COPY_THREADS or half the cores
   // pageable sources only
   uint8_t* bounce[2] = {nullptr, nullptr};     // pinned, same layout as stage[]
   int64_t bounce_bytes = 0;
@@ -164,6 +169,7 @@ static int ctx_release(ff_host_ctx* c) {
   if (c->cnt_dev) cudaFree(c->cnt_dev);
   if (c->skip_dev) cudaFree(c->skip_dev);
   if (c->scalars_dev) cudaFree(c->scalars_dev);
+  if (c->ws) cudaFree(c->ws);
   if (c->scalars_host) cudaFreeHost(c->scalars_host);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->compute_stream) cudaStreamDestroy(c->compute_stream);
@@ -186,6 +192,7 @@ static int ctx_reserve_bounce(ff_host_ctx* c, int64_t bytes) {
   if (c->pool == nullptr) {
     int n = (int)std::thread::hardware_concurrency() / 2 - 1;       // the calling thread copies too
     if (const char* e = getenv("FF_HOST_COPY_THREADS")) n = atoi(e) - 1;
+    if (c->copy_threads > 0) n = c->copy_threads - 1;
     if (n < 0) n = 0;
     if (n > 15) n = 15;
     c->pool = new (std::nothrow) CopyPool(n);
@@ -194,7 +201,14 @@ static int ctx_reserve_bounce(ff_host_ctx* c, int64_t bytes) {
   return FF_OK;
 }
 
-static int ctx_reserve(ff_host_ctx* c, int64_t stage_bytes, int64_t partial_elems, int64_t frames) {
+static int ctx_reserve(ff_host_ctx* c, int64_t stage_bytes, int64_t partial_elems, int64_t frames, int64_t ws_bytes) {
+  if (ws_bytes > c->ws_bytes) {
+    if (c->ws) FF_CUDA_TRY(cudaFree(c->ws));
+    c->ws = nullptr;
+    FF_CUDA_TRY(cudaMalloc(&c->ws, (size_t)ws_bytes));
+    FF_CUDA_TRY(cudaMemset(c->ws, 0, (size_t)ws_bytes));
+    c->ws_bytes = ws_bytes;
+  }
   if (stage_bytes > c->stage_bytes) {
     for (int i = 0; i < 2; ++i) {
       if (c->stage[i]) FF_CUDA_TRY(cudaFree(c->stage[i]));
@@ -207,7 +221,7 @@ static int ctx_reserve(ff_host_ctx* c, int64_t stage_bytes, int64_t partial_elem
     for (int i = 0; i < 2; ++i) {
       if (c->partial[i]) FF_CUDA_TRY(cudaFree(c->partial[i]));
       c->partial[i] = nullptr;
-      FF_CUDA_TRY(cudaMalloc(&c->partial[i], sizeof(int32_t) * (size_t)partial_elems));
+      if (partial_elems > 0) FF_CUDA_TRY(cudaMalloc(&c->partial[i], sizeof(int32_t) * (size_t)partial_elems));
     }
     c->partial_elems = partial_elems;
   }
@@ -395,8 +409,8 @@ int ff_host_ctx_create(int device, int64_t chunk_bytes, ff_host_ctx** ctx_out) {
     guard(cudaEventCreateWithFlags(&c->copied[i], cudaEventDisableTiming), "cudaEventCreate");
     guard(cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming), "cudaEventCreate");
   }
-  guard(cudaMalloc(&c->scalars_dev, 4 * sizeof(int32_t)), "cudaMalloc(scalars)");
-  guard(cudaMallocHost(&c->scalars_host, 4 * sizeof(int32_t)), "cudaMallocHost(scalars)");
+  guard(cudaMalloc(&c->scalars_dev, 32 * sizeof(int32_t)), "cudaMalloc(scalars)");
+  guard(cudaMallocHost(&c->scalars_host, 8 * sizeof(int32_t)), "cudaMallocHost(scalars)");
   if (rc != FF_OK) {
     ctx_release(c);
     return rc;
@@ -406,6 +420,16 @@ int ff_host_ctx_create(int device, int64_t chunk_bytes, ff_host_ctx** ctx_out) {
 }
 
 int ff_host_ctx_destroy(ff_host_ctx* ctx) { return ctx_release(ctx); }
+
+int ff_host_ctx_set_copy_threads(ff_host_ctx* c, int n_threads) {
+  if (c == nullptr || n_threads < 1) return FF_ERR_INVALID;
+  if (c->pool != nullptr && n_threads != c->copy_threads) {      // takes effect for the next pageable source
+    delete c->pool;
+    c->pool = nullptr;
+  }
+  c->copy_threads = n_threads > 16 ? 16 : n_threads;
+  return FF_OK;
+}
 
 int ff_host_upload(ff_host_ctx* c, const void* src_host, void* dst_dev, int64_t bytes) {
   if (c == nullptr || src_host == nullptr || dst_dev == nullptr || bytes < 0) return FF_ERR_INVALID;
@@ -442,18 +466,19 @@ int ff_host_upload(ff_host_ctx* c, const void* src_host, void* dst_dev, int64_t 
   return FF_OK;
 }
 
-int ff_process_host(ff_host_ctx* c, const void* frames_host, const void* halo_host, int64_t n_frames,
-                    int64_t first_frame, int height, int width, int bits, int32_t bg, int32_t empty_thr,
-                    int64_t min_signal_count, int method, int use_frame_diff, int32_t diff_thr,
-                    int32_t threshold_floor, int32_t grad2_bound, int32_t min_run_px, int32_t exit_margin_px,
-                    const uint8_t* skip_host, int32_t* pos_out_host, int32_t* count_out_host,
-                    int64_t* frames_done_out, int32_t* first_exit_out) {
-  if (c == nullptr || frames_host == nullptr || pos_out_host == nullptr) return FF_ERR_INVALID;
+int ff_process_host_range(ff_host_ctx* c, const ff_host_args* ha) {
+  if (c == nullptr || ha == nullptr || ha->frames_host == nullptr) return FF_ERR_INVALID;
+  const int64_t n_frames = ha->n_frames, first_frame = ha->first_frame;
+  const int height = ha->height, width = ha->width, bits = ha->bits;
+  const bool to_block = ha->pos_block_dev != nullptr;
+  if (!to_block && ha->pos_out_host == nullptr) return FF_ERR_INVALID;
+  if (to_block && (ha->count_block_dev == nullptr || ha->first_exit_block_dev == nullptr)) return FF_ERR_INVALID;
   if (n_frames <= 0 || height <= 0 || width <= 0 || n_frames > 0x7FFFFFFF) return FF_ERR_INVALID;
   if (bits != 8 && bits != 12 && bits != 16) return FF_ERR_UNSUPPORTED;
   const int64_t px = (int64_t)height * width;
   if (bits == 12 && (px & 1)) return FF_ERR_UNSUPPORTED;
   FF_CUDA_TRY(cudaSetDevice(c->device));
+  const uint8_t* skip_host = ha->skip_host;
 
   const int64_t fb = frame_bytes_of(px, bits);
   // Staging buffer = [halo slot][chunk frames]; the halo slot is padded so frames stay 16-B aligned.
@@ -462,29 +487,47 @@ int ff_process_host(ff_host_ctx* c, const void* frames_host, const void* halo_ho
   if (chunk_frames < 1) chunk_frames = 1;
   if (chunk_frames > n_frames) chunk_frames = n_frames;
   const Tiling tl = choose_tiling(px);
-  int rc = ctx_reserve(c, halo_slot + chunk_frames * fb, chunk_frames * tl.partials_per_frame, n_frames);
+  const bool fused = range_is_fused(px, FF_DIFF_NONE, false, false);
+  int rc = ctx_reserve(c, halo_slot + chunk_frames * fb, fused ? 0 : chunk_frames * tl.partials_per_frame,
+                       n_frames, range_workspace_bytes(chunk_frames));
   if (rc != FF_OK) return rc;
 
   cudaStream_t cs = c->copy_stream, ks = c->compute_stream;
-  int32_t* bg_dev = c->scalars_dev;
-  int32_t* exit_dev = c->scalars_dev + 1;
-  c->scalars_host[0] = bg;
+  int32_t* scal_dev = c->scalars_dev;
+  int32_t* pos_dev = to_block ? ha->pos_block_dev : c->pos_dev;
+  int32_t* cnt_dev = to_block ? ha->count_block_dev : c->cnt_dev;
+  int32_t* exit_dev = to_block ? ha->first_exit_block_dev : c->scalars_dev + 16;
+  RangeHooks hooks = hooks_from(ha->hooks);
+  const int hook_flags = hooks.flags;
+  const int32_t* global_exit_dev = (ha->hooks != nullptr && hooks.table != nullptr) ? ha->hooks->exit_word_dev : nullptr;
+  c->scalars_host[0] = ha->bg;
   c->scalars_host[1] = FF_NO_EXIT;
-  c->scalars_host[2] = c->scalars_host[3] = FF_NO_EXIT;
-  FF_CUDA_TRY(cudaMemcpyAsync(c->scalars_dev, c->scalars_host, 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ks));
-  FF_CUDA_TRY(cudaMemsetAsync(c->cnt_dev, 0, sizeof(int32_t) * (size_t)n_frames, ks));
+  for (int k = 2; k < 6; ++k) c->scalars_host[k] = FF_NO_EXIT;
+  FF_CUDA_TRY(cudaMemcpyAsync(scal_dev, c->scalars_host, sizeof(int32_t), cudaMemcpyHostToDevice, ks));
+  // first-exit word = FF_NO_EXIT; in a range-sharded run: wait until the peers no longer read the block
+  hooks.flags = hook_flags & FF_HOOK_WAIT;
+  rc = prep_impl(nullptr, height, width, bits, nullptr, nullptr, 0, exit_dev, nullptr, hooks, ks);
+  if (rc != FF_OK) return rc;
+  hooks.flags = 0;                       // the chunks only propagate exit frames; the block is published at the end
+  FF_CUDA_TRY(cudaMemsetAsync(cnt_dev, 0, sizeof(int32_t) * (size_t)n_frames, ks));
   const uint8_t* skip_dev = nullptr;
   if (skip_host != nullptr) {
     FF_CUDA_TRY(cudaMemcpyAsync(c->skip_dev, skip_host, (size_t)n_frames, cudaMemcpyHostToDevice, ks));
     skip_dev = c->skip_dev;
   }
+  int32_t seen_exit = FF_NO_EXIT;        // smallest exit frame this rank knows of (own chunks, and the peers')
+  if (global_exit_dev != nullptr) {      // another rank may already have seen the flame leave
+    FF_CUDA_TRY(cudaMemcpyAsync(c->scalars_host + 4, global_exit_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, ks));
+    FF_CUDA_TRY(cudaStreamSynchronize(ks));
+    seen_exit = c->scalars_host[4];
+  }
 
-  const uint8_t* src = static_cast<const uint8_t*>(frames_host);
+  const uint8_t* src = static_cast<const uint8_t*>(ha->frames_host);
   const int64_t n_chunks = (n_frames + chunk_frames - 1) / chunk_frames;
   // Pinned (or registered) sources are DMA'd in place; anything else goes through the bounce buffers.
   cudaPointerAttributes attr{};
   bool pageable = true;
-  if (cudaPointerGetAttributes(&attr, frames_host) == cudaSuccess)
+  if (cudaPointerGetAttributes(&attr, ha->frames_host) == cudaSuccess)
     pageable = !(attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
   else
     cudaGetLastError();       // unregistered memory reports an error on old drivers: clear it
@@ -494,8 +537,7 @@ int ff_process_host(ff_host_ctx* c, const void* frames_host, const void* halo_ho
   }
   bool bounce_used[2] = {false, false};
   bool used[2] = {false, false};
-  int64_t frames_done = 0;
-  int32_t seen_exit = FF_NO_EXIT;
+  int64_t frames_done = 0, bytes_up = 0;
 
   for (int64_t ci = 0; ci < n_chunks; ++ci) {
     const int b = (int)(ci & 1);
@@ -503,12 +545,14 @@ int ff_process_host(ff_host_ctx* c, const void* frames_host, const void* halo_ho
     const int64_t e = (a + chunk_frames < n_frames) ? a + chunk_frames : n_frames;
     if (used[b]) {  // chunk ci-2 must be finished before its buffer is overwritten
       FF_CUDA_TRY(cudaEventSynchronize(c->done[b]));
-      if (c->scalars_host[2 + b] < seen_exit) seen_exit = c->scalars_host[2 + b];
+      seen_exit = std::min(seen_exit, std::min(c->scalars_host[2 + b], c->scalars_host[4 + b]));
     }
     // Chunk ci-1 may already be finished too: peek without blocking.
-    if (used[b ^ 1] && cudaEventQuery(c->done[b ^ 1]) == cudaSuccess && c->scalars_host[2 + (b ^ 1)] < seen_exit)
-      seen_exit = c->scalars_host[2 + (b ^ 1)];
-    if (seen_exit != FF_NO_EXIT) break;  // the reference loop breaks at the exit frame (:1494)
+    if (used[b ^ 1] && cudaEventQuery(c->done[b ^ 1]) == cudaSuccess)
+      seen_exit = std::min(seen_exit, std::min(c->scalars_host[2 + (b ^ 1)], c->scalars_host[4 + (b ^ 1)]));
+    // The reference loop breaks at the exit frame (:1494): nothing at or behind it is copied, whichever
+    // rank found it.  (An exit in one of this range's own chunks always lies before the next chunk.)
+    if ((int64_t)seen_exit <= first_frame + a) break;
 
     uint8_t* halo_dst = c->stage[b] + (halo_slot - fb);
     uint8_t* frames_dst = c->stage[b] + halo_slot;
@@ -532,7 +576,7 @@ int ff_process_host(ff_host_ctx* c, const void* frames_host, const void* halo_ho
         from = bh;
         bytes = (size_t)((e - a + 1) * fb);
       } else {
-        const void* hsrc = h >= 0 ? static_cast<const void*>(src + h * fb) : halo_host;
+        const void* hsrc = h >= 0 ? static_cast<const void*>(src + h * fb) : ha->halo_host;
         if (hsrc != nullptr) {
           std::memcpy(bh, hsrc, (size_t)fb);
           halo_dev = halo_dst;
@@ -544,50 +588,119 @@ int ff_process_host(ff_host_ctx* c, const void* frames_host, const void* halo_ho
       FF_CUDA_TRY(cudaMemcpyAsync(c->stage[b] + (from - c->bounce[b]), from, bytes, cudaMemcpyHostToDevice, cs));
       FF_CUDA_TRY(cudaEventRecord(c->bounce_free[b], cs));
       bounce_used[b] = true;
+      bytes_up += (int64_t)bytes;
     } else if (h >= 0 && h == a - 1) {
       FF_CUDA_TRY(cudaMemcpyAsync(halo_dst, src + h * fb, (size_t)((e - a + 1) * fb), cudaMemcpyHostToDevice, cs));
       halo_dev = halo_dst;
+      bytes_up += (e - a + 1) * fb;
     } else {
-      const void* hsrc = h >= 0 ? static_cast<const void*>(src + h * fb) : halo_host;
+      const void* hsrc = h >= 0 ? static_cast<const void*>(src + h * fb) : ha->halo_host;
       if (hsrc != nullptr) {
         FF_CUDA_TRY(cudaMemcpyAsync(halo_dst, hsrc, (size_t)fb, cudaMemcpyHostToDevice, cs));
         halo_dev = halo_dst;
+        bytes_up += fb;
       }
       FF_CUDA_TRY(cudaMemcpyAsync(frames_dst, src + a * fb, (size_t)((e - a) * fb), cudaMemcpyHostToDevice, cs));
+      bytes_up += (e - a) * fb;
     }
     FF_CUDA_TRY(cudaEventRecord(c->copied[b], cs));
     FF_CUDA_TRY(cudaStreamWaitEvent(ks, c->copied[b], 0));
 
-    const uint8_t* skip_chunk = skip_dev ? skip_dev + a : nullptr;
-    rc = stream_frames_impl(frames_dst, halo_dev, e - a, height, width, bits, bg_dev, empty_thr, diff_thr, skip_chunk,
-                            c->partial[b], nullptr, FF_DIFF_NONE, nullptr, ks);
-    if (rc != FF_OK) return rc;
-    rc = detect_impl(frames_dst, halo_dev, e - a, first_frame + a, height, width, bits, bg_dev, c->partial[b],
-                     min_signal_count, method, use_frame_diff, diff_thr, threshold_floor, grad2_bound, min_run_px,
-                     exit_margin_px, skip_chunk, c->pos_dev + a, c->cnt_dev + a, exit_dev, nullptr, ks);
+    RangeJob j{};
+    j.frames = frames_dst;
+    j.halo = halo_dev;
+    j.n_frames = e - a;
+    j.first_frame = first_frame + a;
+    j.height = height;
+    j.width = width;
+    j.bits = bits;
+    j.method = ha->method;
+    j.use_frame_diff = ha->use_frame_diff;
+    j.min_run_px = ha->min_run_px;
+    j.exit_margin_px = ha->exit_margin_px;
+    j.diff_thr = ha->diff_thr;
+    j.grad2_bound = ha->grad2_bound;
+    j.empty_thr = ha->empty_thr;
+    j.threshold_floor = ha->threshold_floor;
+    j.min_signal_count = ha->min_signal_count;
+    j.skip = skip_dev ? skip_dev + a : nullptr;
+    j.scalars = scal_dev;
+    j.pos_out = pos_dev + a;
+    j.count_out = cnt_dev + a;
+    j.first_exit = exit_dev;
+    j.diff_dtype = FF_DIFF_NONE;
+    j.partial = c->partial[b];
+    j.ws = static_cast<RangeWorkspace*>(c->ws);
+    j.hooks = hooks;
+    rc = process_range_impl(j, ks);
     if (rc != FF_OK) return rc;
     FF_CUDA_TRY(cudaMemcpyAsync(c->scalars_host + 2 + b, exit_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, ks));
+    if (global_exit_dev != nullptr)
+      FF_CUDA_TRY(cudaMemcpyAsync(c->scalars_host + 4 + b, global_exit_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, ks));
     FF_CUDA_TRY(cudaEventRecord(c->done[b], ks));
-    // The next copy into this buffer waits for these kernels on the device side as well.
-    FF_CUDA_TRY(cudaStreamWaitEvent(cs, c->done[b], 0));
+    // (the next copy into stage[b] is issued only after the host has waited for done[b] above, so the
+    // copy of chunk ci+1 into the other buffer overlaps these kernels)
     used[b] = true;
     frames_done = e;
   }
 
   // Frames never copied are, by construction, at or beyond the exit frame.
   if (frames_done < n_frames)
-    FF_CUDA_TRY(cudaMemsetAsync(c->pos_dev + frames_done, 0xFF, sizeof(int32_t) * (size_t)(n_frames - frames_done), ks));
-  rc = truncate_impl(c->pos_dev, n_frames, first_frame, exit_dev, ks);
-  if (rc != FF_OK) return rc;
-  FF_CUDA_TRY(cudaMemcpyAsync(pos_out_host, c->pos_dev, sizeof(int32_t) * (size_t)n_frames, cudaMemcpyDeviceToHost, ks));
-  if (count_out_host != nullptr)
-    FF_CUDA_TRY(cudaMemcpyAsync(count_out_host, c->cnt_dev, sizeof(int32_t) * (size_t)n_frames, cudaMemcpyDeviceToHost, ks));
+    FF_CUDA_TRY(cudaMemsetAsync(pos_dev + frames_done, 0xFF, sizeof(int32_t) * (size_t)(n_frames - frames_done), ks));
+  if (to_block) {
+    // range-sharded: truncation happens in the merge, against the clip-global exit frame
+    if (hooks.table != nullptr && (hook_flags & FF_HOOK_PUBLISH)) {
+      hooks.flags = FF_HOOK_PUBLISH;
+      rc = publish_impl(hooks, ks);
+      if (rc != FF_OK) return rc;
+    }
+  } else {
+    rc = truncate_impl(pos_dev, n_frames, first_frame, exit_dev, ks);
+    if (rc != FF_OK) return rc;
+  }
+  if (ha->pos_out_host != nullptr)
+    FF_CUDA_TRY(cudaMemcpyAsync(ha->pos_out_host, pos_dev, sizeof(int32_t) * (size_t)n_frames, cudaMemcpyDeviceToHost, ks));
+  if (ha->count_out_host != nullptr)
+    FF_CUDA_TRY(cudaMemcpyAsync(ha->count_out_host, cnt_dev, sizeof(int32_t) * (size_t)n_frames, cudaMemcpyDeviceToHost, ks));
   FF_CUDA_TRY(cudaMemcpyAsync(c->scalars_host + 1, exit_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, ks));
   FF_CUDA_TRY(cudaStreamSynchronize(ks));
   FF_CUDA_TRY(cudaStreamSynchronize(cs));
-  if (frames_done_out) *frames_done_out = frames_done;
-  if (first_exit_out) *first_exit_out = c->scalars_host[1];
+  if (ha->frames_done_out) *ha->frames_done_out = frames_done;
+  if (ha->first_exit_out) *ha->first_exit_out = c->scalars_host[1];
+  if (ha->bytes_uploaded_out) *ha->bytes_uploaded_out = bytes_up;
   return FF_OK;
+}
+
+int ff_process_host(ff_host_ctx* c, const void* frames_host, const void* halo_host, int64_t n_frames,
+                    int64_t first_frame, int height, int width, int bits, int32_t bg, int32_t empty_thr,
+                    int64_t min_signal_count, int method, int use_frame_diff, int32_t diff_thr,
+                    int32_t threshold_floor, int32_t grad2_bound, int32_t min_run_px, int32_t exit_margin_px,
+                    const uint8_t* skip_host, int32_t* pos_out_host, int32_t* count_out_host,
+                    int64_t* frames_done_out, int32_t* first_exit_out) {
+  ff_host_args a{};
+  a.frames_host = frames_host;
+  a.halo_host = halo_host;
+  a.n_frames = n_frames;
+  a.first_frame = first_frame;
+  a.height = height;
+  a.width = width;
+  a.bits = bits;
+  a.bg = bg;
+  a.empty_thr = empty_thr;
+  a.min_signal_count = min_signal_count;
+  a.method = method;
+  a.use_frame_diff = use_frame_diff;
+  a.diff_thr = diff_thr;
+  a.threshold_floor = threshold_floor;
+  a.grad2_bound = grad2_bound;
+  a.min_run_px = min_run_px;
+  a.exit_margin_px = exit_margin_px;
+  a.skip_host = skip_host;
+  a.pos_out_host = pos_out_host;
+  a.count_out_host = count_out_host;
+  a.frames_done_out = frames_done_out;
+  a.first_exit_out = first_exit_out;
+  return ff_process_host_range(c, &a);
 }
 
 }  // extern "C"

@@ -80,6 +80,57 @@ inline Tiling choose_tiling(int64_t px_per_frame) {
 
 inline int64_t frame_bytes_of(int64_t px, int bits) { return px * bits / 8; }
 
+// ---- range-sharded runs: what the compute kernels need to know about the peer exchange ---------
+// (filled by ff_exchange_begin; see csrc/ff_exchange.cu for the protocol)
+constexpr int kMaxRanks = 64;
+struct PeerTable {                    // lives in device memory, owned by the ff_exchange
+  int32_t* base[kMaxRanks];           // every rank's exchange buffer (own entry = local memory)
+  int64_t flags_off, acks_off, exit_off, status_off;   // int32 offsets inside such a buffer
+};
+struct RangeHooks {                   // passed to kernels by value (24 bytes)
+  const PeerTable* table;             // nullptr: single-GPU run, every hook is a no-op
+  int32_t epoch, world, rank;
+  int32_t flags;                      // FF_HOOK_WAIT: prep_kernel waits for the peers' acks of epoch-2;
+                                      // FF_HOOK_PUBLISH: the last CTA of the range publishes the block.
+                                      // Exit frames are propagated to the peers' exit words in any case.
+  long long spin_limit;               // clock64 ticks before a wait gives up and raises the status word
+};
+inline RangeHooks no_hooks() {
+  RangeHooks h{};
+  return h;
+}
+inline RangeHooks hooks_from(const ff_range_hooks* h) {
+  RangeHooks r{};
+  if (h != nullptr && h->table_dev != nullptr) {
+    r.table = static_cast<const PeerTable*>(h->table_dev);
+    r.epoch = h->epoch;
+    r.world = h->world;
+    r.rank = h->rank;
+    r.flags = h->flags;
+    r.spin_limit = h->spin_limit;
+  }
+  return r;
+}
+
+// ---- workspace of ff_process_range (zero-filled by its owner once; every kernel that uses a word
+// leaves it zero again) ---------------------------------------------------------------------------
+constexpr int kPrepMaxCtas = 64;
+struct RangeWorkspace {
+  unsigned int prep_ticket;           // CTAs of prep_kernel that delivered their partial maximum
+  unsigned int tail_ticket;           // CTAs of the fused / detect kernel that are done
+  unsigned int pad[2];
+  int32_t prep_max[kPrepMaxCtas];     // per-CTA maxima of frame 0
+  unsigned long long stats[8];        // FF_RANGE_STATS=1 (diagnostics): detector-warp cycle counters, see range_kernel
+  // followed by one 64-bit word per frame, {arrivals:32 | above-noise count:32}, each on its OWN 128-byte
+  // line: all CTAs sweep through the clip together, so the words of neighbouring frames are hit at the same
+  // time - packed 16 to a line they serialise in one L2 slice (measured: C3 range kernel 1.79 -> 1.2 ms)
+};
+constexpr int64_t kWorkspaceHeader = 512;
+constexpr int64_t kArriveStride = 16;      // in 64-bit words
+inline int64_t range_workspace_bytes(int64_t n_frames) {
+  return kWorkspaceHeader + 8 * kArriveStride * (n_frames > 0 ? n_frames : 0);
+}
+
 #if defined(__CUDACC__)
 // ---- mbarrier + bulk async copy (TMA 1-D) ------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -192,6 +243,32 @@ __device__ __forceinline__ void count12x8(uint32_t w0, uint32_t w1, uint32_t w2,
   add_gt(cnt, t3 & 0xFFFFFu, nk_lo);
 }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its
+// predecessor on the stream still runs; griddep_wait() blocks until that predecessor has
+// completed and its memory is visible (no-op without the attribute).  The predecessor allows the
+// early start with griddep_launch_dependents().
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---- system-scope flags in peer memory (range exchange, csrc/ff_exchange.cu) --------------------
+__device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int32_t ld_relaxed_sys(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_min_sys(int32_t* p, int32_t v) {
+  asm volatile("red.relaxed.sys.global.min.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // One pixel out of a packed buffer whose first byte holds flat pixel 0 (any bit depth).
 template <int BITS>
 __device__ __forceinline__ int load_px_generic(const uint8_t* __restrict__ base, int64_t q) {
@@ -199,6 +276,24 @@ __device__ __forceinline__ int load_px_generic(const uint8_t* __restrict__ base,
   if (BITS == 16) return (int)base[2 * q] | ((int)base[2 * q + 1] << 8);
   const uint8_t* t = base + (q >> 1) * 3;
   return (q & 1) ? (((int)(t[1] & 15) << 8) | (int)t[2]) : (((int)t[0] << 4) | ((int)t[1] >> 4));
+}
+
+// Kernel launch with the optional PDL attribute (the kernel may start while its predecessor on the
+// stream still runs and must griddep_wait() before it touches that predecessor's outputs).
+template <class Kern, class Params>
+inline int launch_kernel(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, const Params& p) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  FF_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
+  return FF_OK;
 }
 #endif  // __CUDACC__
 

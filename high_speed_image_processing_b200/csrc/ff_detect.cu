@@ -10,53 +10,12 @@
 //   threshold     ballot scan from the right for the rightmost run of p > T
 // All quantities are integers (see ff_stream.cu), so the answers are bit-exact.
 #include <climits>
-#include "ff_common.cuh"
+#include "ff_detect_core.cuh"
 
 namespace ff {
 namespace {
 
 constexpr int kDetectWarps = 8;
-
-struct DetectParams {
-  const uint8_t* frames;
-  const uint8_t* halo;
-  int64_t frame_bytes;
-  int64_t px_per_frame;
-  int n_frames;
-  int64_t first_frame;
-  int height, width;
-  const int32_t* bg_dev;
-  const int32_t* partial;
-  int partials_per_frame;
-  int64_t min_signal_count;
-  int method;
-  int use_diff;
-  int diff_thr;
-  int threshold_floor;
-  int grad2_bound;
-  int min_run;
-  int exit_margin;
-  const uint8_t* skip;
-  int32_t* pos_out;
-  int32_t* count_out;
-  int32_t* first_exit;
-  int32_t* profile_out;
-  int raw_stride;  // bytes reserved per staged row (multiple of 4)
-};
-
-// Stage bytes [lo, lo+n) of `src` into `dst` (per-warp shared memory), whole words when the
-// global address allows it.
-__device__ __forceinline__ void warp_copy_bytes(uint8_t* dst, const uint8_t* __restrict__ src, int n, int lane) {
-  if ((reinterpret_cast<uintptr_t>(src) & 3u) == 0) {
-    const int nw = n >> 2;
-    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
-    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-    for (int i = lane; i < nw; i += 32) d32[i] = __ldg(s32 + i);
-    for (int i = (nw << 2) + lane; i < n; i += 32) dst[i] = __ldg(src + i);
-  } else {
-    for (int i = lane; i < n; i += 32) dst[i] = __ldg(src + i);
-  }
-}
 
 template <int BITS>
 __global__ void __launch_bounds__(kDetectWarps * 32) detect_kernel(const DetectParams p) {
@@ -70,20 +29,10 @@ __global__ void __launch_bounds__(kDetectWarps * 32) detect_kernel(const DetectP
   uint8_t* raw_pri = raw_base + p.raw_stride;
   const unsigned full = 0xFFFFFFFFu;
 
+  griddep_wait();                       // partial counts / scalars come from the kernels before this one
   const int bg = __ldg(p.bg_dev);
-  const int row = p.height / 2;
-  // Flat pixel index of the centre row inside a frame, and the byte span that holds it.
-  const int64_t q0 = (int64_t)row * W;
-  int64_t byte_lo, byte_hi;
-  if (BITS == 12) {
-    byte_lo = (q0 >> 1) * 3;
-    byte_hi = ((q0 + W - 1) >> 1) * 3 + 3;
-  } else {
-    byte_lo = q0 * (BITS / 8);
-    byte_hi = (q0 + W) * (BITS / 8);
-  }
-  const int nbytes = (int)(byte_hi - byte_lo);
-  const int64_t qbase = (BITS == 12) ? (q0 & ~(int64_t)1) : q0;  // pixel held by raw byte 0
+  const int thr_floor = p.threshold_dev != nullptr ? __ldg(p.threshold_dev) : p.threshold_floor;
+  const RowSpan rs = centre_row_span<BITS>(p.height, W);
 
   // Frames are dealt to warps in strides: warp w looks at frames w, w + nw, w + 2 nw, ... 32 at a
   // time, one candidate per lane.  Every lane sums its candidate's partial counts (the empty-frame
@@ -115,133 +64,250 @@ __global__ void __launch_bounds__(kDetectWarps * 32) detect_kernel(const DetectP
       const bool skipped_c = p.skip != nullptr && p.skip[fc] != 0;
       const bool empty_c = (int64_t)cnt_c < p.min_signal_count;
       // without a prior frame there is no difference profile: only frame 0 of a range without halo
-      // (or a range that starts with skipped frames) - resolved exactly in the per-frame path below
+      // (or a range that starts with skipped frames) - resolved exactly in the per-frame path
       need_c = !skipped_c && (!empty_c || p.profile_out != nullptr);
       if (!need_c) p.pos_out[fc] = FF_POS_NONE;
     }
     unsigned pending = __ballot_sync(full, need_c);
     while (pending) {
-    const int src = __ffs((int)pending) - 1;
-    pending &= pending - 1;
-    const int f = (int)(base + (int64_t)src * nw);
-    const int cnt = __shfl_sync(full, cnt_c, src);
-    const bool skipped = false;
-    const bool empty = (int64_t)cnt < p.min_signal_count;
-
-    // prior frame: the latest non-skipped frame before f (:469, :1462, :1443-1445)
-    const uint8_t* prior = nullptr;
-    if (p.use_diff) {
-      int hf = f - 1;
-      if (p.skip != nullptr)
-        while (hf >= 0 && p.skip[hf]) --hf;
-      prior = hf >= 0 ? p.frames + (int64_t)hf * p.frame_bytes : p.halo;
+      const int src = __ffs((int)pending) - 1;
+      pending &= pending - 1;
+      const int f = (int)(base + (int64_t)src * nw);
+      const int cnt = __shfl_sync(full, cnt_c, src);
+      const bool empty = (int64_t)cnt < p.min_signal_count;
+      const int pos = detect_one_frame<BITS>(p, rs, f, empty, bg, thr_floor, prof, raw_cur, raw_pri, lane);
+      if (lane == 0) commit_position(p, f, pos);
     }
-    const bool have_profile = !skipped && (!p.use_diff || prior != nullptr);
+  }
+  // last CTA of the launch: local truncation, publication to the peers
+  if (p.ws != nullptr) {
+    __syncthreads();
+    if (warp == 0) range_tail(p, lane);
+  }
+}
 
-    int pos = FF_POS_NONE;
-    if (have_profile && (!empty || p.profile_out != nullptr)) {
-      __syncwarp();
-      warp_copy_bytes(raw_cur, p.frames + (int64_t)f * p.frame_bytes + byte_lo, nbytes, lane);
-      if (p.use_diff) warp_copy_bytes(raw_pri, prior + byte_lo, nbytes, lane);
-      __syncwarp();
-      for (int x = lane; x < W; x += 32) {
-        const int64_t q = q0 + x - qbase;
-        int v = max(load_px_generic<BITS>(raw_cur, q) - bg, 0);
-        if (p.use_diff) {
-          v -= max(load_px_generic<BITS>(raw_pri, q) - bg, 0);
-          if (v < p.diff_thr) v = 0;
-        }
-        prof[x] = v;
-        if (p.profile_out != nullptr) p.profile_out[(int64_t)f * W + x] = v;
+// ---- prep_kernel: everything a range needs before its frames are streamed -----------------------
+//   * (range-sharded runs) wait until every peer has finished reading the block this epoch will
+//     overwrite (their acks of epoch-2), see csrc/ff_exchange.cu;
+//   * the range's first-exit word = FF_NO_EXIT;
+//   * the clip's background scalar = max of frame 0 (scripts/process_videos.py:1357-1358), the centre
+//     row of frame 0 (:1361-1362) and - for the threshold method - the float64 statistics of that row
+//     and the flame threshold max(mean + 5 std, 2 max) (:1363-1370), evaluated in NumPy's own order
+//     of operations (pairwise summation of add.reduce) so that the threshold is the bit-identical
+//     float64; the host repeats the computation with NumPy itself as a cross-check.
+// The kernel lets its dependents start at once (PDL): the streaming kernel behind it brings its
+// CTAs up and its producer warps begin to fetch tiles while this one runs.
+struct PrepParams {
+  const uint8_t* frame0;     // nullptr: scalars are already known
+  int64_t n_px;
+  int height, width;
+  int32_t* scalars;          // int32[16]: [0] bg, [1] floor(flame threshold), [2] status; float64 at byte 16: mean, std, max, threshold
+  uint16_t* centerline;      // uint16[W], nullable
+  int want_stats;
+  int32_t* first_exit;       // nullable
+  RangeWorkspace* ws;
+  RangeHooks hooks;
+};
+
+constexpr int kPrepThreads = 256;
+constexpr int kMaxLeaves = 96;      // W <= 4096: at most 64 leaves of NumPy's pairwise summation
+
+// np.add.reduce over n float64 values = pairwise_sum(a, n) (numpy/_core/src/umath/loops_utils.h.src):
+// n < 8 plain loop; n <= 128 eight strided accumulators combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))
+// plus the n % 8 tail; else split at n2 = n/2 - (n/2) % 8.  The leaves (n <= 128) are summed by groups of
+// eight threads, one accumulator each; one thread then adds the leaf sums in the order of the recursion.
+__device__ int pairwise_leaves(int n, int* off, int* len) {
+  int so[16], sn[16], sp = 0, count = 0;
+  so[0] = 0;
+  sn[0] = n;
+  while (sp >= 0) {
+    const int o = so[sp], m = sn[sp];
+    --sp;
+    if (m <= 128) {
+      off[count] = o;
+      len[count] = m;
+      ++count;
+    } else {
+      int n2 = m / 2;
+      n2 -= n2 % 8;
+      ++sp; so[sp] = o + n2; sn[sp] = m - n2;     // right half: popped after the left one
+      ++sp; so[sp] = o;      sn[sp] = n2;
+    }
+  }
+  return count;
+}
+__device__ double pairwise_combine(int n, const double* leaf) {
+  int ns[16], st[16], sp = 0, next = 0;
+  double acc[16], ret = 0.0;
+  ns[0] = n;
+  st[0] = 0;
+  while (sp >= 0) {
+    const int m = ns[sp];
+    if (m <= 128) {
+      ret = leaf[next++];
+      --sp;
+      continue;
+    }
+    int n2 = m / 2;
+    n2 -= n2 % 8;
+    if (st[sp] == 0) {
+      st[sp] = 1;
+      ns[sp + 1] = n2;
+      st[sp + 1] = 0;
+      ++sp;
+    } else if (st[sp] == 1) {
+      acc[sp] = ret;
+      st[sp] = 2;
+      ns[sp + 1] = m - n2;
+      st[sp + 1] = 0;
+      ++sp;
+    } else {
+      ret = __dadd_rn(acc[sp], ret);
+      --sp;
+    }
+  }
+  return ret;
+}
+// Whole CTA: np.add.reduce(xs[0:n]).  leaf_* are shared arrays; result valid in every thread.
+__device__ double cta_pairwise_sum(const double* xs, int n, const int* leaf_off, const int* leaf_len, int n_leaves,
+                                   double* leaf_sum, double* result) {
+  const int gid = threadIdx.x >> 3, j = threadIdx.x & 7;
+  for (int it = 0; it * (kPrepThreads / 8) < n_leaves; ++it) {
+    const int L = it * (kPrepThreads / 8) + gid;
+    const bool valid = L < n_leaves;
+    const int off = valid ? leaf_off[L] : 0;
+    const int len = valid ? leaf_len[L] : 0;
+    double r = 0.0;
+    const int body = len - (len % 8);
+    if (len >= 8) {
+      r = xs[off + j];
+      for (int i = 8; i < body; i += 8) r = __dadd_rn(r, xs[off + i + j]);
+    }
+    r = __dadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 1));
+    r = __dadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 2));
+    r = __dadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 4));
+    if (valid && j == 0) {
+      if (len < 8) {
+        r = 0.0;
+        for (int i = 0; i < len; ++i) r = __dadd_rn(r, xs[off + i]);
+      } else {
+        for (int i = body; i < len; ++i) r = __dadd_rn(r, xs[off + i]);
       }
-      __syncwarp();
+      leaf_sum[L] = r;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *result = pairwise_combine(n, leaf_sum);
+  __syncthreads();
+  return *result;
+}
 
-      if (!empty) {
-        const int nchunk = (W + 31) >> 5;
-        if (p.method == FF_METHOD_HALF_MAXIMUM) {
-          // first arg-max: maximise (value, -x)
-          long long best = LLONG_MIN;
-          for (int x = lane; x < W; x += 32) {
-            const long long key = ((long long)prof[x] << 32) | (unsigned)(0x7FFFFFFF - x);
-            best = key > best ? key : best;
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const long long other = __shfl_xor_sync(full, best, o);
-            best = other > best ? other : best;
-          }
-          const int peak = (int)(best >> 32);
-          const int k = 0x7FFFFFFF - (int)(best & 0xFFFFFFFFll);
-          if (peak > 0) {
-            for (int c = (k + 1) >> 5; c < nchunk; ++c) {
-              const int x = (c << 5) + lane;
-              const bool below = x > k && x < W && 2 * prof[x] < peak;
-              const unsigned bits = __ballot_sync(full, below);
-              if (bits) {
-                pos = (c << 5) + __ffs(bits) - 1;
-                break;
-              }
-            }
-          }
-        } else if (p.method == FF_METHOD_GRADIENT) {
-          // np.gradient: central (f[i+1]-f[i-1])/2, one-sided at both ends; compare 2*g.
-          long long best = LLONG_MAX;
-          for (int x = lane; x < W; x += 32) {
-            int g2;
-            if (x == 0) g2 = 2 * (prof[1] - prof[0]);
-            else if (x == W - 1) g2 = 2 * (prof[W - 1] - prof[W - 2]);
-            else g2 = prof[x + 1] - prof[x - 1];
-            const long long key = ((long long)g2 << 32) | (unsigned)x;
-            best = key < best ? key : best;
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const long long other = __shfl_xor_sync(full, best, o);
-            best = other < best ? other : best;
-          }
-          const int g2min = (int)(best >> 32);
-          if (g2min < p.grad2_bound) pos = (int)(best & 0xFFFFFFFFll);
-        } else {
-          // rightmost run of (p > T) with length >= min_run, scanned right to left
-          bool in_run = false;
-          int run_end = -1, run_len = 0;
-          for (int c = nchunk - 1; c >= 0 && pos < 0; --c) {
-            const int x = (c << 5) + lane;
-            const unsigned w = __ballot_sync(full, x < W && prof[x] > p.threshold_floor);
-            int hi = 31;  // next bit to examine
-            while (hi >= 0) {
-              if (in_run) {
-                const unsigned shifted = w << (31 - hi);
-                const int ones = __clz((int)~shifted);  // leading ones from bit hi downward
-                run_len += ones;
-                hi -= ones;
-                if (hi >= 0) {  // a zero bit ended the run inside this word
-                  if (run_len >= p.min_run) {
-                    pos = run_end;
-                    break;
-                  }
-                  in_run = false;
-                }
-              } else {
-                const unsigned masked = hi == 31 ? w : (w & ((2u << hi) - 1u));
-                if (!masked) break;
-                hi = 31 - __clz((int)masked);
-                run_end = (c << 5) + hi;
-                run_len = 0;
-                in_run = true;
-              }
-            }
-          }
-          if (pos < 0 && in_run && run_len >= p.min_run) pos = run_end;
+template <int BITS>
+__global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepParams p) {
+  griddep_launch_dependents();
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ int s_max[kPrepThreads / 32];
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+
+  if (blockIdx.x == 0) {
+    if (p.hooks.table != nullptr && (p.hooks.flags & FF_HOOK_WAIT) && tid < p.hooks.world) {
+      // the block (and exit word) of this epoch's parity was last used two epochs ago
+      const PeerTable* t = p.hooks.table;
+      const int32_t* ack = t->base[p.hooks.rank] + t->acks_off + tid;
+      const long long t0 = clock64();
+      while (ld_acquire_sys(ack) < p.hooks.epoch - 2) {
+        if (clock64() - t0 > p.hooks.spin_limit) {
+          atomicExch(t->base[p.hooks.rank] + t->status_off, 0x100 + tid);
+          break;
         }
       }
     }
-    if (lane == 0) {
-      p.pos_out[f] = pos;
-      if (pos >= 0 && pos >= W - p.exit_margin)  // scripts/process_videos.py:1488-1489
-        atomicMin(p.first_exit, (int)(p.first_frame + f));
+    __syncthreads();
+    if (tid == 0 && p.first_exit != nullptr) *p.first_exit = FF_NO_EXIT;
+  }
+  if (p.frame0 == nullptr) return;
+
+  // ---- max of frame 0: every CTA a slice, the last one to finish combines --------------------------
+  int m = 0;
+  const bool words = BITS == 12 && (p.n_px & 7) == 0 && (reinterpret_cast<uintptr_t>(p.frame0) & 3u) == 0;
+  if (words) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p.frame0);
+    for (int64_t g = (int64_t)blockIdx.x * kPrepThreads + tid; g < p.n_px / 8; g += (int64_t)gridDim.x * kPrepThreads) {
+      int v[8];
+      decode12x8(__ldg(w + 3 * g), __ldg(w + 3 * g + 1), __ldg(w + 3 * g + 2), v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m = max(m, v[k]);
     }
-    }  // pending frames of this round
+  } else {
+    for (int64_t q = (int64_t)blockIdx.x * kPrepThreads + tid; q < p.n_px; q += (int64_t)gridDim.x * kPrepThreads)
+      m = max(m, load_px_generic<BITS>(p.frame0, q));
+  }
+  m = __reduce_max_sync(0xFFFFFFFFu, m);
+  if ((tid & 31) == 0) s_max[tid >> 5] = m;
+  __syncthreads();
+  if (tid == 0) {
+    int mm = 0;
+    for (int k = 0; k < kPrepThreads / 32; ++k) mm = max(mm, s_max[k]);
+    p.ws->prep_max[blockIdx.x] = mm;
+    __threadfence();
+    s_last = atomicAdd(&p.ws->prep_ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid == 0) {
+    int mm = 0;
+    for (unsigned k = 0; k < gridDim.x; ++k) mm = max(mm, ((volatile int32_t*)p.ws->prep_max)[k]);
+    p.scalars[0] = mm;
+    p.ws->prep_ticket = 0;
+  }
+  const int W = p.width;
+  const int64_t q0 = (int64_t)(p.height / 2) * W;
+  if (p.centerline != nullptr)
+    for (int x = tid; x < W; x += kPrepThreads) p.centerline[x] = (uint16_t)load_px_generic<BITS>(p.frame0, q0 + x);
+  if (!p.want_stats) return;
+
+  // ---- float64 statistics of the centre row, NumPy's order of operations ------------------------------
+  double* xs = reinterpret_cast<double*>(smem);                 // [W]
+  double* leaf_sum = xs + W;                                    // [kMaxLeaves]
+  double* result = leaf_sum + kMaxLeaves;                       // [1]
+  int* leaf_off = reinterpret_cast<int*>(result + 1);           // [kMaxLeaves]
+  int* leaf_len = leaf_off + kMaxLeaves;                        // [kMaxLeaves]
+  __shared__ int s_leaves;
+  int mx = 0;
+  for (int x = tid; x < W; x += kPrepThreads) {
+    const int v = load_px_generic<BITS>(p.frame0, q0 + x);
+    xs[x] = (double)v;
+    mx = max(mx, v);
+  }
+  mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+  if ((tid & 31) == 0) s_max[tid >> 5] = mx;
+  if (tid == 0) s_leaves = pairwise_leaves(W, leaf_off, leaf_len);
+  __syncthreads();
+  mx = 0;
+  for (int k = 0; k < kPrepThreads / 32; ++k) mx = max(mx, s_max[k]);
+  const int n_leaves = s_leaves;
+  const double mean = __ddiv_rn(cta_pairwise_sum(xs, W, leaf_off, leaf_len, n_leaves, leaf_sum, result), (double)W);
+  for (int x = tid; x < W; x += kPrepThreads) {
+    const double d = __dsub_rn(xs[x], mean);                    // arr - arrmean
+    xs[x] = __dmul_rn(d, d);                                    // multiply(x, x)
+  }
+  __syncthreads();
+  const double var = __ddiv_rn(cta_pairwise_sum(xs, W, leaf_off, leaf_len, n_leaves, leaf_sum, result), (double)W);
+  if (tid == 0) {
+    const double sd = __dsqrt_rn(var);
+    const double a = __dadd_rn(mean, __dmul_rn(5.0, sd));       // mean + 5 * std           (:1367)
+    const double b = __dmul_rn((double)mx, 2.0);                // centerline_max * 2.0      (:1369)
+    const double thr = b > a ? b : a;                           // max(a, b)
+    double fl = floor(thr);
+    if (fl > 2147483647.0) fl = 2147483647.0;
+    p.scalars[1] = (int32_t)fl;
+    double* out = reinterpret_cast<double*>(p.scalars + 4);
+    out[0] = mean;
+    out[1] = sd;
+    out[2] = (double)mx;
+    out[3] = thr;
   }
 }
 
@@ -268,13 +334,13 @@ __global__ void truncate_kernel(int32_t* pos, int64_t n, int64_t first_frame, co
 
 }  // namespace
 
-int detect_impl(const void* frames, const void* halo, int64_t n_frames, int64_t first_frame, int height,
-                int width, int bits, const int32_t* bg_dev, const int32_t* partial, int64_t min_signal_count,
-                int method, int use_frame_diff, int32_t diff_thr, int32_t threshold_floor, int32_t grad2_bound,
-                int32_t min_run_px, int32_t exit_margin_px, const uint8_t* skip, int32_t* pos_out,
-                int32_t* count_out, int32_t* first_exit, int32_t* profile_out, cudaStream_t st) {
-  if (frames == nullptr || bg_dev == nullptr || partial == nullptr || pos_out == nullptr || first_exit == nullptr)
-    return FF_ERR_INVALID;
+int make_detect_params(DetectParams* out, const void* frames, const void* halo, int64_t n_frames,
+                       int64_t first_frame, int height, int width, int bits, const int32_t* bg_dev,
+                       const int32_t* partial, int64_t min_signal_count, int method, int use_frame_diff,
+                       int32_t diff_thr, int32_t threshold_floor, int32_t grad2_bound, int32_t min_run_px,
+                       int32_t exit_margin_px, const uint8_t* skip, int32_t* pos_out, int32_t* count_out,
+                       int32_t* first_exit, int32_t* profile_out) {
+  if (frames == nullptr || bg_dev == nullptr || pos_out == nullptr || first_exit == nullptr) return FF_ERR_INVALID;
   if (n_frames <= 0 || height <= 0 || width <= 0 || n_frames > 0x7FFFFFFF) return FF_ERR_INVALID;
   if (first_frame < 0 || first_frame + n_frames > 0x7FFFFFFF) return FF_ERR_INVALID;
   if (bits != 8 && bits != 12 && bits != 16) return FF_ERR_UNSUPPORTED;
@@ -309,11 +375,15 @@ int detect_impl(const void* frames, const void* halo, int64_t n_frames, int64_t 
   p.count_out = count_out;
   p.first_exit = first_exit;
   p.profile_out = profile_out;
-  const int row_bytes = (bits == 12) ? (width / 2 + 2) * 3 : width * (bits / 8);
-  p.raw_stride = (row_bytes + 3 + 15) & ~15;
+  p.raw_stride = detect_row_stride(width, bits);
+  *out = p;
+  return FF_OK;
+}
 
-  const size_t smem = (size_t)kDetectWarps * width * sizeof(int) + (size_t)kDetectWarps * 2 * p.raw_stride;
-  if (smem > 200 * 1024) return FF_ERR_UNSUPPORTED;  // W beyond ~5k columns: not a Photron sensor
+int launch_detect(const DetectParams& p, int bits, bool pdl, cudaStream_t st) {
+  if (p.partial == nullptr) return FF_ERR_INVALID;
+  const size_t smem = detect_warp_smem(p.width, bits) * kDetectWarps;
+  if (smem > 200 * 1024) return FF_ERR_UNSUPPORTED;  // W beyond ~3.5k columns: not a Photron sensor
   auto launch = [&](auto kern) -> int {
     if (smem > 48 * 1024)
       FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -322,16 +392,62 @@ int detect_impl(const void* frames, const void* halo, int64_t n_frames, int64_t 
     FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDetectWarps * 32, smem));
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int64_t blocks = (int64_t)sms * (occ > 0 ? occ : 1);
-    const int64_t enough = (n_frames + kDetectWarps - 1) / kDetectWarps;
+    const int64_t enough = ((int64_t)p.n_frames + kDetectWarps - 1) / kDetectWarps;
     if (blocks > enough) blocks = enough;
-    kern<<<(unsigned)blocks, kDetectWarps * 32, smem, st>>>(p);
-    FF_CUDA_TRY(cudaGetLastError());
-    return FF_OK;
+    return launch_kernel(kern, dim3((unsigned)blocks), dim3(kDetectWarps * 32), smem, st, pdl, p);
   };
   switch (bits) {
     case 8: return launch(detect_kernel<8>);
     case 12: return launch(detect_kernel<12>);
     default: return launch(detect_kernel<16>);
+  }
+}
+
+int detect_impl(const void* frames, const void* halo, int64_t n_frames, int64_t first_frame, int height,
+                int width, int bits, const int32_t* bg_dev, const int32_t* partial, int64_t min_signal_count,
+                int method, int use_frame_diff, int32_t diff_thr, int32_t threshold_floor, int32_t grad2_bound,
+                int32_t min_run_px, int32_t exit_margin_px, const uint8_t* skip, int32_t* pos_out,
+                int32_t* count_out, int32_t* first_exit, int32_t* profile_out, cudaStream_t st) {
+  DetectParams p{};
+  const int rc = make_detect_params(&p, frames, halo, n_frames, first_frame, height, width, bits, bg_dev, partial,
+                                    min_signal_count, method, use_frame_diff, diff_thr, threshold_floor, grad2_bound,
+                                    min_run_px, exit_margin_px, skip, pos_out, count_out, first_exit, profile_out);
+  if (rc != FF_OK) return rc;
+  return launch_detect(p, bits, false, st);
+}
+
+// Launches prep_kernel.  frame0 may be null (scalars known: only the first-exit word and the peers' acks).
+int prep_impl(const void* frame0, int height, int width, int bits, int32_t* scalars, uint16_t* centerline,
+              int want_stats, int32_t* first_exit, RangeWorkspace* ws, const RangeHooks& hooks, cudaStream_t st) {
+  if (height <= 0 || width <= 0) return FF_ERR_INVALID;
+  if (bits != 8 && bits != 12 && bits != 16) return FF_ERR_UNSUPPORTED;
+  const int64_t px = (int64_t)height * width;
+  if (bits == 12 && (px & 1)) return FF_ERR_UNSUPPORTED;
+  if (frame0 != nullptr && (scalars == nullptr || ws == nullptr)) return FF_ERR_INVALID;
+  if (frame0 == nullptr && first_exit == nullptr && hooks.table == nullptr) return FF_OK;      // nothing to do
+  if (want_stats && width > 4096) return FF_ERR_UNSUPPORTED;
+  PrepParams p{};
+  p.frame0 = static_cast<const uint8_t*>(frame0);
+  p.n_px = px;
+  p.height = height;
+  p.width = width;
+  p.scalars = scalars;
+  p.centerline = centerline;
+  p.want_stats = frame0 != nullptr && want_stats;
+  p.first_exit = first_exit;
+  p.ws = ws;
+  p.hooks = hooks;
+  int64_t blocks = 1;
+  if (frame0 != nullptr) {
+    blocks = (px + kPrepThreads * 32 - 1) / (kPrepThreads * 32);        // ~32 pixels per thread
+    if (blocks > kPrepMaxCtas) blocks = kPrepMaxCtas;
+    if (blocks < 1) blocks = 1;
+  }
+  const size_t smem = p.want_stats ? (size_t)width * 8 + kMaxLeaves * 8 + 8 + 2 * kMaxLeaves * 4 : 0;
+  switch (bits) {
+    case 8: return launch_kernel(prep_kernel<8>, dim3((unsigned)blocks), dim3(kPrepThreads), smem, st, false, p);
+    case 12: return launch_kernel(prep_kernel<12>, dim3((unsigned)blocks), dim3(kPrepThreads), smem, st, false, p);
+    default: return launch_kernel(prep_kernel<16>, dim3((unsigned)blocks), dim3(kPrepThreads), smem, st, false, p);
   }
 }
 

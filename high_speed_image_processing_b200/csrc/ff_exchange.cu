@@ -2,9 +2,9 @@
 //
 // The reference gathers pickled per-rank result lists on rank 0 and sorts them
 // (scripts/process_videos.py:1533-1541), and every MPI rank `break`s on its own exit frame
-// (:1494).  Here each rank's ff_detect writes straight into a RANGE BLOCK
+// (:1494).  Here each rank's range kernel writes straight into a RANGE BLOCK
 //
-//     int32 block[4 + 2*cap] = { first_exit, n_local, first_frame, epoch | pos[cap] | counts[cap] }
+//     int32 block[4 + 2*cap] = { first_exit, 0, 0, 0 | pos[cap] | counts[cap] }
 //
 // and ONE kernel per rank finishes the clip: global exit frame = min over the blocks' headers,
 // truncation against it (README.md:145-149), and de-padding of the per-rank arrays into the
@@ -12,27 +12,39 @@
 //
 //   gathered   the blocks were all-gathered into one local buffer by the process group
 //              (one NCCL all_gather_into_tensor; gloo in the CPU tests)       -> ff_merge_ranges
-//   peer       ff_exchange_*: the blocks stay where ff_detect wrote them; every rank maps its
-//              peers' blocks over NVLink (CUDA IPC) and the finishing kernel pulls them
-//              directly.  A monotonically increasing epoch written into each peer's flag row
-//              (st.release.sys / ld.acquire.sys) replaces the collective's barrier, and blocks
-//              are double-buffered so no second barrier is needed before the next step.
+//   peer       ff_exchange_*: the blocks stay where they were written; every rank maps its peers'
+//              exchange buffers over NVLink (CUDA IPC) and the finishing kernel pulls the blocks
+//              directly.  No collective and no barrier on the data path; the protocol is four
+//              kinds of words in every rank's buffer, all written with system-scope stores:
+//
+//       flags[r]  epoch of the latest block rank r has COMPLETED.  Written by the last CTA of
+//                 r's range kernel (range_tail) - the compute kernel publishes, not the merge.
+//       acks[r]   epoch of the latest merge rank r has finished, i.e. r no longer reads my
+//                 block of that epoch.  Blocks are double-buffered by epoch parity, so before
+//                 epoch e overwrites the block of e-2 the prep kernel waits for acks >= e-2.
+//       exit[2]   per epoch parity: min over ALL ranks of the exit frames seen so far in this
+//                 clip (red.min.sys from the detecting warps).  The host-streamed path polls it
+//                 between chunks and stops uploading frames that lie behind it - the
+//                 cross-rank form of the reference's `break` (:1494).  Reset by the merge.
+//       status    non-zero when a wait timed out.
+//
+//   The merge kernel depends on nothing but the flags, so it runs on a side stream while the
+//   main stream already streams the next clip: the exchange is off the critical path.
 #include <cstdlib>
 #include <cstring>
 #include <new>
 
-#include "ff_common.cuh"
+#include "ff_internal.h"
 
 namespace ff {
 namespace {
 
-constexpr int kMaxRanks = 64;
 constexpr int kHdr = 4;   // int32 header words per block
 
 struct MergeParams {
   const int32_t* gathered;            // [world][stride], or nullptr for the peer transport
-  const int32_t* peer[kMaxRanks];     // peer transport: block of rank r for this epoch
   int64_t stride;                     // int32 elements per block
+  int64_t slot_off;                   // peer transport: offset of this epoch's block in every buffer
   int64_t cap;                        // capacity (frames) of a block's pos / counts arrays
   int world;
   int rank;
@@ -41,21 +53,12 @@ struct MergeParams {
   int32_t* count_out;
   int32_t* first_exit_out;
   // peer transport only
-  int32_t* my_flags;                  // [world] epochs published to me
-  int32_t* peer_flags[kMaxRanks];     // flag rows of the peers (their my_flags)
+  const PeerTable* table;
   int32_t epoch;
-  int32_t* status;                    // device word: set non-zero if a peer never arrived
-  long long spin_limit;               // clock64 ticks before giving up
+  int publish;                        // this rank's flag is still to be written (block filled by hand)
+  unsigned int* ticket;               // CTAs of this kernel that are done (left zero)
+  long long spin_limit;
 };
-
-__device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
-  int32_t v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 // Owner rank and local offset of global frame i under contiguous_range(total, r, world):
 // the first total % world ranks hold one extra frame (src/photron/parallel.py:101-113).
@@ -76,32 +79,33 @@ __global__ void __launch_bounds__(256) merge_ranges_kernel(const MergeParams p) 
   __shared__ int s_fe;
   __shared__ int s_ok;
   const int tid = threadIdx.x;
+  const PeerTable* t = p.table;
+  if (tid == 0) s_ok = 1;
+  __syncthreads();
   if (PEER) {
-    // Publish: my block for this epoch is complete (ff_detect ran earlier on this stream).
-    if (blockIdx.x == 0 && tid < p.world) {
+    if (p.publish && blockIdx.x == 0 && tid < p.world) {
       __threadfence_system();
-      st_release_sys(p.peer_flags[tid] + p.rank, p.epoch);
+      st_release_sys(t->base[tid] + t->flags_off + p.rank, p.epoch);
     }
     // Arrive: wait until every rank has published this epoch to me.
-    if (tid == 0) s_ok = 1;
-    __syncthreads();
     if (tid < p.world) {
+      const int32_t* flag = t->base[p.rank] + t->flags_off + tid;
       const long long t0 = clock64();
-      while (ld_acquire_sys(p.my_flags + tid) < p.epoch) {
+      while (ld_acquire_sys(flag) < p.epoch) {
         if (clock64() - t0 > p.spin_limit) {
           s_ok = 0;
-          atomicExch(p.status, 1 + tid);
+          atomicExch(t->base[p.rank] + t->status_off, 1 + tid);
           break;
         }
       }
     }
     __syncthreads();
-    if (!s_ok) return;
   }
+  const bool ok = s_ok != 0;
   if (tid == 0) s_fe = FF_NO_EXIT;
   __syncthreads();
-  if (tid < p.world) {
-    const int32_t* b = PEER ? p.peer[tid] : p.gathered + (int64_t)tid * p.stride;
+  if (ok && tid < p.world) {
+    const int32_t* b = PEER ? t->base[tid] + p.slot_off : p.gathered + (int64_t)tid * p.stride;
     atomicMin(&s_fe, PEER ? __ldcv(b) : b[0]);
   }
   __syncthreads();
@@ -110,26 +114,71 @@ __global__ void __launch_bounds__(256) merge_ranges_kernel(const MergeParams p) 
 
   const int64_t base = p.total / p.world, extra = p.total % p.world;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < p.total; i += (int64_t)gridDim.x * blockDim.x) {
+    if (!ok) {               // a peer never arrived: defined outputs, the status word tells
+      p.pos_out[i] = FF_POS_NONE;
+      if (p.count_out != nullptr) p.count_out[i] = 0;
+      continue;
+    }
     int r;
     int64_t off;
     owner_of(i, base, extra, r, off);
-    const int32_t* b = PEER ? p.peer[r] : p.gathered + (int64_t)r * p.stride;
+    const int32_t* b = PEER ? t->base[r] + p.slot_off : p.gathered + (int64_t)r * p.stride;
     const int32_t* src_pos = b + kHdr + off;
     const int32_t* src_cnt = b + kHdr + p.cap + off;
     const int32_t v = PEER ? __ldcv(src_pos) : *src_pos;
     p.pos_out[i] = i >= fe ? FF_POS_DROPPED : v;
     if (p.count_out != nullptr) p.count_out[i] = PEER ? __ldcv(src_cnt) : *src_cnt;
   }
+  if (PEER) {
+    // last CTA: nobody writes this epoch's exit word any more (every rank has published) - reset it
+    // for epoch + 2 - and tell the peers that their blocks of this epoch are no longer read here.
+    __shared__ int s_last;
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+      if (tid == 0) {
+        *p.ticket = 0;
+        t->base[p.rank][t->exit_off + (p.epoch & 1)] = FF_NO_EXIT;
+      }
+      __syncthreads();
+      if (tid < p.world) {
+        __threadfence_system();
+        st_release_sys(t->base[tid] + t->acks_off + p.rank, p.epoch);
+      }
+    }
+  }
+}
+
+// Block filled by hand (results that came back from somewhere else): wait for the peers' acks and
+// reset the header (what prep_kernel does for ff_process_range) / publish the finished block.
+__global__ void publish_kernel(const RangeHooks h) {
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const PeerTable* t = h.table;
+    for (int r = 0; r < h.world; ++r) st_release_sys(t->base[r] + t->flags_off + h.rank, h.epoch);
+  }
 }
 
 int merge_grid(int64_t total) {
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > 148) blocks = 148;
+  int64_t blocks = (total + 2047) / 2048;
+  if (blocks > 32) blocks = 32;       // few CTAs: this kernel shares the GPU with the next clip's range kernel
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
 
 }  // namespace
+
+int publish_impl(const RangeHooks& hooks, cudaStream_t st) {
+  if (hooks.table == nullptr) return FF_OK;
+  publish_kernel<<<1, 32, 0, st>>>(hooks);
+  FF_CUDA_TRY(cudaGetLastError());
+  return FF_OK;
+}
+
 }  // namespace ff
 
 using namespace ff;
@@ -139,15 +188,40 @@ struct ff_exchange {
   int device = 0, rank = 0, world = 1;
   int64_t cap = 0;                 // frames per block
   int64_t stride = 0;              // int32 elements per block
-  // one cudaMalloc: [block slot 0 | block slot 1 | flags[kMaxRanks] | status | no_exit constant]
+  // one cudaMalloc, mapped by the peers: [block slot 0 | block slot 1 | flags[kMaxRanks] | acks[kMaxRanks] |
+  //                                       exit[2] pad | status | ticket ...]
   int32_t* local = nullptr;
-  int64_t flags_off = 0, status_off = 0, const_off = 0, alloc_elems = 0;
+  int64_t flags_off = 0, acks_off = 0, exit_off = 0, status_off = 0, ticket_off = 0, alloc_elems = 0;
   int32_t* peer_base[kMaxRanks] = {nullptr};
   bool opened[kMaxRanks] = {false};
   bool peers_ready = false;
+  PeerTable* table_dev = nullptr;  // local device memory
   int32_t epoch = 0;               // epoch of the block handed out last
   int32_t* status_host = nullptr;  // pinned readback
+  long long spin_limit = 0;
 };
+
+static int upload_table(ff_exchange* x) {
+  PeerTable t{};
+  for (int r = 0; r < x->world; ++r) t.base[r] = x->peer_base[r];
+  t.flags_off = x->flags_off;
+  t.acks_off = x->acks_off;
+  t.exit_off = x->exit_off;
+  t.status_off = x->status_off;
+  FF_CUDA_TRY(cudaMemcpy(x->table_dev, &t, sizeof(t), cudaMemcpyHostToDevice));
+  return FF_OK;
+}
+
+static RangeHooks hooks_of(const ff_exchange* x, int flags) {
+  RangeHooks h{};
+  h.table = x->table_dev;
+  h.epoch = x->epoch;
+  h.world = x->world;
+  h.rank = x->rank;
+  h.flags = flags;
+  h.spin_limit = x->spin_limit;
+  return h;
+}
 
 extern "C" {
 
@@ -191,22 +265,38 @@ int ff_exchange_create(int device, int rank, int world, int64_t cap_frames, ff_e
   x->cap = cap_frames;
   x->stride = (kHdr + 2 * cap_frames + 3) & ~(int64_t)3;      // keep slot 1 16-byte aligned
   x->flags_off = 2 * x->stride;
-  x->status_off = x->flags_off + kMaxRanks;
-  x->const_off = x->status_off + 4;
-  x->alloc_elems = x->const_off + 4;
+  x->acks_off = x->flags_off + kMaxRanks;
+  x->exit_off = x->acks_off + kMaxRanks;
+  x->status_off = x->exit_off + 4;
+  x->ticket_off = x->status_off + 4;
+  x->alloc_elems = x->ticket_off + 4;
+  // A peer that never arrives must not hang the GPU for ever: give up after FF_EXCHANGE_TIMEOUT_S
+  // seconds (default 20; ranks may legitimately reach a step seconds apart, e.g. after file I/O).
+  const char* env_t = getenv("FF_EXCHANGE_TIMEOUT_S");
+  const double timeout_s = env_t ? atof(env_t) : 20.0;
+  int khz = 1900000;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);       // clock64 ticks at the SM clock
+  x->spin_limit = (long long)((timeout_s > 0.01 ? timeout_s : 0.01) * 1e3 * (double)(khz > 0 ? khz : 1900000));
   cudaError_t e = cudaMalloc(&x->local, sizeof(int32_t) * (size_t)x->alloc_elems);
   if (e == cudaSuccess) e = cudaMemset(x->local, 0, sizeof(int32_t) * (size_t)x->alloc_elems);
-  const int32_t no_exit = FF_NO_EXIT;
-  if (e == cudaSuccess) e = cudaMemcpy(x->local + x->const_off, &no_exit, sizeof(no_exit), cudaMemcpyHostToDevice);
+  const int32_t no_exit[2] = {FF_NO_EXIT, FF_NO_EXIT};
+  if (e == cudaSuccess) e = cudaMemcpy(x->local + x->exit_off, no_exit, sizeof(no_exit), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&x->table_dev, sizeof(PeerTable));
   if (e == cudaSuccess) e = cudaMallocHost(&x->status_host, sizeof(int32_t));
   if (e != cudaSuccess) {
     set_cuda_error(e, "ff_exchange_create");
     if (x->local) cudaFree(x->local);
+    if (x->table_dev) cudaFree(x->table_dev);
     delete x;
     return FF_ERR_CUDA;
   }
   *x->status_host = 0;
   x->peer_base[rank] = x->local;
+  if (world == 1) {
+    x->peers_ready = true;
+    const int rc = upload_table(x);
+    if (rc != FF_OK) return rc;
+  }
   *out = x;
   return FF_OK;
 }
@@ -235,38 +325,57 @@ int ff_exchange_open_peers(ff_exchange* x, const void* handles) {
     x->peer_base[r] = static_cast<int32_t*>(ptr);
     x->opened[r] = true;
   }
+  const int rc = upload_table(x);
+  if (rc != FF_OK) return rc;
   x->peers_ready = true;
   return FF_OK;
 }
 
 int ff_exchange_begin(ff_exchange* x, int32_t** pos_dev, int32_t** count_dev, int32_t** first_exit_dev,
-                      void* stream) {
+                      ff_range_hooks* hooks_out) {
   if (x == nullptr || pos_dev == nullptr || count_dev == nullptr || first_exit_dev == nullptr) return FF_ERR_INVALID;
-  FF_CUDA_TRY(cudaSetDevice(x->device));
+  if (!x->peers_ready) return FF_ERR_INVALID;
   x->epoch += 1;
   int32_t* blk = x->local + (int64_t)(x->epoch & 1) * x->stride;
-  FF_CUDA_TRY(cudaMemcpyAsync(blk, x->local + x->const_off, sizeof(int32_t), cudaMemcpyDeviceToDevice,
-                              static_cast<cudaStream_t>(stream)));
   *first_exit_dev = blk;
   *pos_dev = blk + kHdr;
   *count_dev = blk + kHdr + x->cap;
+  if (hooks_out != nullptr) {
+    hooks_out->table_dev = x->table_dev;
+    hooks_out->epoch = x->epoch;
+    hooks_out->world = x->world;
+    hooks_out->rank = x->rank;
+    hooks_out->flags = FF_HOOK_WAIT | FF_HOOK_PUBLISH;
+    hooks_out->spin_limit = x->spin_limit;
+    hooks_out->exit_word_dev = x->local + x->exit_off + (x->epoch & 1);
+  }
   return FF_OK;
+}
+
+int ff_exchange_acquire(ff_exchange* x, void* stream) {
+  if (x == nullptr || x->epoch < 1) return FF_ERR_INVALID;
+  FF_CUDA_TRY(cudaSetDevice(x->device));
+  int32_t* blk = x->local + (int64_t)(x->epoch & 1) * x->stride;
+  return prep_impl(nullptr, 1, 1, 8, nullptr, nullptr, 0, blk, nullptr, hooks_of(x, FF_HOOK_WAIT),
+                   static_cast<cudaStream_t>(stream));
+}
+
+int ff_exchange_publish(ff_exchange* x, void* stream) {
+  if (x == nullptr || x->epoch < 1) return FF_ERR_INVALID;
+  FF_CUDA_TRY(cudaSetDevice(x->device));
+  return publish_impl(hooks_of(x, FF_HOOK_PUBLISH), static_cast<cudaStream_t>(stream));
 }
 
 int ff_exchange_finish(ff_exchange* x, int64_t total_frames, int32_t* pos_out_dev, int32_t* count_out_dev,
                        int32_t* first_exit_out_dev, void* stream) {
   if (x == nullptr || pos_out_dev == nullptr || first_exit_out_dev == nullptr) return FF_ERR_INVALID;
-  if (!x->peers_ready && x->world > 1) return FF_ERR_INVALID;
+  if (!x->peers_ready) return FF_ERR_INVALID;
   if (x->epoch < 1 || total_frames < 0) return FF_ERR_INVALID;
   if ((total_frames + x->world - 1) / x->world > x->cap) return FF_ERR_INVALID;
   FF_CUDA_TRY(cudaSetDevice(x->device));
   MergeParams p{};
   p.gathered = nullptr;
-  const int64_t slot = (int64_t)(x->epoch & 1) * x->stride;
-  for (int r = 0; r < x->world; ++r) {
-    p.peer[r] = x->peer_base[r] + slot;
-    p.peer_flags[r] = x->peer_base[r] + x->flags_off;
-  }
+  p.slot_off = (int64_t)(x->epoch & 1) * x->stride;
   p.stride = x->stride;
   p.cap = x->cap;
   p.world = x->world;
@@ -275,14 +384,11 @@ int ff_exchange_finish(ff_exchange* x, int64_t total_frames, int32_t* pos_out_de
   p.pos_out = pos_out_dev;
   p.count_out = count_out_dev;
   p.first_exit_out = first_exit_out_dev;
-  p.my_flags = x->local + x->flags_off;
+  p.table = x->table_dev;
   p.epoch = x->epoch;
-  p.status = x->local + x->status_off;
-  // A peer that never arrives must not hang the GPU for ever: give up after FF_EXCHANGE_TIMEOUT_S
-  // seconds (default 20; ranks may legitimately reach this step seconds apart, e.g. after file I/O).
-  const char* env_t = getenv("FF_EXCHANGE_TIMEOUT_S");
-  const double timeout_s = env_t ? atof(env_t) : 20.0;
-  p.spin_limit = (long long)((timeout_s > 0.01 ? timeout_s : 0.01) * 1.9e9);
+  p.publish = 0;
+  p.ticket = reinterpret_cast<unsigned int*>(x->local + x->ticket_off);
+  p.spin_limit = x->spin_limit;
   merge_ranges_kernel<true><<<merge_grid(total_frames), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   FF_CUDA_TRY(cudaGetLastError());
   return FF_OK;
@@ -293,6 +399,7 @@ int ff_exchange_status(ff_exchange* x, int32_t* status_out, void* stream) {
   FF_CUDA_TRY(cudaSetDevice(x->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   FF_CUDA_TRY(cudaMemcpyAsync(x->status_host, x->local + x->status_off, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  FF_CUDA_TRY(cudaMemsetAsync(x->local + x->status_off, 0, sizeof(int32_t), st));     // reported once
   FF_CUDA_TRY(cudaStreamSynchronize(st));
   *status_out = *x->status_host;
   return FF_OK;
@@ -304,6 +411,7 @@ int ff_exchange_destroy(ff_exchange* x) {
   for (int r = 0; r < x->world; ++r)
     if (x->opened[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
   if (x->local) cudaFree(x->local);
+  if (x->table_dev) cudaFree(x->table_dev);
   if (x->status_host) cudaFreeHost(x->status_host);
   delete x;
   return FF_OK;

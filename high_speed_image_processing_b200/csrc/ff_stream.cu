@@ -18,7 +18,7 @@
 // (scripts/process_videos.py:670-674, :397-399, :759), so results are bit-exact.
 #include <cstdlib>
 
-#include "ff_common.cuh"
+#include "ff_detect_core.cuh"
 
 namespace ff {
 namespace {
@@ -40,6 +40,12 @@ struct StreamParams {
   int32_t* partial;
   void* diff_out;
   uint16_t* decoded_out;
+  int idle_ns;             // how long an idle detector warp sleeps between looks at the queue
+  int stats;               // diagnostics (FF_RANGE_STATS=1): detector warps add their cycle counters to ws->stats
+  int slab_shift;          // range_kernel: 2^slab_shift consecutive items per slab (slabs are dealt to the CTAs round-robin)
+  int slab_step_frames;    // (gridDim.x << slab_shift) = slab_step_frames * tiles_per_frame + slab_step_tiles:
+  int slab_step_tiles;     // how far (frame, tile) moves from one slab of a CTA to its next
+  int pdl;                 // host side only: launch with the programmatic-dependent-launch attribute
 };
 
 template <int BITS>
@@ -134,6 +140,7 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const StreamParams p) 
   __syncthreads();
 
   int bg = 0, cthr = 0;
+  griddep_wait();                      // the background scalar may come from the kernel right before this one
   if (COUNT || DIFF != FF_DIFF_NONE) {
     bg = __ldg(p.bg_dev);
     const int ethr = p.empty_thr >= 0 ? p.empty_thr : max(10, bg >> 1);
@@ -417,6 +424,7 @@ __global__ void __launch_bounds__(kCountThreads) count12_kernel(const StreamPara
   }
 
   // ---- consumers ---------------------------------------------------------------------------------
+  griddep_wait();                      // the background scalar may come from the kernel right before this one
   const int bg = __ldg(p.bg_dev);
   const int ethr = p.empty_thr >= 0 ? p.empty_thr : max(10, bg >> 1);
   const uint32_t c = (uint32_t)min((int64_t)bg + ethr, (int64_t)kMaxPx);       // no pixel exceeds kMaxPx
@@ -497,8 +505,343 @@ int launch_count12(StreamParams p, cudaStream_t st) {
   p.items_per_cta = (total_work + wave - 1) / wave;
   if (p.items_per_cta < 1) p.items_per_cta = 1;
   const int64_t grid = (total_work + p.items_per_cta - 1) / p.items_per_cta;
-  kern<<<(unsigned)grid, kCountThreads, kSmem, st>>>(p);
-  FF_CUDA_TRY(cudaGetLastError());
+  return launch_kernel(kern, dim3((unsigned)grid), dim3(kCountThreads), kSmem, st, p.pdl != 0, p);
+}
+
+// ---- the whole range in ONE kernel: counts + empty-frame decision + detection + exit min + truncation ----
+// count12_kernel's ring and compare, plus:
+//   * the (frame, tile) items, in frame-major order, are cut into SLABS of 2^k consecutive items and the
+//     slabs are dealt to the CTAs round-robin: all CTAs sweep through the clip together (a sliding window of
+//     a few MB over all DRAM channels) and - what matters - the frames that hold a flame, which are
+//     consecutive in time, are spread over ALL CTAs instead of landing in a handful of them;
+//   * a SEGMENT is the part of a slab that lies in one frame.  Every consumer warp keeps the above-noise
+//     count of its segment and adds it to the segment's word in SHARED memory ({warps arrived | count}, one
+//     shared-memory atomic per warp and segment - not one partial-count store per warp and tile).  The warp
+//     that arrives last hands (frame, count) to the CTA's DETECTOR WARP through a shared-memory queue.
+//     Consumers never touch global memory besides the tiles: a global atomic whose result is needed costs
+//     1.5-3 us under a saturated memory system, and putting it into the streaming loop (first version)
+//     slowed the kernel by 20-150 %;
+//   * the detector warp (warp 9) drains the queue, up to 32 segments at once, one per lane: it adds
+//     {1 segment, count} to the frame's 64-bit word in global memory; the lane whose segment completes
+//     the frame knows the frame's count, writes count_out and decides is_empty_frame
+//     (scripts/process_videos.py:759-763).  Non-empty frames are then resolved by the whole warp
+//     (detect_one_frame) - all of it while the consumers keep streaming;
+//   * the detector warp of the CTA that finishes last truncates the range at its first exit frame and
+//     publishes the block to the peers of a range-sharded run (range_tail).
+// No partial-count array, no detect / truncate launches; the frames are still read from HBM exactly once
+// (the two centre rows a detection needs come back through L2: 3 KB per flame frame).
+constexpr int kDetWarps = 4;                              // detector warps per CTA (a detection is a chain of latencies: ~30 us)
+constexpr int kFusedThreads = kThreads + 32 + 32 * kDetWarps;   // 8 consumer warps + producer warp + detector warps
+constexpr int kQueue = 128;                               // (frame, count) entries waiting for the detector warps
+constexpr int kSegRing = 16;                              // segment words in flight (warps drift < ring depth items apart)
+
+template <int BITS, int kCountStages>
+__global__ void __launch_bounds__(kFusedThreads) range_kernel(const StreamParams p, const DetectParams d) {
+  constexpr int kTileBytes = 4 * kThreads * BITS;
+  constexpr int kMaxPx = BITS == 8 ? 255 : (BITS == 12 ? 4095 : 65535);
+  static_assert(kCountStages < kSegRing, "segment ring must outlast the tile ring");
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kCountStages * kTileBytes);
+  uint64_t* empty = full + kCountStages;
+  volatile int* q_f = reinterpret_cast<volatile int*>(empty + kCountStages);   // queue: frame (-1 = slot empty) ...
+  volatile int* q_cnt = q_f + kQueue;                                           // ... and the segment's count
+  int* q_ctl = const_cast<int*>(q_cnt) + kQueue;          // [0] entries claimed, [1] consumer warps done, [2] detector warps done,
+                                                          // [4 + w] next entry of detector warp w (entry e belongs to warp e % kDetWarps)
+  unsigned* seg = reinterpret_cast<unsigned*>(q_ctl + 4 + kDetWarps);           // [kSegRing] {warps arrived : 8 | count : 24}
+  uint8_t* det_smem = reinterpret_cast<uint8_t*>(seg + kSegRing);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kCountStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kWarpsPerCta);
+    }
+    fence_mbar_init();
+    q_ctl[0] = q_ctl[1] = q_ctl[2] = 0;
+    for (int w = 0; w < kDetWarps; ++w) q_ctl[4 + w] = w;
+  }
+  if (tid < kQueue) q_f[tid] = -1;
+  if (tid < kSegRing) seg[tid] = 0;
+  __syncthreads();
+
+  const int T = p.tiles_per_frame;
+  const int sh = p.slab_shift;
+  const int64_t S = (int64_t)1 << sh;
+  const int64_t total_work = (int64_t)T * p.n_frames;
+  const int64_t n_slabs = (total_work + S - 1) >> sh;        // gridDim.x <= n_slabs: every CTA has work
+  const int64_t groups_per_frame = p.px_per_frame / kGroupPx;
+  // (frame, tile) of this CTA's first slab; later slabs are reached by stepping - no divisions in the loops
+  int f0, tile0;
+  {
+    const uint32_t first = (uint32_t)((int64_t)blockIdx.x << sh);   // < 2^31, see the launcher
+    f0 = (int)(first / (uint32_t)T);
+    tile0 = (int)(first - (uint32_t)f0 * (uint32_t)T);
+  }
+
+  if (warp == kWarpsPerCta) {            // ---- producer: one elected lane drives the TMA ring
+    if (lane == 0) {
+      const uint64_t policy = policy_evict_first();
+      uint32_t it = 0;
+      int fs = f0, ts = tile0;
+      for (int64_t slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
+        const int64_t i0 = slab << sh, i1 = min(i0 + S, total_work);
+        int64_t f = fs;
+        int tile = ts;
+        fs += p.slab_step_frames;
+        ts += p.slab_step_tiles;
+        if (ts >= T) { ts -= T; ++fs; }
+        for (int64_t i = i0; i < i1; ++i, ++it) {
+          const int s = it % kCountStages;
+          mbar_wait(&empty[s], ((it / kCountStages) & 1) ^ 1);   // first pass: fresh barriers pass at once
+          const int64_t g0 = (int64_t)tile * (4 * kThreads);
+          const uint32_t bytes = (uint32_t)min((int64_t)(4 * kThreads), groups_per_frame - g0) * (uint32_t)BITS;
+          mbar_arrive_expect_tx(&full[s], bytes);
+          bulk_g2s(smem + s * kTileBytes, p.frames + f * p.frame_bytes + (int64_t)tile * kTileBytes, bytes, &full[s], policy);
+          if (++tile == T) { tile = 0; ++f; }
+        }
+      }
+    }
+    return;
+  }
+
+  griddep_wait();                        // scalars, first-exit word and workspace come from prep_kernel
+  const int bg_raw = __ldg(p.bg_dev);
+
+  if (warp > kWarpsPerCta) {             // ---- detector warps
+    const int dw = warp - kWarpsPerCta - 1;
+    const int thr_floor = d.threshold_dev != nullptr ? __ldg(d.threshold_dev) : d.threshold_floor;
+    const RowSpan rs = centre_row_span<BITS>(d.height, d.width);
+    uint8_t* mine = det_smem + (size_t)dw * detect_warp_smem(d.width, BITS);
+    int* prof = reinterpret_cast<int*>(mine);
+    uint8_t* raw_cur = mine + (size_t)d.width * sizeof(int);
+    uint8_t* raw_pri = raw_cur + d.raw_stride;
+    unsigned long long* arrive = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(d.ws) + kWorkspaceHeader);
+    volatile int* ctl = q_ctl;
+    const unsigned full_mask = 0xFFFFFFFFu;
+    int head = dw;                       // my next entry; mine are dw, dw + kDetWarps, ...
+    // An idle detector warp must not poll often: 8 of them per SM looking at the queue every 100 ns took 17 % of
+    // the issue slots from the consumers (C2 step 0.619 -> 0.584 ms).  Back off while idle, be quick after work.
+    int idle_ns = 250;
+    long long t_atom = 0, t_det = 0, t_done = 0, n_det = 0, n_iter = 0;
+    for (;;) {
+      if (p.stats && t_done == 0 && ctl[1] == kWarpsPerCta) t_done = clock64();
+      // the leading run of my filled queue slots, one per lane (kQueue / kDetWarps = 32 of mine fit the ring)
+      const int slot = (head + lane * kDetWarps) % kQueue;
+      const int fq = q_f[slot];
+      const unsigned ready = __ballot_sync(full_mask, fq >= 0);
+      const int n = __ffs((int)~ready) - 1;               // number of leading ones (-1: all 32)
+      const int take = n < 0 ? 32 : n;
+      if (take == 0) {
+        int stop = 0;
+        if (lane == 0) stop = ctl[1] == kWarpsPerCta && ctl[0] <= head;     // consumers done, nothing of mine claimed
+        if (__shfl_sync(full_mask, stop, 0)) break;
+        __nanosleep(idle_ns);
+        idle_ns = min(2 * idle_ns, p.idle_ns);
+        continue;
+      }
+      idle_ns = 250;
+      bool need = false;
+      const long long ta = p.stats ? clock64() : 0;
+      ++n_iter;
+      if (lane < take) {
+        const int cnt = q_cnt[slot];
+        q_f[slot] = -1;
+        // this segment joins its frame: the lane that completes the frame owns the frame's decision
+        const int64_t s_lo = ((int64_t)fq * T) >> sh, s_hi = ((int64_t)(fq + 1) * T - 1) >> sh;
+        const unsigned expected = (unsigned)(s_hi - s_lo + 1);
+        unsigned long long* word = arrive + (int64_t)fq * kArriveStride;
+        unsigned long long old = 0;
+        if (expected > 1) old = atomicAdd(word, (1ull << 32) | (unsigned)cnt);     // (a frame inside one slab needs no word)
+        if ((unsigned)(old >> 32) + 1u == expected) {
+          if (expected > 1) *word = 0;                     // left zero for the next launch
+          const int total = (int)((unsigned)old + (unsigned)cnt);
+          if (d.count_out != nullptr) d.count_out[fq] = total;
+          const bool skipped = d.skip != nullptr && d.skip[fq] != 0;
+          need = !skipped && (int64_t)total >= d.min_signal_count;
+          if (!need) d.pos_out[fq] = FF_POS_NONE;
+        }
+      }
+      head += take * kDetWarps;
+      __syncwarp();
+      if (lane == 0) ctl[4 + dw] = head;                   // my slots may be refilled
+      unsigned pending = __ballot_sync(full_mask, need);
+      const long long tb = p.stats ? clock64() : 0;
+      t_atom += tb - ta;
+      n_det += __popc(pending);
+      while (pending) {
+        const int src = __ffs((int)pending) - 1;
+        pending &= pending - 1;
+        const int f = __shfl_sync(full_mask, fq, src);
+        const int pos = detect_one_frame<BITS>(d, rs, f, false, bg_raw, thr_floor, prof, raw_cur, raw_pri, lane);
+        if (lane == 0) commit_position(d, f, pos);
+      }
+      if (p.stats) t_det += clock64() - tb;
+    }
+    if (p.stats && lane == 0) {
+      unsigned long long* st = d.ws->stats;
+      atomicAdd(st + 0, (unsigned long long)t_atom);
+      atomicAdd(st + 1, (unsigned long long)t_det);
+      atomicAdd(st + 2, (unsigned long long)n_det);
+      atomicAdd(st + 3, (unsigned long long)n_iter);
+      atomicMax(st + 4, (unsigned long long)(t_done ? clock64() - t_done : 0));     // longest tail behind the consumers
+      atomicMax(st + 5, (unsigned long long)t_det);
+      atomicMax(st + 6, (unsigned long long)t_atom);
+    }
+    // the detector warp that leaves last finishes the CTA's part of the range
+    int last = 0;
+    if (lane == 0) {
+      __threadfence();
+      last = atomicAdd(q_ctl + 2, 1) == kDetWarps - 1;
+    }
+    if (__shfl_sync(full_mask, last, 0)) range_tail(d, lane);
+    return;
+  }
+
+  // ---- consumers ---------------------------------------------------------------------------------
+  const int ethr = p.empty_thr >= 0 ? p.empty_thr : max(10, bg_raw >> 1);
+  const uint32_t c = (uint32_t)min((int64_t)bg_raw + ethr, (int64_t)kMaxPx);       // no pixel exceeds kMaxPx
+  const uint32_t kA = BITS == 12 ? ((c << 4) | 15u) : c;
+  const uint32_t kA2 = kA * 0x00010001u;
+  const uint32_t nkA2 = ((0x10000u - kA) & 0xFFFFu) * 0x00010001u;
+  const uint32_t nc2 = ((0x10000u - c) & 0xFFFFu) * 0x00010001u;
+  const int my_group = tid * 4;
+
+  uint32_t it = 0;
+  unsigned seg_no = 0;                   // segments this warp has finished (the same sequence in every warp)
+  int fs = f0, ts = tile0;
+  for (int64_t slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
+    const int64_t i0 = slab << sh, i1 = min(i0 + S, total_work);
+    int f = fs;
+    int tile = ts;
+    fs += p.slab_step_frames;
+    ts += p.slab_step_tiles;
+    if (ts >= T) { ts -= T; ++fs; }
+    int wcnt = 0;
+    for (int64_t i = i0; i < i1; ++i, ++it) {
+      const int s = it % kCountStages;
+      mbar_wait(&full[s], (it / kCountStages) & 1);
+      const int tile_groups = (int)min((int64_t)(4 * kThreads), groups_per_frame - (int64_t)tile * (4 * kThreads));
+      uint32_t acc = 0;
+      if (BITS == 12) {
+        if (my_group < tile_groups) {        // groups per frame are a multiple of 4: all four or none
+          const uint4* qq = reinterpret_cast<const uint4*>(smem + s * kTileBytes + tid * 48);
+          const uint4 q0 = qq[0], q1 = qq[1], q2 = qq[2];
+          acc = count12x8_simd(q0.x, q0.y, q0.z, kA2, nkA2, nc2) + count12x8_simd(q0.w, q1.x, q1.y, kA2, nkA2, nc2) +
+                count12x8_simd(q1.z, q1.w, q2.x, kA2, nkA2, nc2) + count12x8_simd(q2.y, q2.z, q2.w, kA2, nkA2, nc2);
+        }
+      } else {
+        const uint32_t one2 = 0x00010001u;
+        const int pieces = tile_groups * BITS / 16;                      // 16-byte pieces in this tile
+        const uint4* qq = reinterpret_cast<const uint4*>(smem + s * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kTileBytes / 16 / kThreads; ++k) {
+          const int j0 = tid + k * kThreads;
+          if (j0 < pieces) {
+            const uint4 v = qq[j0];
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (BITS == 16) {
+                acc += __viaddmin_u16x2(__vimax3_u16x2(w4[j], kA2, kA2), nkA2, one2);
+              } else {
+                acc += __viaddmin_s16x2_relu(__byte_perm(w4[j], 0u, 0x4140), nc2, one2) +
+                       __viaddmin_s16x2_relu(__byte_perm(w4[j], 0u, 0x4342), nc2, one2);
+              }
+            }
+          }
+        }
+      }
+      int cnt = (int)(acc & 0xFFFFu) + (int)(acc >> 16);
+      cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);      // also orders every lane's smem reads before the release
+      const bool last_of_frame = tile + 1 == T;
+      if (lane == 0) {
+        mbar_arrive(&empty[s]);
+        wcnt += cnt;
+        if (last_of_frame || i + 1 == i1) {           // the segment ends: leaving the frame, or the slab
+          unsigned* word = seg + (seg_no & (kSegRing - 1));
+          ++seg_no;
+          const unsigned old = atomicAdd(word, (1u << 24) | (unsigned)wcnt);
+          if ((old >> 24) == kWarpsPerCta - 1) {      // last warp of the CTA: the segment goes to the detector warp
+            *word = 0;
+            const int total = (int)((old & 0xFFFFFFu) + (unsigned)wcnt);
+            const int slot = atomicAdd(q_ctl, 1);
+            while (slot - ((volatile int*)q_ctl)[4 + slot % kDetWarps] >= kQueue) __nanosleep(64);
+            q_cnt[slot % kQueue] = total;
+            __threadfence_block();
+            q_f[slot % kQueue] = f;
+          }
+          wcnt = 0;
+        }
+      }
+      if (last_of_frame) { tile = 0; ++f; } else { ++tile; }
+    }
+  }
+  if (lane == 0) {
+    __threadfence_block();
+    atomicAdd(q_ctl + 1, 1);
+  }
+}
+
+template <int BITS, int kCountStages>
+int launch_range_fused(StreamParams p, const DetectParams& d, cudaStream_t st) {
+  const size_t smem = (size_t)kCountStages * (4 * kThreads * BITS) + 2 * kCountStages * 8 + 2 * kQueue * 4 +
+                      (4 + kDetWarps) * 4 + kSegRing * 4 + kDetWarps * detect_warp_smem(d.width, BITS);
+  auto kern = range_kernel<BITS, kCountStages>;
+  // launch configuration per device, recomputed only when the frame width (detector smem) changes
+  static std::mutex m;
+  static size_t have_smem[64] = {};
+  static int have_occ[64] = {};
+  int dev = 0, occ = 0;
+  FF_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return FF_ERR_INVALID;
+  {
+    std::lock_guard<std::mutex> g(m);
+    if (have_smem[dev] != smem) {
+      FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kFusedThreads, smem));
+      int cap = kCountCtasPerSm;             // bytes in flight per SM: see launch_count12
+      if (const char* e = getenv("FF_COUNT12_CTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;   // tuning knob
+      if (occ > cap) occ = cap;
+      if (occ < 1) occ = 1;
+      have_occ[dev] = occ;
+      have_smem[dev] = smem;
+    }
+    occ = have_occ[dev];
+  }
+  const int64_t wave = (int64_t)sm_count_cached() * occ;
+  const int64_t total_work = (int64_t)p.tiles_per_frame * p.n_frames;
+  // slab size: as large as possible (fewer segments per frame, longer contiguous reads) while every CTA
+  // still gets >= 64 slabs, which bounds the imbalance of the round-robin deal to 1.6 %
+  int64_t slab = total_work / (wave * 64);
+  static const int slab_env = getenv("FF_RANGE_SLAB") ? atoi(getenv("FF_RANGE_SLAB")) : 0;       // tuning knob
+  if (slab_env > 0) slab = slab_env;
+  if (slab > 32 && slab_env <= 0) slab = 32;
+  if (slab < 1) slab = 1;
+  int shift = 0;
+  while ((2ll << shift) <= slab) ++shift;                  // largest power of two <= slab
+  p.slab_shift = shift;
+  p.stats = getenv("FF_RANGE_STATS") != nullptr;
+  static const int idle_env = getenv("FF_RANGE_IDLE_NS") ? atoi(getenv("FF_RANGE_IDLE_NS")) : 0;     // tuning knob
+  p.idle_ns = idle_env > 0 ? idle_env : 4000;
+  const int64_t n_slabs = (total_work + (1ll << shift) - 1) >> shift;
+  const int64_t grid = n_slabs < wave ? n_slabs : wave;
+  if ((grid << shift) > 0x7FFFFFFFll) return FF_ERR_UNSUPPORTED;
+  p.slab_step_frames = (int)((grid << shift) / p.tiles_per_frame);
+  p.slab_step_tiles = (int)((grid << shift) % p.tiles_per_frame);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kFusedThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  FF_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p, d));
   return FF_OK;
 }
 
@@ -575,6 +918,7 @@ __global__ void __launch_bounds__(kOutThreads) streamx_kernel(const StreamParams
   uint32_t nc2 = 0, nbg2 = 0, k2 = 0, c2 = 0, bg2 = 0, t2 = 0;
   int tm1 = 0;
   const uint32_t one2 = 0x00010001u;
+  if (!producer) griddep_wait();       // the background scalar may come from the kernel right before this one
   if (!producer && (COUNT || DIFF)) {
     bg = min(__ldg(p.bg_dev), kMaxPx);                   // a larger bg zeroes everything anyway
     const int ethr = p.empty_thr >= 0 ? p.empty_thr : max(10, __ldg(p.bg_dev) >> 1);
@@ -727,9 +1071,7 @@ int launch_streamx(StreamParams p, int ctas_cap, cudaStream_t st) {
   p.items_per_cta = (total_work + wave - 1) / wave;
   if (p.items_per_cta < 1) p.items_per_cta = 1;
   const int64_t grid = (total_work + p.items_per_cta - 1) / p.items_per_cta;
-  kern<<<(unsigned)grid, kOutThreads, kSmem, st>>>(p);
-  FF_CUDA_TRY(cudaGetLastError());
-  return FF_OK;
+  return launch_kernel(kern, dim3((unsigned)grid), dim3(kOutThreads), kSmem, st, p.pdl != 0, p);
 }
 
 template <int BITS, bool COUNT, bool DIFF, bool DECODED>
@@ -850,9 +1192,7 @@ int launch_stream(StreamParams p, cudaStream_t st) {
   if (p.items_per_cta < 1) p.items_per_cta = 1;
   const int64_t grid = (total_work + p.items_per_cta - 1) / p.items_per_cta;
   if (grid > 0x7FFFFFFF) return FF_ERR_UNSUPPORTED;
-  kern<<<(unsigned)grid, kThreads, kSmem, st>>>(p);
-  FF_CUDA_TRY(cudaGetLastError());
-  return FF_OK;
+  return launch_kernel(kern, dim3((unsigned)grid), dim3(kThreads), kSmem, st, p.pdl != 0, p);
 }
 
 template <int BITS, bool COUNT, int DIFF, bool DECODED>
@@ -909,10 +1249,46 @@ int dispatch_generic(const StreamParams& p, int diff, cudaStream_t st) {
 
 }  // namespace
 
+// True when a range with these outputs runs as ONE kernel (range_kernel): counts-only work on the TMA path.
+bool range_is_fused(int64_t px, int diff_dtype, bool decoded, bool profiles) {
+  const Tiling t = choose_tiling(px);
+  if (getenv("FF_RANGE_UNFUSED")) return false;       // tuning / cross-check knob: the three-kernel sequence
+  return t.fast && t.k == 4 && diff_dtype == FF_DIFF_NONE && !decoded && !profiles;
+}
+
+// range_kernel for the frames described by `d` (whose ws / hooks / truncate say what the last CTA does).
+int range_fused_impl(const DetectParams& d, int bits, int32_t empty_thr, bool pdl, cudaStream_t st) {
+  const Tiling t = choose_tiling(d.px_per_frame);
+  if (!range_is_fused(d.px_per_frame, FF_DIFF_NONE, false, d.profile_out != nullptr) || d.ws == nullptr)
+    return FF_ERR_INVALID;
+  if (((reinterpret_cast<uintptr_t>(d.frames) | reinterpret_cast<uintptr_t>(d.halo)) & 15u) != 0) return FF_ERR_ALIGNMENT;
+  StreamParams p{};
+  p.frames = d.frames;
+  p.halo = d.halo;
+  p.frame_bytes = d.frame_bytes;
+  p.px_per_frame = d.px_per_frame;
+  p.n_frames = d.n_frames;
+  p.tiles_per_frame = t.tiles_per_frame;
+  p.items_per_cta = 1;
+  p.bg_dev = d.bg_dev;
+  p.empty_thr = empty_thr;
+  p.diff_thr = d.diff_thr;
+  p.skip = d.skip;
+  p.pdl = pdl ? 1 : 0;
+  static const int stages = getenv("FF_COUNT12_STAGES") ? atoi(getenv("FF_COUNT12_STAGES")) : 4;   // tuning knob
+  if (bits == 16) return launch_range_fused<16, 4>(p, d, st);
+  if (bits == 8) return launch_range_fused<8, 6>(p, d, st);
+  switch (stages) {
+    case 3: return launch_range_fused<12, 3>(p, d, st);
+    case 6: return launch_range_fused<12, 6>(p, d, st);
+    default: return launch_range_fused<12, 4>(p, d, st);
+  }
+}
+
 int stream_frames_impl(const void* frames, const void* halo, int64_t n_frames, int height, int width,
                        int bits, const int32_t* bg_dev, int32_t empty_thr, int32_t diff_thr,
                        const uint8_t* skip, int32_t* partial, void* diff_out, int diff_dtype,
-                       uint16_t* decoded_out, cudaStream_t st) {
+                       uint16_t* decoded_out, cudaStream_t st, bool pdl) {
   if (frames == nullptr || bg_dev == nullptr || partial == nullptr) return FF_ERR_INVALID;
   if (n_frames <= 0 || height <= 0 || width <= 0 || n_frames > 0x7FFFFFFF) return FF_ERR_INVALID;
   if (bits != 8 && bits != 12 && bits != 16) return FF_ERR_UNSUPPORTED;
@@ -939,6 +1315,7 @@ int stream_frames_impl(const void* frames, const void* halo, int64_t n_frames, i
   p.partial = partial;
   p.diff_out = diff_out;
   p.decoded_out = decoded_out;
+  p.pdl = pdl ? 1 : 0;
 
   const bool aligned = ((reinterpret_cast<uintptr_t>(frames) | reinterpret_cast<uintptr_t>(halo) |
                          reinterpret_cast<uintptr_t>(diff_out) | reinterpret_cast<uintptr_t>(decoded_out)) & 15u) == 0;

@@ -19,7 +19,7 @@ import torch
 
 from . import _cabi
 from ._cabi import (FF_DIFF_F32, FF_DIFF_F64, FF_DIFF_NONE, FF_DIFF_U16, FF_METHOD, FF_NO_EXIT, FF_PX_F64,
-                    FF_PX_U8, FF_PX_U16)
+                    FF_PX_U8, FF_PX_U16, HostArgs, RangeArgs, RangeHooks)
 
 DETECTION_METHODS = tuple(FF_METHOD)  # ("threshold", "gradient", "half_maximum")
 INT32_MAX = 2**31 - 1
@@ -121,17 +121,61 @@ def derive_kernel_bounds(scalars: ClipScalars, params: DetectionParams, n_pixels
     )
 
 
-@dataclass
+class PendingScalars:
+    """The clip's frame-0 statistics on their way to the host: the clip-scalar block and the centre row of
+    frame 0 are copied to pinned memory on a side stream behind the launches of ``process_range``; the
+    float64 statistics are evaluated with NumPy (the reference's own expressions,
+    scripts/process_videos.py:1362-1370) when somebody asks for them - the host never waits inside
+    ``process_range``.  For the threshold method the value the kernels used (computed on the device in
+    NumPy's order of operations) is compared with NumPy's and a difference raises."""
+
+    def __init__(self, engine: "FlameFrontEngine", done: torch.cuda.Event, slot: int, generation: int,
+                 width: int, check_threshold: bool):
+        self._engine, self._done, self._slot, self._generation = engine, done, slot, generation
+        self._width, self._check = width, check_threshold
+        self._value: Optional[ClipScalars] = None
+
+    def get(self) -> ClipScalars:
+        if self._value is None:
+            eng = self._engine
+            self._done.synchronize()
+            if eng._scalar_ring_gen[self._slot] != self._generation:
+                raise RuntimeError("the clip scalars of this result were overwritten by later process_range calls; "
+                                   f"read RangeResult.scalars within {len(eng._scalar_ring_gen)} calls")
+            scal_host, line_host = eng._scalar_ring[self._slot]
+            value = ClipScalars.from_frame0_stats(int(scal_host[0].item()), line_host[:self._width].numpy())
+            if self._check:
+                dev_floor = int(scal_host[1].item())
+                if dev_floor != _clamp_i32(math.floor(value.flame_threshold)):
+                    raise RuntimeError(
+                        f"flame threshold evaluated on the device (floor {dev_floor}) differs from NumPy's "
+                        f"({value.flame_threshold!r}): this NumPy sums in another order than the prep kernel "
+                        "assumes - pass scalars=/bg_dev= from clip_scalars() instead of frame0")
+            self._value = value
+        return self._value
+
+
 class RangeResult:
     """Device-resident outputs of one contiguous frame range."""
-    first_frame: int
-    pos: torch.Tensor                 # int32[n]  (>=0, -1 none, -2 dropped after truncate)
-    counts: torch.Tensor              # int32[n]  above-noise pixel count
-    first_exit: torch.Tensor          # int32[1]  global frame index or FF_NO_EXIT
-    diff: Optional[torch.Tensor] = None       # [n,H,W]
-    profiles: Optional[torch.Tensor] = None   # int32[n,W]
-    decoded: Optional[torch.Tensor] = None    # uint16[n,H,W]
-    scalars: Optional[ClipScalars] = None
+
+    def __init__(self, first_frame: int, pos: torch.Tensor, counts: torch.Tensor, first_exit: torch.Tensor,
+                 diff: Optional[torch.Tensor] = None, profiles: Optional[torch.Tensor] = None,
+                 decoded: Optional[torch.Tensor] = None, scalars=None):
+        self.first_frame = first_frame
+        self.pos = pos                    # int32[n]  (>=0, -1 none, -2 dropped after truncate)
+        self.counts = counts              # int32[n]  above-noise pixel count
+        self.first_exit = first_exit      # int32[1]  global frame index or FF_NO_EXIT
+        self.diff = diff                  # [n,H,W]
+        self.profiles = profiles          # int32[n,W]
+        self.decoded = decoded            # uint16[n,H,W]
+        self._scalars = scalars           # ClipScalars | PendingScalars | None
+
+    @property
+    def scalars(self) -> Optional[ClipScalars]:
+        """Per-clip scalars (host float64).  Synchronises on two tiny device-to-host copies the first time."""
+        if isinstance(self._scalars, PendingScalars):
+            self._scalars = self._scalars.get()
+        return self._scalars
 
 
 @dataclass
@@ -148,10 +192,15 @@ class HeadRangeResult:
 @dataclass
 class HostResult:
     first_frame: int
-    pos: np.ndarray
-    counts: np.ndarray
-    first_exit: int
+    pos: Optional[np.ndarray]         # None when the results stayed on the device (range block)
+    counts: Optional[np.ndarray]
+    first_exit: int                   # this range's own first exit frame (global index) or FF_NO_EXIT
     frames_done: int
+    bytes_uploaded: int = 0           # host -> device bytes actually moved (the early exit keeps it small)
+
+
+SCALAR_BLOCK = 16                     # int32 words of the clip-scalar block ([0] background scalar)
+MAX_DEVICE_STATS_WIDTH = 4096         # widest centre row whose float64 statistics prep_kernel evaluates
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -162,7 +211,7 @@ class FlameFrontEngine:
     """One engine per GPU.  All methods launch on the current torch CUDA stream."""
 
     def __init__(self, device: Union[int, str, torch.device, None] = None,
-                 host_chunk_bytes: int = 64 << 20):
+                 host_chunk_bytes: int = 64 << 20, host_copy_threads: Optional[int] = None):
         self._lib = _cabi.load()                      # raises if the .so is missing
         if not torch.cuda.is_available():
             raise RuntimeError("FlameFrontEngine needs a CUDA device (no CPU fallback exists)")
@@ -175,12 +224,17 @@ class FlameFrontEngine:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self._host_chunk_bytes = int(host_chunk_bytes)
         # ff_process_host copies pageable (memory-mapped) sources into pinned bounce buffers with a
-        # thread pool, by default half the host's cores; under torchrun share the cores between ranks
-        if "FF_HOST_COPY_THREADS" not in os.environ and os.environ.get("LOCAL_WORLD_SIZE", "1").isdigit():
-            ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-            if ranks > 1:
-                os.environ["FF_HOST_COPY_THREADS"] = str(max(1, min(8, (os.cpu_count() or 2) // ranks)))
+        # thread pool, by default half the host's cores; under torchrun the ranks share the cores
+        self._copy_threads: Optional[int] = host_copy_threads
+        if host_copy_threads is None and "FF_HOST_COPY_THREADS" not in os.environ:
+            ranks = os.environ.get("LOCAL_WORLD_SIZE", "1")
+            if ranks.isdigit() and int(ranks) > 1:
+                self._copy_threads = max(1, min(8, (os.cpu_count() or 2) // int(ranks)))
         self._host_ctx: Optional[C.c_void_p] = None
+        self._ws: Optional[torch.Tensor] = None        # ff_process_range workspace (kept zero-filled by the kernels)
+        self._scalar_ring = None                      # pinned (scalar block, centre row) buffers of _scalars_to_host
+        self._scalar_ring_gen = None
+        self._scalar_ring_next = 0
         self.launches = 0                             # kernels launched through this engine
         self._side_stream = None
         self._pinned = {}
@@ -229,7 +283,7 @@ class FlameFrontEngine:
         self._check_dev(frame0, "frame0")
         if frame0.dtype != torch.uint8 or frame0.numel() < frame_nbytes(height, width, bits):
             raise ValueError("frame0 must be a uint8 tensor holding one whole frame")
-        bg = torch.empty(1, dtype=torch.int32, device=self.device)
+        bg = torch.empty(SCALAR_BLOCK, dtype=torch.int32, device=self.device)[:1]     # [0] of a clip-scalar block
         line = torch.empty(width, dtype=torch.uint16, device=self.device)
         with torch.cuda.device(self.device):
             _cabi.check(self._lib.ff_background(frame0.data_ptr(), height, width, bits, bg.data_ptr(),
@@ -238,19 +292,19 @@ class FlameFrontEngine:
         return bg, line
 
     def _fetch_frame0_stats_async(self, bg_dev: torch.Tensor, line_dev: torch.Tensor):
-        """Copy the background scalar and centre row to pinned host memory on a side stream
-        that depends only on the background kernel, so later work on the main stream does not
-        delay them.  Returns (event, bg_host, line_host)."""
+        """Copy the clip-scalar words (``bg_dev``: int32[1] or the whole int32[16] block) and the centre row
+        to pinned host memory on a side stream that depends only on what is on the current stream so far,
+        so later work on the main stream does not delay them.  Returns (event, scalars_host, line_host)."""
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream(self.device)
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(self.device))
         side = self._side_stream
         side.wait_event(ready)
-        key = line_dev.numel()
+        key = (bg_dev.numel(), line_dev.numel())
         if key not in self._pinned:       # reused: the previous values were consumed under a sync
-            self._pinned[key] = (torch.empty(1, dtype=torch.int32).pin_memory(),
-                                 torch.empty(key, dtype=torch.uint16).pin_memory())
+            self._pinned[key] = (torch.empty(key[0], dtype=torch.int32).pin_memory(),
+                                 torch.empty(key[1], dtype=torch.uint16).pin_memory())
         bg_host, line_host = self._pinned[key]
         with torch.cuda.stream(side):
             bg_host.copy_(bg_dev, non_blocking=True)
@@ -261,6 +315,38 @@ class FlameFrontEngine:
             done.record(side)
         return done, bg_host, line_host
 
+    _SCALAR_RING = 64
+
+    def _scalars_to_host(self, scal_dev: torch.Tensor, line_dev: torch.Tensor, width: int,
+                         check_threshold: bool) -> "PendingScalars":
+        """Queue the copies of the clip-scalar block and the centre row into the next slot of a ring of
+        pinned buffers (side stream, behind everything launched so far) without waiting for them."""
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(self.device)
+        if self._scalar_ring is None:
+            self._scalar_ring = [None] * self._SCALAR_RING
+            self._scalar_ring_gen = [0] * self._SCALAR_RING
+        slot = self._scalar_ring_next % self._SCALAR_RING
+        self._scalar_ring_next += 1
+        buf = self._scalar_ring[slot]
+        if buf is None or buf[1].numel() < width:
+            buf = (torch.empty(SCALAR_BLOCK, dtype=torch.int32).pin_memory(),
+                   torch.empty(max(width, 1024), dtype=torch.uint16).pin_memory())
+            self._scalar_ring[slot] = buf
+        self._scalar_ring_gen[slot] += 1
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        side = self._side_stream
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            buf[0].copy_(scal_dev, non_blocking=True)
+            buf[1][:width].copy_(line_dev, non_blocking=True)
+            scal_dev.record_stream(side)
+            line_dev.record_stream(side)
+            done = torch.cuda.Event()
+            done.record(side)
+        return PendingScalars(self, done, slot, self._scalar_ring_gen[slot], width, check_threshold)
+
     def clip_scalars(self, frame0: torch.Tensor, height: int, width: int, bits: int):
         """Background reduction + host-side float64 statistics.  Synchronises on two tiny D2H
         copies.  Returns ``(ClipScalars, bg_dev)``."""
@@ -270,6 +356,12 @@ class FlameFrontEngine:
         return ClipScalars.from_frame0_stats(bg_host, line_host), bg
 
     # ------------------------------------------------------------------ stages 2b-4
+    def _workspace(self, n_bytes: int) -> torch.Tensor:
+        """The zero-filled workspace of ``ff_process_range`` (every call leaves it zero-filled again)."""
+        if self._ws is None or self._ws.numel() < n_bytes:
+            self._ws = torch.zeros(max(n_bytes, 1 << 20), dtype=torch.uint8, device=self.device)
+        return self._ws
+
     def process_range(self, frames: torch.Tensor, n_frames: int, height: int, width: int, bits: int,
                       params: DetectionParams, scalars: Optional[ClipScalars] = None,
                       bg_dev: Optional[torch.Tensor] = None, *, frame0: Optional[torch.Tensor] = None,
@@ -278,20 +370,22 @@ class FlameFrontEngine:
                       keep_profiles: bool = False, keep_decoded: bool = False,
                       first_exit: Optional[torch.Tensor] = None, truncate: bool = True,
                       partial: Optional[torch.Tensor] = None, pos_out: Optional[torch.Tensor] = None,
-                      counts_out: Optional[torch.Tensor] = None) -> RangeResult:
-        """Fused front end + detection + exit min (+ local truncation) on a device-resident
-        contiguous frame range.  Nothing but two tiny scalars ever goes to the host.
+                      counts_out: Optional[torch.Tensor] = None, hooks: Optional[RangeHooks] = None,
+                      init_first_exit: Optional[bool] = None, want_scalars: bool = True) -> RangeResult:
+        """Stages 2-4 on a device-resident contiguous frame range in one C-ABI call (``ff_process_range``):
+        prep kernel -> ONE range kernel for counts-only work (stream + count + empty-frame decision +
+        detection + exit min + truncation), or stream kernel -> detect kernel when an image output is
+        retained.  Nothing on the GPU waits for the host.
 
-        Either pass ``scalars``/``bg_dev`` from :meth:`clip_scalars`, or pass ``frame0`` (the
-        clip's first frame, packed, on the device; defaults to ``frames[0]`` when
-        ``first_frame == 0``): then the background reduction is launched first, the streaming
-        kernel starts right behind it with device-side thresholds, and the host computes the
-        float64 centre-row statistics while that kernel runs - the GPU never waits for the host.
+        Either pass ``scalars``/``bg_dev`` from :meth:`clip_scalars`, or pass ``frame0`` (the clip's first
+        frame, packed, on the device; defaults to ``frames[0]`` when ``first_frame == 0``): then the prep
+        kernel derives the background scalar - and, for the threshold method, the float64 flame threshold in
+        NumPy's order of operations - on the device; the host repeats the statistics with NumPy from the
+        copied-back centre row (``RangeResult.scalars``) and raises if the two thresholds ever differed.
 
-        ``pos_out`` / ``counts_out`` / ``first_exit`` let the caller supply the int32 output
-        arrays - e.g. views into a range block of ``sharding.RangeExchange`` so that the
-        multi-GPU exchange needs no packing copy (``first_exit`` must then be pre-set to
-        FF_NO_EXIT by the block's owner)."""
+        ``pos_out`` / ``counts_out`` / ``first_exit`` let the caller supply the int32 output arrays - e.g.
+        the views of a ``sharding.RangeExchange`` block together with its ``hooks`` (the kernels then wait
+        for the peers before writing and publish the finished block to them)."""
         self._check_dev(frames, "frames")
         for name, t in (("pos_out", pos_out), ("counts_out", counts_out)):
             if t is not None:
@@ -321,35 +415,65 @@ class FlameFrontEngine:
         if diff_code == FF_DIFF_U16 and diff_thr < 0:
             raise ValueError("uint16 difference images need frame_diff_threshold >= 0")
 
+        if scalars is None and params.method == "threshold" and width > MAX_DEVICE_STATS_WIDTH:
+            # a centre row wider than the prep kernel's shared memory: statistics on the host first
+            if frame0 is None:
+                if first_frame != 0:
+                    raise ValueError("frame0 (the clip's first frame) is required for a sub-range")
+                frame0 = frames[:fb]
+            scalars, bg_dev = self.clip_scalars(frame0, height, width, bits)
         line_dev = None
         if scalars is None:
             if frame0 is None:
                 if first_frame != 0:
                     raise ValueError("frame0 (the clip's first frame) is required for a sub-range")
                 frame0 = frames[:fb]
-            bg_dev, line_dev = self.background(frame0, height, width, bits)
-            fetch = self._fetch_frame0_stats_async(bg_dev, line_dev)
-            empty_thr = -1            # derived on the device: floor(max(10, bg/2))  (:1458)
+            self._check_dev(frame0, "frame0")
+            if frame0.dtype != torch.uint8 or frame0.numel() < fb:
+                raise ValueError("frame0 must be a uint8 tensor holding one whole frame")
+            scal_dev = torch.empty(SCALAR_BLOCK, dtype=torch.int32, device=self.device)
+            line_dev = torch.empty(width, dtype=torch.uint16, device=self.device) if want_scalars else None
+            empty_thr, threshold_floor = -1, 0        # derived on the device (:1458, :1367-1370)
         else:
+            self._check_dev(bg_dev, "bg_dev")
+            scal_dev = bg_dev
             empty_thr = _clamp_i32(math.floor(scalars.noise_threshold))
+            threshold_floor = _clamp_i32(math.floor(scalars.flame_threshold))
 
-        n_elems = C.c_int64(0)
-        tiles = C.c_int(0)
-        _cabi.check(self._lib.ff_partial_len(n_frames, height, width, bits, C.byref(n_elems), C.byref(tiles)),
-                    "ff_partial_len")
-        if partial is None or partial.numel() < n_elems.value:
-            partial = torch.empty(max(1, n_elems.value), dtype=torch.int32, device=self.device)
+        ws_bytes, n_partial, fused = C.c_int64(0), C.c_int64(0), C.c_int(0)
+        _cabi.check(self._lib.ff_process_range_plan(n_frames, height, width, bits, diff_code, int(keep_decoded),
+                                                    int(keep_profiles), C.byref(ws_bytes), C.byref(n_partial),
+                                                    C.byref(fused)), "ff_process_range_plan")
+        ws = self._workspace(ws_bytes.value)
+        if n_partial.value and (partial is None or partial.numel() < n_partial.value):
+            partial = torch.empty(n_partial.value, dtype=torch.int32, device=self.device)
         pos = pos_out[:n_frames] if pos_out is not None else torch.empty(n_frames, dtype=torch.int32,
                                                                          device=self.device)
         counts = counts_out[:n_frames] if counts_out is not None else torch.empty(n_frames, dtype=torch.int32,
                                                                                   device=self.device)
+        if init_first_exit is None:
+            init_first_exit = first_exit is None
         if first_exit is None:
-            first_exit = torch.full((1,), FF_NO_EXIT, dtype=torch.int32, device=self.device)
+            first_exit = torch.empty(1, dtype=torch.int32, device=self.device)
         diff = None if diff_torch is None else torch.empty((n_frames, height, width), dtype=diff_torch,
                                                            device=self.device)
         profiles = torch.zeros((n_frames, width), dtype=torch.int32, device=self.device) if keep_profiles else None
         decoded = torch.empty((n_frames, height, width), dtype=torch.uint16,
                               device=self.device) if keep_decoded else None
+        kb_min = min_signal_count(height * width, params.min_signal_fraction)
+        args = RangeArgs(
+            frames_dev=frames.data_ptr(), halo_dev=_ptr(halo), frame0_dev=None if scalars is not None else frame0.data_ptr(),
+            n_frames=n_frames, first_frame=first_frame, height=height, width=width, bits=bits,
+            method=FF_METHOD[params.method], use_frame_diff=int(params.use_frame_diff), min_run_px=params.min_run_px,
+            exit_margin_px=params.exit_margin_px, diff_thr=diff_thr,
+            grad2_bound=_clamp_i32(math.ceil(-2.0 * params.min_gradient_strength)), empty_thr=empty_thr,
+            threshold_floor=threshold_floor, min_signal_count=kb_min, skip_dev=_ptr(skip),
+            scalars_dev=scal_dev.data_ptr(), centerline_dev=_ptr(line_dev), pos_out_dev=pos.data_ptr(),
+            count_out_dev=counts.data_ptr(), first_exit_dev=first_exit.data_ptr(),
+            init_first_exit=int(bool(init_first_exit)), truncate=int(bool(truncate)), diff_out_dev=_ptr(diff),
+            diff_dtype=diff_code, decoded_out_dev=_ptr(decoded), profile_out_dev=_ptr(profiles),
+            partial_dev=_ptr(partial) if n_partial.value else None, workspace_dev=ws.data_ptr(),
+            hooks=C.pointer(hooks) if hooks is not None else None)
         st = self._stream()
         with torch.cuda.device(self.device):
             ev = self._stream_events
@@ -357,27 +481,17 @@ class FlameFrontEngine:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-            _cabi.check(self._lib.ff_stream_frames(
-                frames.data_ptr(), _ptr(halo), n_frames, height, width, bits, bg_dev.data_ptr(),
-                empty_thr, diff_thr, _ptr(skip), partial.data_ptr(), _ptr(diff), diff_code,
-                _ptr(decoded), st), "ff_stream_frames")
+            rc = self._lib.ff_process_range(C.byref(args), st)
+            if rc != 0:
+                self._ws = None           # a failed launch sequence may leave workspace words set
+            _cabi.check(rc, "ff_process_range")
             if ev is not None:
                 e1.record()
                 ev.append((e0, e1))
-            if scalars is None:       # host statistics overlap with the streaming kernel
-                done, bg_host, line_host = fetch
-                done.synchronize()
-                scalars = ClipScalars.from_frame0_stats(int(bg_host.item()), line_host.numpy())
-            kb = derive_kernel_bounds(scalars, params, height * width)
-            _cabi.check(self._lib.ff_detect(
-                frames.data_ptr(), _ptr(halo), n_frames, first_frame, height, width, bits, bg_dev.data_ptr(),
-                partial.data_ptr(), kb.min_signal_count, FF_METHOD[params.method], int(params.use_frame_diff),
-                kb.diff_thr, kb.threshold_floor, kb.grad2_bound, params.min_run_px, params.exit_margin_px,
-                _ptr(skip), pos.data_ptr(), counts.data_ptr(), first_exit.data_ptr(), _ptr(profiles), st),
-                "ff_detect")
-            self.launches += 2
-            if truncate:
-                self.truncate(pos, first_frame, first_exit)
+        has_prep = scalars is None or init_first_exit or hooks is not None
+        self.launches += (1 if has_prep else 0) + (1 if fused.value else 2)
+        if scalars is None and want_scalars:
+            scalars = self._scalars_to_host(scal_dev, line_dev, width, params.method == "threshold")
         return RangeResult(first_frame, pos, counts, first_exit, diff, profiles, decoded, scalars)
 
     # ------------------------------------------------------------------ HEAD-parity detector
@@ -624,6 +738,9 @@ class FlameFrontEngine:
             ctx = C.c_void_p()
             _cabi.check(self._lib.ff_host_ctx_create(self.device.index, self._host_chunk_bytes, C.byref(ctx)),
                         "ff_host_ctx_create")
+            if self._copy_threads is not None:
+                _cabi.check(self._lib.ff_host_ctx_set_copy_threads(ctx, int(self._copy_threads)),
+                            "ff_host_ctx_set_copy_threads")
             self._host_ctx = ctx
         return self._host_ctx
 
@@ -640,9 +757,16 @@ class FlameFrontEngine:
     def process_host(self, frames: Union[np.ndarray, torch.Tensor], n_frames: int, height: int, width: int,
                      bits: int, params: DetectionParams, scalars: ClipScalars, *, first_frame: int = 0,
                      halo: Union[np.ndarray, torch.Tensor, None] = None,
-                     skip: Optional[np.ndarray] = None) -> HostResult:
-        """End-to-end form: frames live in host memory (pinned tensor or mmapped file); chunks
-        are copied H2D double-buffered against the kernels; blocks until results are on the host."""
+                     skip: Optional[np.ndarray] = None, block=None, hooks: Optional[RangeHooks] = None,
+                     to_host: bool = True) -> HostResult:
+        """End-to-end form: frames live in host memory (pinned tensor or mmapped file); chunks are copied
+        H2D double-buffered against the range kernel; blocks until the results are complete.
+
+        ``block`` (a ``sharding.RangeBlock``) + ``hooks``: one rank's range of a range-sharded clip - the
+        results are written into the block on the device and published to the peers, exit frames are
+        shared between the ranks while they stream, and nothing at or behind the smallest exit frame ANY
+        rank has seen is uploaded (``HostResult.bytes_uploaded``).  ``to_host=False`` then skips the
+        copies of the rank-local arrays to the host."""
         fb = frame_nbytes(height, width, bits)
         src_ptr, src_bytes, _keep = _host_buffer(frames)
         if src_bytes < n_frames * fb:
@@ -661,21 +785,31 @@ class FlameFrontEngine:
         if params.method == "gradient" and width < 2:
             raise ValueError("Shape of array too small to calculate a numerical gradient, "
                              "at least 2 elements are required.")
+        if block is None and not to_host:
+            raise ValueError("to_host=False needs a block for the results")
         kb = derive_kernel_bounds(scalars, params, height * width)
         self._ctx()
-        pos = np.empty(n_frames, dtype=np.int32)
-        counts = np.empty(n_frames, dtype=np.int32)
-        done = C.c_int64(0)
-        fexit = C.c_int32(FF_NO_EXIT)
-        _cabi.check(self._lib.ff_process_host(
-            self._host_ctx, src_ptr, halo_ptr, n_frames, first_frame, height, width, bits,
-            int(scalars.background), kb.empty_thr, kb.min_signal_count, FF_METHOD[params.method],
-            int(params.use_frame_diff), kb.diff_thr, kb.threshold_floor, kb.grad2_bound, params.min_run_px,
-            params.exit_margin_px, skip_ptr, pos.ctypes.data, counts.ctypes.data, C.byref(done), C.byref(fexit)),
-            "ff_process_host")
-        n_chunks = -(-n_frames // max(1, self._host_chunk_bytes // fb))
-        self.launches += 2 * n_chunks + 1
-        return HostResult(first_frame, pos, counts, int(fexit.value), int(done.value))
+        pos = np.empty(n_frames, dtype=np.int32) if to_host else None
+        counts = np.empty(n_frames, dtype=np.int32) if to_host else None
+        done, fexit, moved = C.c_int64(0), C.c_int32(FF_NO_EXIT), C.c_int64(0)
+        args = HostArgs(
+            frames_host=src_ptr, halo_host=halo_ptr, n_frames=n_frames, first_frame=first_frame, height=height,
+            width=width, bits=bits, bg=int(scalars.background), empty_thr=kb.empty_thr,
+            method=FF_METHOD[params.method], use_frame_diff=int(params.use_frame_diff), diff_thr=kb.diff_thr,
+            threshold_floor=kb.threshold_floor, grad2_bound=kb.grad2_bound, min_run_px=params.min_run_px,
+            exit_margin_px=params.exit_margin_px, min_signal_count=kb.min_signal_count, skip_host=skip_ptr,
+            pos_out_host=None if pos is None else pos.ctypes.data,
+            count_out_host=None if counts is None else counts.ctypes.data,
+            pos_block_dev=None if block is None else block.pos.data_ptr(),
+            count_block_dev=None if block is None else block.counts.data_ptr(),
+            first_exit_block_dev=None if block is None else block.first_exit.data_ptr(),
+            hooks=C.pointer(hooks) if hooks is not None else None,
+            frames_done_out=C.pointer(done), first_exit_out=C.pointer(fexit), bytes_uploaded_out=C.pointer(moved))
+        _cabi.check(self._lib.ff_process_host_range(self._host_ctx, C.byref(args)), "ff_process_host_range")
+        chunk_frames = max(1, min(n_frames, self._host_chunk_bytes // fb))
+        n_chunks = -(-int(done.value) // chunk_frames)
+        self.launches += 1 + n_chunks + 1      # prep, one range kernel per chunk, truncate / publish
+        return HostResult(first_frame, pos, counts, int(fexit.value), int(done.value), int(moved.value))
 
 
 def _host_buffer(buf: Union[np.ndarray, torch.Tensor]):

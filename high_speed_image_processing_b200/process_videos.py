@@ -219,26 +219,27 @@ def process_video(video: PhotonVideo, config: VideoSourceConfig, calibration: fl
         # every rank handles its contiguous range; one exchange kernel per rank finishes the clip
         if exchange.engine is None:
             exchange.engine = eng
-        if residency == "device":       # range uploaded once; ff_detect fills the range block in place
-            blk = exchange.begin(n, eng.device)
-            if b - a > 0:
-                frames_dev = eng.upload(video.raw_frames(a, b))
-                halo_dev = None if halo_np is None else eng.upload(halo_np)
-                skip_dev = None if skip_range is None else torch.from_numpy(skip_range.copy()).to(eng.device)
-                eng.process_range(frames_dev, b - a, h, w, bits, params, scalars, bg_dev, first_frame=a,
-                                  halo=halo_dev, skip=skip_dev, truncate=False, pos_out=blk.pos,
-                                  counts_out=blk.counts, first_exit=blk.first_exit)
-            g = exchange.finish(blk)
-        else:                           # range streamed from host memory
-            if b - a > 0:
-                hres = eng.process_host(video.raw_frames(a, b), b - a, h, w, bits, params, scalars, first_frame=a,
-                                        halo=halo_np, skip=skip_range)
-                pos_l, cnt_l, fe_l = hres.pos, hres.counts, hres.first_exit
-            else:
-                pos_l, cnt_l, fe_l = np.empty(0, np.int32), np.empty(0, np.int32), FF_NO_EXIT
-            g = exchange.finish_arrays(torch.from_numpy(pos_l).to(eng.device),
-                                       torch.tensor([fe_l], dtype=torch.int32, device=eng.device), n,
-                                       counts_local=torch.from_numpy(cnt_l).to(eng.device))
+        blk = exchange.begin(n, eng.device)
+        if b - a == 0:                  # more ranks than frames: an empty block, still part of the exchange
+            exchange.acquire(blk)
+            exchange.publish(blk)
+        elif residency == "device":     # range uploaded once; the range kernel fills the block in place
+            frames_dev = eng.upload(video.raw_frames(a, b))
+            halo_dev = None if halo_np is None else eng.upload(halo_np)
+            skip_dev = None if skip_range is None else torch.from_numpy(skip_range.copy()).to(eng.device)
+            eng.process_range(frames_dev, b - a, h, w, bits, params, scalars, bg_dev, first_frame=a,
+                              halo=halo_dev, skip=skip_dev, **exchange.range_kwargs(blk))
+        elif blk.hooks is not None:     # range streamed from host memory straight into the block; the ranks share
+            #                             exit frames while they stream and stop uploading behind the first one
+            eng.process_host(video.raw_frames(a, b), b - a, h, w, bits, params, scalars, first_frame=a,
+                             halo=halo_np, skip=skip_range, block=blk, hooks=blk.hooks, to_host=False)
+        else:                           # gathered transport: results come back to the host first
+            hres = eng.process_host(video.raw_frames(a, b), b - a, h, w, bits, params, scalars, first_frame=a,
+                                    halo=halo_np, skip=skip_range)
+            blk.pos[:b - a].copy_(torch.from_numpy(hres.pos))
+            blk.counts[:b - a].copy_(torch.from_numpy(hres.counts))
+            blk.first_exit.fill_(hres.first_exit)
+        g = exchange.finish(blk)
         pos_np, cnt_np, first_exit = g.pos.cpu().numpy(), g.counts.cpu().numpy(), g.first_exit
         exchange.check()
     elif residency == "device":

@@ -9,7 +9,7 @@ Frames shard naturally:
 * across clips: whole videos round-robin over ranks (src/photron/parallel.py:173-208).
 
 The single real exchange is tiny - the first exit frame (one int32, min over ranks) and the
-per-rank position / count arrays - and it is ONE step: every rank's ``ff_detect`` writes into
+per-rank position / count arrays - and it is ONE step: every rank's range kernel writes into
 a *range block* ``{first_exit,0,0,0 | pos[cap] | counts[cap]}`` and one kernel per rank turns
 the blocks of all ranks into the truncated whole-clip arrays (csrc/ff_exchange.cu).  It
 replaces the reference's pickled ``comm.gather`` (scripts/process_videos.py:1533-1541) and
@@ -17,9 +17,12 @@ turns the per-rank ``break`` (:1494) into a global truncation (README.md:145-149
 
 Transports for the blocks:
 
-``peer``      (GPUs of one box) blocks stay in place; peers map them over NVLink through CUDA
-              IPC and the finishing kernel pulls them itself, synchronising on epoch flags in
-              peer memory - no collective on the data path (``ff_exchange_*``).
+``peer``      (GPUs of one box) blocks stay in place; peers map every rank's exchange buffer over
+              NVLink through CUDA IPC.  The range kernel's last CTA publishes the block (epoch flag
+              in peer memory), the merge kernel waits for the flags, pulls the blocks and acknowledges
+              - it runs on a SIDE stream, off the critical path of the next clip - and every exit
+              frame is min-reduced into an exit word on every rank, which lets the host-streamed path
+              stop uploading behind an exit another rank found.  No collective on the data path.
 ``gathered``  one ``all_gather_into_tensor`` of the blocks (NCCL; gloo in the CPU tests), then
               ``ff_merge_ranges``.
 """
@@ -34,7 +37,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-from ._cabi import FF_NO_EXIT
+from ._cabi import FF_NO_EXIT, RangeHooks
 
 BLOCK_HEADER = 4        # int32 words in front of a range block's arrays (csrc/ff_exchange.cu: kHdr)
 
@@ -110,19 +113,44 @@ class RangeBlock:
     cap: int                        # capacity of pos / counts (ceil(total / world) or larger)
     pos: torch.Tensor               # int32[cap] view  - ff_detect's pos_out
     counts: torch.Tensor            # int32[cap] view  - ff_detect's count_out
-    first_exit: torch.Tensor        # int32[1] view    - ff_detect's first_exit (pre-set to FF_NO_EXIT)
+    first_exit: torch.Tensor        # int32[1] view    - ff_detect's first_exit
     send: Optional[torch.Tensor] = None     # gathered transport: the whole block
+    hooks: object = None            # peer transport: _cabi.RangeHooks for ff_process_range / ff_process_host_range
+    init_first_exit: bool = False   # peer transport: the prep kernel resets first_exit (after waiting for the peers)
 
 
-@dataclass
 class GatheredRange:
-    first_exit_t: torch.Tensor      # int32[1] global index of the first exit frame, or FF_NO_EXIT
-    pos: torch.Tensor               # int32[total] positions of the whole clip, truncated
-    counts: Optional[torch.Tensor]  # int32[total] above-noise counts
+    """The whole clip's results on this rank.  With the peer transport they are produced by the merge
+    kernel on a side stream: reading an attribute makes the current stream wait for it."""
+
+    def __init__(self, first_exit_t: torch.Tensor, pos: torch.Tensor, counts: Optional[torch.Tensor],
+                 ready: Optional["torch.cuda.Event"] = None, check=None):
+        self._first_exit_t, self._pos, self._counts, self._ready, self._check = first_exit_t, pos, counts, ready, check
+
+    def wait(self) -> "GatheredRange":
+        if self._ready is not None:
+            torch.cuda.current_stream(self._pos.device).wait_event(self._ready)
+            self._ready = None
+        return self
 
     @property
-    def first_exit(self) -> int:    # synchronises on the device scalar
-        return int(self.first_exit_t.item())
+    def first_exit_t(self) -> torch.Tensor:      # int32[1] global index of the first exit frame, or FF_NO_EXIT
+        return self.wait()._first_exit_t
+
+    @property
+    def pos(self) -> torch.Tensor:               # int32[total] positions of the whole clip, truncated
+        return self.wait()._pos
+
+    @property
+    def counts(self) -> Optional[torch.Tensor]:  # int32[total] above-noise counts
+        return self.wait()._counts
+
+    @property
+    def first_exit(self) -> int:                 # synchronises on the device scalar (and on the exchange's status)
+        value = int(self.first_exit_t.item())
+        if self._check is not None:
+            self._check()
+        return value
 
 
 class _DevicePointerView:
@@ -160,6 +188,9 @@ class RangeExchange:
         self._xchg_buf = None           # torch view of the exchange's local allocation
         self._bufs = {}                 # gathered transport: (cap, device) -> (send, recv, init)
         self._peer_failed = False
+        self._views = {}                # peer transport: torch views of the two block slots
+        self._merge_stream = None       # peer transport: the merge kernels run here
+        self._last_merge = None         # event behind the latest merge
 
     # ------------------------------------------------------------------ partition
     def my_range(self, total: int) -> Tuple[int, int]:
@@ -235,12 +266,13 @@ class RangeExchange:
             self.engine._lib.ff_exchange_destroy(self._xchg)
             self._xchg = None
             self._xchg_buf = None
+            self._views = {}
+            self._last_merge = None
 
     # ------------------------------------------------------------------ one step
     def begin(self, total: int, device: Optional[torch.device] = None) -> RangeBlock:
-        """Start a step: returns the block whose views ``ff_detect`` fills
-        (``engine.process_range(..., pos_out=blk.pos, counts_out=blk.counts,
-        first_exit=blk.first_exit, truncate=False)``)."""
+        """Start a step: returns the block the range kernel fills
+        (``engine.process_range(..., **exchange.range_kwargs(blk))``)."""
         cap = self.block_cap(total)
         if device is None:
             device = self.engine.device if self.engine is not None else torch.device("cpu")
@@ -251,16 +283,18 @@ class RangeExchange:
         if self._xchg is not None:
             eng = self.engine
             pos_p, cnt_p, fe_p = C.c_void_p(), C.c_void_p(), C.c_void_p()
-            with torch.cuda.device(eng.device):
-                st = eng._lib.ff_exchange_begin(self._xchg, C.byref(pos_p), C.byref(cnt_p), C.byref(fe_p),
-                                                torch.cuda.current_stream(eng.device).cuda_stream)
+            hooks = RangeHooks()
+            st = eng._lib.ff_exchange_begin(self._xchg, C.byref(pos_p), C.byref(cnt_p), C.byref(fe_p), C.byref(hooks))
             if st != 0:
                 raise RuntimeError(f"ff_exchange_begin failed ({st})")
             xc = self._xchg_cap
+            views = self._views.get((pos_p.value, xc))
+            if views is None:
 
-            def view(ptr, n):
-                return torch.as_tensor(_DevicePointerView(ptr.value, n), device=eng.device)
-            return RangeBlock(total, xc, view(pos_p, xc), view(cnt_p, xc), view(fe_p, 1))
+                def view(ptr, n):
+                    return torch.as_tensor(_DevicePointerView(ptr.value, n), device=eng.device)
+                views = self._views[(pos_p.value, xc)] = (view(pos_p, xc), view(cnt_p, xc), view(fe_p, 1))
+            return RangeBlock(total, xc, views[0], views[1], views[2], None, hooks, True)
         key = (cap, str(device))
         if key not in self._bufs:
             n = BLOCK_HEADER + 2 * cap
@@ -275,21 +309,41 @@ class RangeExchange:
 
     def finish(self, blk: RangeBlock, merge: Optional[MergeFn] = None, want_counts: bool = True) -> GatheredRange:
         """Exchange + merge: every rank returns the whole clip's truncated positions, counts and
-        the global first exit frame.  ``merge`` defaults to the engine's ``ff_merge_ranges``."""
+        the global first exit frame.  ``merge`` defaults to the engine's ``ff_merge_ranges``.
+
+        Peer transport: the block was published by the kernel that filled it (``hooks``); the merge kernel
+        is launched on a side stream behind everything the current stream holds so far, and the returned
+        ``GatheredRange`` makes its reader wait for it - the caller can go on with the next clip."""
         device = blk.pos.device
+        if blk.send is None:            # peer transport
+            eng = self.engine
+            if self._merge_stream is None:
+                self._merge_stream = torch.cuda.Stream(eng.device)
+            side = self._merge_stream
+            filled = torch.cuda.Event()
+            filled.record(torch.cuda.current_stream(eng.device))
+            side.wait_event(filled)
+            with torch.cuda.stream(side):
+                pos = torch.empty(blk.total, dtype=torch.int32, device=device)
+                counts = torch.empty(blk.total, dtype=torch.int32, device=device) if want_counts else None
+                fe = torch.empty(1, dtype=torch.int32, device=device)
+                st = eng._lib.ff_exchange_finish(self._xchg, blk.total, pos.data_ptr(),
+                                                 None if counts is None else counts.data_ptr(), fe.data_ptr(),
+                                                 side.cuda_stream)
+                if st != 0:
+                    raise RuntimeError(f"ff_exchange_finish failed ({st})")
+                ready = torch.cuda.Event()
+                ready.record(side)
+            main = torch.cuda.current_stream(eng.device)
+            for t in (pos, counts, fe):
+                if t is not None:
+                    t.record_stream(main)
+            self._last_merge = ready
+            eng.launches += 1
+            return GatheredRange(fe, pos, counts, ready, self.check)
         pos = torch.empty(blk.total, dtype=torch.int32, device=device)
         counts = torch.empty(blk.total, dtype=torch.int32, device=device) if want_counts else None
         fe = torch.empty(1, dtype=torch.int32, device=device)
-        if blk.send is None:            # peer transport
-            eng = self.engine
-            with torch.cuda.device(eng.device):
-                st = eng._lib.ff_exchange_finish(self._xchg, blk.total, pos.data_ptr(),
-                                                 None if counts is None else counts.data_ptr(), fe.data_ptr(),
-                                                 torch.cuda.current_stream(eng.device).cuda_stream)
-            if st != 0:
-                raise RuntimeError(f"ff_exchange_finish failed ({st})")
-            eng.launches += 1
-            return GatheredRange(fe, pos, counts)
         key = (blk.cap, str(device))
         send, recv, _ = self._bufs[key]
         if self.active and self.size > 1:
@@ -303,16 +357,49 @@ class RangeExchange:
         merge(recv, self.size, blk.cap, blk.total, pos, counts, fe)
         return GatheredRange(fe, pos, counts)
 
+    def join(self) -> None:
+        """Make the current stream wait for the latest merge (peer transport; e.g. before a timing event)."""
+        if self._last_merge is not None:
+            torch.cuda.current_stream(self.engine.device).wait_event(self._last_merge)
+
+    @staticmethod
+    def range_kwargs(blk: RangeBlock) -> dict:
+        """Keyword arguments that make ``engine.process_range`` fill ``blk`` in place (and, with the peer
+        transport, wait for the peers first and publish the block from its last CTA)."""
+        return dict(pos_out=blk.pos, counts_out=blk.counts, first_exit=blk.first_exit, truncate=False,
+                    hooks=blk.hooks, init_first_exit=blk.init_first_exit)
+
+    def acquire(self, blk: RangeBlock) -> None:
+        """Before a block is filled by hand (peer transport): wait until no peer reads its previous use and
+        reset its first-exit word - what the prep kernel does for ``engine.process_range``."""
+        if blk.send is None:
+            eng = self.engine
+            st = eng._lib.ff_exchange_acquire(self._xchg, torch.cuda.current_stream(eng.device).cuda_stream)
+            if st != 0:
+                raise RuntimeError(f"ff_exchange_acquire failed ({st})")
+            eng.launches += 1
+
+    def publish(self, blk: RangeBlock) -> None:
+        """After a block was filled by hand (peer transport): tell the peers it is complete."""
+        if blk.send is None:
+            eng = self.engine
+            st = eng._lib.ff_exchange_publish(self._xchg, torch.cuda.current_stream(eng.device).cuda_stream)
+            if st != 0:
+                raise RuntimeError(f"ff_exchange_publish failed ({st})")
+            eng.launches += 1
+
     def finish_arrays(self, pos_local: torch.Tensor, first_exit_local: torch.Tensor, total: int,
                       merge: Optional[MergeFn] = None, counts_local: Optional[torch.Tensor] = None) -> GatheredRange:
-        """Same step for results that were not written in place (e.g. they came back from the
-        host-streamed path): copies them into a block first."""
+        """Same step for results that were not written in place (they came from somewhere else):
+        copies them into a block first."""
         blk = self.begin(total, pos_local.device)
+        self.acquire(blk)
         n = pos_local.numel()
         blk.pos[:n].copy_(pos_local)
         if counts_local is not None:
             blk.counts[:n].copy_(counts_local)
         blk.first_exit.copy_(first_exit_local.reshape(1))
+        self.publish(blk)
         return self.finish(blk, merge, want_counts=counts_local is not None)
 
     def check(self) -> None:
@@ -325,5 +412,6 @@ class RangeExchange:
             st = eng._lib.ff_exchange_status(self._xchg, C.byref(status),
                                              torch.cuda.current_stream(eng.device).cuda_stream)
         if st != 0 or status.value != 0:
-            raise RuntimeError(f"peer-memory exchange: rank {status.value - 1} never published its block "
-                               f"(status {st})")
+            who = (f"rank {status.value - 1} never published its block" if status.value < 0x100
+                   else f"rank {status.value - 0x100} never acknowledged an earlier block")
+            raise RuntimeError(f"peer-memory exchange: {who} (status {st}); the results of that step are invalid")

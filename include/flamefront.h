@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FF_ABI_VERSION 5
+#define FF_ABI_VERSION 6
 
 /* status codes */
 #define FF_OK                 0
@@ -149,6 +149,73 @@ int ff_detect(const void* frames_dev, const void* halo_dev, int64_t n_frames, in
 int ff_truncate(int32_t* pos_dev, int64_t n_frames, int64_t first_frame,
                 const int32_t* first_exit_dev, void* stream);
 
+/* ---- stages 2-4 in one call: a contiguous frame range, frames on the device -------------------------
+ * The call SURVEY.md section 8b proposes for seam B3: replaces the frame loop of process_video_source
+ * (scripts/process_videos.py:1441-1516) for one contiguous frame range, including the per-clip scalars of
+ * :1356-1370 when frame0_dev is given.  Nothing here waits for the host.
+ *
+ *   prep kernel     (frame0_dev != NULL) background scalar = max of frame 0, its centre row, and - for the
+ *                   threshold method - the float64 mean / std / max of that row and max(mean + 5 std, 2 max)
+ *                   in NumPy's own order of operations (pairwise add.reduce), i.e. the bit-identical
+ *                   threshold; first-exit word = FF_NO_EXIT; in a range-sharded run the wait for the peers
+ *   range kernel    counts-only ranges (no image output, H*W % 32 == 0, H*W >= 128 Ki pixels): ONE kernel
+ *                   streams the frames once (TMA ring), counts above-noise pixels, decides is_empty_frame,
+ *                   resolves the detection_method on the non-empty frames (a detector warp per CTA), takes
+ *                   the exit-frame min, truncates and publishes to the peers.  The kernel starts while
+ *                   the prep kernel still runs (programmatic dependent launch).
+ *   otherwise       ff_stream_frames -> ff_detect, with the same tail in ff_detect's last CTA.
+ * ff_process_range_plan tells the caller what to allocate: workspace_bytes (zero-filled ONCE by its owner;
+ * every call leaves it zero-filled again, so it can be reused without clearing), partial_elems (int32
+ * scratch of the three-kernel form, 0 when the range runs fused) and whether it runs fused.
+ *
+ *   scalars_dev     int32[16] clip-scalar block.  [0] background scalar, [1] floor(flame threshold);
+ *                   float64 at byte 16: centre-row mean, std, max, flame threshold (threshold method only).
+ *                   Written by the prep kernel when frame0_dev != NULL, else [0] is read (ff_background's
+ *                   output) and threshold_floor is taken from the argument.
+ *   centerline_dev  uint16[W] centre row of frame 0 for the host's own float64 statistics, nullable
+ *   empty_thr       as ff_stream_frames (< 0: derived from the background scalar on the device)
+ *   init_first_exit set *first_exit_dev = FF_NO_EXIT first (else the caller did, or carries a value in)
+ *   truncate        drop positions at/after *first_exit_dev (single-GPU; range-sharded runs truncate in
+ *                   the merge against the global exit frame)
+ *   hooks           range-sharded runs: from ff_exchange_begin (NULL or zeroed otherwise)                */
+#define FF_HOOK_WAIT     1   /* before the block is written: wait until the peers no longer read its previous use */
+#define FF_HOOK_PUBLISH  2   /* when the block is complete: tell the peers (flag = epoch)                          */
+typedef struct ff_range_hooks {
+  void*    table_dev;     /* device table of the peers' exchange buffers (owned by the ff_exchange)       */
+  int32_t  epoch, world, rank, flags;
+  int64_t  spin_limit;    /* GPU clock ticks a device-side wait may take before it raises the status word */
+  int32_t* exit_word_dev; /* this rank's copy of the clip-global exit-frame min (host-streamed path polls it) */
+} ff_range_hooks;
+
+typedef struct ff_range_args {
+  const void* frames_dev;
+  const void* halo_dev;
+  const void* frame0_dev;
+  int64_t n_frames, first_frame;
+  int32_t height, width, bits;
+  int32_t method, use_frame_diff, min_run_px, exit_margin_px;
+  int32_t diff_thr, grad2_bound, empty_thr, threshold_floor;
+  int64_t min_signal_count;
+  const uint8_t* skip_dev;
+  int32_t*  scalars_dev;
+  uint16_t* centerline_dev;
+  int32_t*  pos_out_dev;
+  int32_t*  count_out_dev;
+  int32_t*  first_exit_dev;
+  int32_t   init_first_exit, truncate;
+  void*     diff_out_dev;
+  int32_t   diff_dtype, reserved;
+  uint16_t* decoded_out_dev;
+  int32_t*  profile_out_dev;
+  int32_t*  partial_dev;
+  void*     workspace_dev;
+  const ff_range_hooks* hooks;
+} ff_range_args;
+
+int ff_process_range_plan(int64_t n_frames, int height, int width, int bits, int diff_dtype, int want_decoded,
+                          int want_profiles, int64_t* workspace_bytes, int64_t* partial_elems, int* fused);
+int ff_process_range(const ff_range_args* args, void* stream);
+
 /* ---- stage 4 across GPUs: the one exchange step of a range-sharded clip -----------------------------
  * Replaces the pickled `comm.gather` + sort of per-rank result lists (scripts/process_videos.py:
  * 1533-1541) and turns the per-rank `break` (:1494) into the global truncation of README.md:145-149.
@@ -160,20 +227,30 @@ int ff_truncate(int32_t* pos_dev, int64_t n_frames, int64_t first_frame,
  * ff_merge_ranges finishes: global exit = min of the headers, truncation, de-padding into
  * pos_out_dev[total] / count_out_dev[total] (nullable) / first_exit_out_dev[1].
  *
- * Transport 2 - peer memory (one box, NVLink): ff_exchange_* keeps the blocks where ff_detect wrote
- * them; peers map them through CUDA IPC and ONE kernel per rank publishes an epoch flag to every
- * peer, waits for theirs, pulls their blocks over NVLink and merges - no collective call on the
- * data path.  Blocks are double-buffered by epoch parity, so a step needs no second barrier.
- *   ff_exchange_create      allocates the local blocks + flag row (cap_frames per block)
+ * Transport 2 - peer memory (one box, NVLink): ff_exchange_* keeps the blocks where they were written;
+ * peers map every rank's exchange buffer through CUDA IPC.  No collective and no barrier on the data path:
+ *   - the LAST CTA of ff_process_range's kernel publishes the finished block (epoch flag in every peer's
+ *     buffer, st.release.sys) - the compute kernel publishes, not the merge;
+ *   - ff_exchange_finish launches the merge kernel (wait for the flags, pull the blocks over NVLink, global
+ *     exit min, truncation, de-padding).  It depends on nothing but the flags, so the caller may launch it
+ *     on a SIDE stream and go on with the next clip on the main stream;
+ *   - the merge acknowledges to the peers that their blocks are no longer read; blocks are double-buffered by
+ *     epoch parity and the prep kernel of epoch e waits for the acks of e-2 before anything is overwritten;
+ *   - every exit frame a detecting warp sees is min-reduced into an exit word in EVERY rank's buffer
+ *     (red.min.sys); ff_process_host_range polls its rank's copy between chunks and stops uploading frames
+ *     that lie behind it - the reference's `break` (scripts/process_videos.py:1494) across ranks.
+ *   ff_exchange_create      allocates the local blocks + flag / ack / exit words (cap_frames per block)
  *   ff_exchange_get_handle  writes ff_exchange_handle_bytes() bytes to exchange with the peers
  *   ff_exchange_open_peers  handles = world * handle_bytes, rank-major (own slot ignored)
- *   ff_exchange_begin       next epoch: returns this epoch's pos/count/first_exit device pointers
- *                           (first_exit reset to FF_NO_EXIT on `stream`) for ff_detect to fill
- *   ff_exchange_finish      the fused publish/wait/pull/merge kernel; every rank must call it once
- *                           per ff_exchange_begin
- *   ff_exchange_status      synchronises `stream`; *status_out != 0 means a peer (value-1) never
- *                           published within FF_EXCHANGE_TIMEOUT_S seconds (environment, default 20)
- *                           and the outputs are invalid                                                */
+ *   ff_exchange_begin       next epoch: this epoch's pos/count/first_exit device pointers and the hooks to hand
+ *                           to ff_process_range / ff_process_host_range (which wait, fill, publish)
+ *   ff_exchange_acquire /   for a block filled by hand instead: wait for the peers + reset the header before
+ *   ff_exchange_publish     writing it / publish it afterwards (both asynchronous on `stream`)
+ *   ff_exchange_finish      the merge kernel; every rank calls it once per ff_exchange_begin
+ *   ff_exchange_status      synchronises `stream`; *status_out != 0 means a wait timed out after
+ *                           FF_EXCHANGE_TIMEOUT_S seconds (environment, default 20): 1+r = rank r never
+ *                           published (the merge then wrote FF_POS_NONE / FF_NO_EXIT), 0x100+r = rank r never
+ *                           acknowledged.  Reading clears it.                                              */
 int ff_range_block_len(int64_t cap_frames, int64_t* n_elems);
 int ff_merge_ranges(const int32_t* gathered_dev, int world, int64_t block_cap_frames, int64_t total_frames,
                     int32_t* pos_out_dev, int32_t* count_out_dev, int32_t* first_exit_out_dev, void* stream);
@@ -183,7 +260,9 @@ int ff_exchange_handle_bytes(void);
 int ff_exchange_get_handle(ff_exchange* x, void* handle_out);
 int ff_exchange_open_peers(ff_exchange* x, const void* handles);
 int ff_exchange_begin(ff_exchange* x, int32_t** pos_dev, int32_t** count_dev, int32_t** first_exit_dev,
-                      void* stream);
+                      ff_range_hooks* hooks_out);
+int ff_exchange_acquire(ff_exchange* x, void* stream);
+int ff_exchange_publish(ff_exchange* x, void* stream);
 int ff_exchange_finish(ff_exchange* x, int64_t total_frames, int32_t* pos_out_dev, int32_t* count_out_dev,
                        int32_t* first_exit_out_dev, void* stream);
 int ff_exchange_status(ff_exchange* x, int32_t* status_out, void* stream);
@@ -277,12 +356,15 @@ int ff_head_images(const void* frames_dev, const void* halo_dev, int64_t n_frame
 typedef struct ff_host_ctx ff_host_ctx;
 int ff_host_ctx_create(int device, int64_t chunk_bytes, ff_host_ctx** ctx_out);
 int ff_host_ctx_destroy(ff_host_ctx* ctx);
+/* Threads that fill the pinned bounce buffers from a pageable source (1..16; default FF_HOST_COPY_THREADS
+ * or half the cores) - e.g. cores / ranks when several ranks share a host.                             */
+int ff_host_ctx_set_copy_threads(ff_host_ctx* ctx, int n_threads);
 /* Blocking host -> device copy of `bytes` bytes for the device-resident entry points.  Pinned or
  * registered sources are DMA'd in place; pageable ones (e.g. np.memmap of the .mraw file, the
  * array the reference gets from pyMRAW at src/photron/video.py:332) are moved through the
- * context's pinned bounce buffers, filled by FF_HOST_COPY_THREADS threads (default: half the
- * cores) while the previous piece's DMA is in flight - 40 GB/s from the page cache against
- * 11 GB/s for a plain cudaMemcpy of pageable memory on the measured box.                        */
+ * context's pinned bounce buffers, filled by the copy threads while the previous piece's DMA is in
+ * flight - 40 GB/s from the page cache against 11 GB/s for a plain cudaMemcpy of pageable memory on
+ * the measured box.                                                                             */
 int ff_host_upload(ff_host_ctx* ctx, const void* src_host, void* dst_dev, int64_t bytes);
 int ff_process_host(ff_host_ctx* ctx,
                     const void* frames_host, const void* halo_host, int64_t n_frames,
@@ -293,6 +375,32 @@ int ff_process_host(ff_host_ctx* ctx,
                     int32_t exit_margin_px, const uint8_t* skip_host,
                     int32_t* pos_out_host, int32_t* count_out_host,
                     int64_t* frames_done_out, int32_t* first_exit_out);
+/* The same for one rank's range of a range-sharded clip: results may stay on the device in the rank's range
+ * block (pos_block_dev / count_block_dev / first_exit_block_dev from ff_exchange_begin; the host arrays are
+ * then optional), `hooks` ties the range to the peers - wait before the block is written, exit frames
+ * propagated to every rank, block published when the last chunk is done - and uploading stops at the first
+ * chunk that starts at or behind the smallest exit frame ANY rank has seen.
+ *   bytes_uploaded_out   host -> device bytes actually moved (the early stop is what keeps it small)     */
+typedef struct ff_host_args {
+  const void* frames_host;
+  const void* halo_host;
+  int64_t n_frames, first_frame;
+  int32_t height, width, bits;
+  int32_t bg, empty_thr;
+  int32_t method, use_frame_diff, diff_thr, threshold_floor, grad2_bound, min_run_px, exit_margin_px;
+  int64_t min_signal_count;
+  const uint8_t* skip_host;
+  int32_t* pos_out_host;
+  int32_t* count_out_host;
+  int32_t* pos_block_dev;
+  int32_t* count_block_dev;
+  int32_t* first_exit_block_dev;
+  const ff_range_hooks* hooks;
+  int64_t* frames_done_out;
+  int32_t* first_exit_out;
+  int64_t* bytes_uploaded_out;
+} ff_host_args;
+int ff_process_host_range(ff_host_ctx* ctx, const ff_host_args* args);
 
 #ifdef __cplusplus
 }

@@ -64,11 +64,10 @@ def main() -> None:
             for step in range(args.steps):
                 blk = ex.begin(n_frames)
                 eng.process_range(mine, b - a, spec.height, spec.width, 12, params, frame0=frame0, first_frame=a,
-                                  halo=halo, truncate=False, pos_out=blk.pos, counts_out=blk.counts,
-                                  first_exit=blk.first_exit)
+                                  halo=halo, **ex.range_kwargs(blk))
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                g = ex.finish(blk)
+                g = ex.finish(blk).wait()        # (the merge runs on a side stream; wait() joins it)
                 e1.record()
                 torch.cuda.synchronize()
                 if step >= 3:

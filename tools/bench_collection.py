@@ -54,13 +54,86 @@ def clip_config(i: int) -> VideoSourceConfig:
     return cfg
 
 
+def run_collection(eng, exchange, device, rank: int, world: int, clips: int, frames: int, vdir, reps: int = 3,
+                   residency: str = "auto", pin: bool = True) -> dict:
+    """Write `clips` recordings under `vdir` (each rank writes the ones it will process), open them as a
+    VideoCollection, stage this rank's videos in pinned memory and time ``process_collection``.
+    Returns {"summary": JSON-able figures, "results", "specs", "configs", "mine"}."""
+    vdir = Path(vdir)
+    specs = [clip_spec(i, frames) for i in range(clips)]
+    weights = [s.n_frames * s.height * s.width for s in specs]
+    mine = assign_videos(clips, rank, world, weights)
+    t0 = time.perf_counter()
+    vdir.mkdir(parents=True, exist_ok=True)
+    for i in mine:
+        spec = specs[i]
+        packed = syn.render_packed_torch(spec, device).cpu().numpy()
+        (vdir / f"run-{i:02d}-.mraw").write_bytes(packed.tobytes())
+        (vdir / f"run-{i:02d}-.cihx").write_bytes(syn.cihx_bytes(spec, spec.n_frames))
+        del packed
+    write_s = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+
+    coll = open_collection(str(vdir))
+    assert len(coll) == clips, f"expected {clips} recordings, found {len(coll)}"
+    cfgs = [clip_config(i) for i in range(clips)]
+    t0 = time.perf_counter()
+    if pin:
+        for i in mine:
+            coll[i].pin_memory()
+    stage_s = time.perf_counter() - t0
+    my_bytes = sum(coll[i].frame_store.nbytes_raw for i in mine)
+    total_frames = sum(len(v) for v in coll)
+    total_bytes = sum(v.frame_store.nbytes_raw for v in coll)
+
+    from high_speed_image_processing_b200.process_videos import process_video
+
+    def per_video(video, cfg, cal, off):
+        return process_video(video, cfg, cal, off, engine=eng, exchange=None, residency=residency)
+
+    def run():
+        return process_collection(coll, cfgs, engine=eng, exchange=exchange if world > 1 else None,
+                                  per_video=per_video)
+
+    results = run()                                   # warm-up (allocations, contexts)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        results = run()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        times.append(dt)
+    sec = min(times)
+    n_rows = sum(len(r.rows) for r in results.values())
+    exits = sum(1 for r in results.values() if r.first_exit is not None)
+    summary = {
+        "config": f"BASELINE config 5: VideoCollection of {clips} synthetic Nova+Mini recordings x {frames} frames, mixed "
+                  f"methods / calibrations, sharded by whole videos over {world} GPU(s)",
+        "scaling": "weak", "pinned": pin, "residency": residency, "clips": clips, "frames_per_clip": frames,
+        "n_gpus": world, "total_frames": total_frames, "total_gb": total_bytes / 1e9,
+        "sharding": "whole videos, size-balanced (assign_videos)", "seconds": sec,
+        "value": total_frames / sec, "unit": "frames/s", "gbs_aggregate": total_bytes / sec / 1e9,
+        "gbs_per_gpu": total_bytes / sec / 1e9 / world, "ms_per_video": sec / (clips / world) * 1e3,
+        "all_times_s": times, "detections": n_rows, "clips_with_exit": exits,
+        "untimed": {"write_files_s": write_s, "pin_stage_s": stage_s, "rank0_bytes": my_bytes}}
+    coll.close_all()
+    return {"summary": summary, "results": results, "specs": specs, "configs": cfgs, "mine": mine}
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--clips", type=int, default=64)
     ap.add_argument("--frames", type=int, default=2000)
     ap.add_argument("--dir", default="/tmp/ff_c5")
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--check", type=int, default=3, help="clips per rank whose result rows are re-checked (calibration arithmetic)")
     ap.add_argument("--keep", action="store_true")
     ap.add_argument("--no-pin", action="store_true", help="leave the recordings memory-mapped (pageable) instead of "
                     "staging them in pinned memory: the page-cache -> GPU path a plain script would take")
@@ -77,88 +150,20 @@ def main() -> None:
     bind_to_gpu_numa_node(local)
     eng = FlameFrontEngine(local)
     exchange = RangeExchange(engine=eng)
-
-    # ---- write the recordings (each rank writes the ones it will process; untimed) -------------
-    vdir = Path(args.dir)
-    specs = [clip_spec(i, args.frames) for i in range(args.clips)]
-    weights = [s.n_frames * s.height * s.width for s in specs]
-    mine = assign_videos(args.clips, rank, world, weights)
-    t0 = time.perf_counter()
-    vdir.mkdir(parents=True, exist_ok=True)
-    for i in mine:
-        spec = specs[i]
-        packed = syn.render_packed_torch(spec, device).cpu().numpy()
-        (vdir / f"run-{i:02d}-.mraw").write_bytes(packed.tobytes())
-        (vdir / f"run-{i:02d}-.cihx").write_bytes(syn.cihx_bytes(spec, spec.n_frames))
-        del packed
-    write_s = time.perf_counter() - t0
-    if world > 1:
-        dist.barrier()
-
-    coll = open_collection(str(vdir))
-    assert len(coll) == args.clips, f"expected {args.clips} recordings, found {len(coll)}"
-    cfgs = [clip_config(i) for i in range(args.clips)]
-    t0 = time.perf_counter()
-    if not args.no_pin:
-        for i in mine:
-            coll[i].pin_memory()
-    stage_s = time.perf_counter() - t0
-    my_bytes = sum(coll[i].frame_store.nbytes_raw for i in mine)
-    total_frames = sum(len(v) for v in coll)
-    total_bytes = sum(v.frame_store.nbytes_raw for v in coll)
-
-    from high_speed_image_processing_b200.process_videos import process_video
-
-    def per_video(video, cfg, cal, off):
-        return process_video(video, cfg, cal, off, engine=eng, exchange=None, residency=args.residency)
-
-    def run():
-        return process_collection(coll, cfgs, engine=eng, exchange=exchange if world > 1 else None,
-                                  per_video=per_video)
-
-    results = run()                                   # warm-up (allocations, contexts)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    times = []
-    for _ in range(args.reps):
-        t0 = time.perf_counter()
-        results = run()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        times.append(dt)
-    sec = min(times)
-
-    # (parity of the collection path against the oracle: tests/test_gpu_pipeline.py; here only the
-    # calibration arithmetic of the rows is re-checked, which needs no oracle)
-    checked = 0
-    for i in mine[:args.check]:
-        cal, off = cfgs[i].get_calibration_for_file(f"run-{i:02d}-.cihx")
-        for frame_idx, t_s, px, p_m, _ in results[i].rows[:50]:
+    rep = run_collection(eng, exchange, device, rank, world, args.clips, args.frames, args.dir, reps=args.reps,
+                         residency=args.residency, pin=not args.no_pin)
+    # (parity of the collection path against the oracle: tests/test_gpu_pipeline.py and bench.py's c5 leg;
+    # here only the calibration arithmetic of the rows is re-checked, which needs no oracle)
+    for i in rep["mine"][:3]:
+        cal, off = rep["configs"][i].get_calibration_for_file(f"run-{i:02d}-.cihx")
+        for frame_idx, t_s, px, p_m, _ in rep["results"][i].rows[:50]:
             assert p_m == px * cal + off
-        checked += 1
-
     if rank == 0:
-        n_rows = sum(len(r.rows) for r in results.values())
-        exits = sum(1 for r in results.values() if r.first_exit is not None)
-        print(json.dumps({
-            "config": "C5", "pinned": not args.no_pin, "residency": args.residency, "clips": args.clips, "frames_per_clip": args.frames, "n_gpus": world,
-            "total_frames": total_frames, "total_gb": total_bytes / 1e9,
-            "sharding": "whole videos, size-balanced (assign_videos)", "seconds": sec,
-            "frames_per_s": total_frames / sec, "gbs_aggregate": total_bytes / sec / 1e9,
-            "gbs_per_gpu": total_bytes / sec / 1e9 / world, "ms_per_video": sec / (args.clips / world) * 1e3,
-            "all_times_s": times, "detections": n_rows, "clips_with_exit": exits,
-            "rows_rechecked_clips_rank0": checked, "untimed": {"write_files_s": write_s, "pin_stage_s": stage_s,
-                                                                "rank0_bytes": my_bytes}}), flush=True)
-    coll.close_all()
+        print(json.dumps(rep["summary"]), flush=True)
     if world > 1:
         dist.barrier()
     if rank == 0 and not args.keep:
-        shutil.rmtree(vdir, ignore_errors=True)
+        shutil.rmtree(args.dir, ignore_errors=True)
     exchange.close()
     eng.close()
     if world > 1:
