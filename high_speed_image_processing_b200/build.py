@@ -77,6 +77,82 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+SASS_MNEMONICS = [
+    ("UBLKCP", r"\bUBLKCP", "1-D bulk async copy global -> shared (TMA, cp.async.bulk)"),
+    ("SYNCS", r"\bSYNCS\.", "mbarrier operations"),
+    ("DPX 16x2", r"\bVI(ADD)?MNMX3?\.[US]16x2", "16x2 SIMD min/max/add (VIMNMX3 / VIADDMNMX .U16x2/.S16x2)"),
+    ("PRMT", r"\bPRMT\b", "byte permutes (12-bit field extraction)"),
+    ("ATOMG/REDG", r"\b(ATOMG|REDG)\.", "global atomics / reductions"),
+    ("ATOMS", r"\bATOMS\.", "shared-memory atomics"),
+    ("sys-scope", r"\.STRONG\.SYS", "system-scope loads / stores / reductions (peer memory flags)"),
+    ("ACQBULK/PDL", r"\bACQBULK\b", "griddepcontrol.wait (programmatic dependent launch)"),
+    ("NANOSLEEP", r"\bNANOSLEEP", "back-off of idle detector warps / bounded spins"),
+    ("DADD/DMUL/DFMA", r"\bD(ADD|MUL|FMA)\b", "float64 arithmetic (HEAD detector, device-side clip statistics)"),
+    ("UTMALDG", r"\bUTMALDG", "tensor-map TMA loads (none expected: tiles are a flat byte stream)"),
+    ("tensor core", r"\b(UTCMMA|HMMA|IMMA|UTCHMMA|TCGEN05)", "tensor-core instructions (none expected: no contraction on this path)"),
+]
+
+
+def sass_summary(out_path=None) -> str:
+    """Per-kernel counts of the SASS mnemonics that show what the kernels are made of (cuobjdump -sass of the
+    built library).  Written to profiles/r02_sass_summary.md by ``--verbose``."""
+    import re
+    dump = subprocess.run([str(Path(find_nvcc()).parent / "cuobjdump"), "-sass", str(LIB_PATH)], stdout=subprocess.PIPE,
+                          stderr=subprocess.STDOUT, text=True, check=True).stdout
+    try:
+        filt = shutil.which("cu++filt") or shutil.which("c++filt")
+    except Exception:
+        filt = None
+    kernels, name, arch = {}, None, set()
+    for line in dump.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            kernels[name] = {k: 0 for k, _, _ in SASS_MNEMONICS}
+            kernels[name]["instructions"] = 0
+            continue
+        m = re.match(r"\s*arch = (sm_\w+)", line)
+        if m:
+            arch.add(m.group(1))
+        if name is None or "/*" not in line or ";" not in line:
+            continue
+        kernels[name]["instructions"] += 1
+        for key, pattern, _ in SASS_MNEMONICS:
+            if re.search(pattern, line):
+                kernels[name][key] += 1
+    names = list(kernels)
+    pretty = dict(zip(names, names))
+    if filt and names:
+        res = subprocess.run([filt], input="\n".join(names), stdout=subprocess.PIPE, text=True)
+        if res.returncode == 0:
+            pretty = dict(zip(names, res.stdout.splitlines()))
+    import hashlib
+    cols = [k for k, _, _ in SASS_MNEMONICS]
+    lines = ["# SASS summary of libflamefront.so (round 2)", "",
+             f"`cuobjdump -sass` of `{LIB_PATH.relative_to(PKG_DIR.parent)}` (sha256 `{hashlib.sha256(LIB_PATH.read_bytes()).hexdigest()[:16]}`), "
+             f"{len(kernels)} kernels, architectures: {', '.join(sorted(arch)) or '?'}.  Regenerate with "
+             "`python -m high_speed_image_processing_b200.build --force --verbose`.", "",
+             "| kernel | instr | " + " | ".join(cols) + " |", "|---|---|" + "---|" * len(cols)]
+    def short(n):
+        n = re.sub(r"\(anonymous namespace\)::|ff::|void ", "", n)
+        return re.sub(r"\((?:[^()]|\([^()]*\))*\)$", "", n)[:90]
+    for n in sorted(names, key=lambda k: short(pretty[k])):
+        k = kernels[n]
+        lines.append(f"| `{short(pretty[n])}` | {k['instructions']} | " + " | ".join(str(k[c]) for c in cols) + " |")
+    tot = {c: sum(k[c] for k in kernels.values()) for c in cols}
+    lines.append("| **all kernels** | " + str(sum(k["instructions"] for k in kernels.values())) + " | " +
+                 " | ".join(f"**{tot[c]}**" for c in cols) + " |")
+    lines += ["", "Columns:"] + [f"* **{k}** - {desc}" for k, _, desc in SASS_MNEMONICS]
+    text = "\n".join(lines) + "\n"
+    if out_path is not None:
+        Path(out_path).write_text(text)
+    return text
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(path)
+    if "--verbose" in sys.argv or "--sass" in sys.argv:
+        out = PKG_DIR.parent / "profiles" / "r02_sass_summary.md"
+        sass_summary(out)
+        print(out)

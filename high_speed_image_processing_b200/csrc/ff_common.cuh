@@ -120,7 +120,6 @@ struct RangeWorkspace {
   unsigned int tail_ticket;           // CTAs of the fused / detect kernel that are done
   unsigned int pad[2];
   int32_t prep_max[kPrepMaxCtas];     // per-CTA maxima of frame 0
-  unsigned long long stats[8];        // FF_RANGE_STATS=1 (diagnostics): detector-warp cycle counters, see range_kernel
   // followed by one 64-bit word per frame, {arrivals:32 | above-noise count:32}, each on its OWN 128-byte
   // line: all CTAs sweep through the clip together, so the words of neighbouring frames are hit at the same
   // time - packed 16 to a line they serialise in one L2 slice (measured: C3 range kernel 1.79 -> 1.2 ms)

@@ -74,8 +74,15 @@ __device__ __forceinline__ void owner_of(int64_t i, int64_t base, int64_t extra,
   }
 }
 
+// Small CTAs (64 threads): on its side stream this kernel runs NEXT TO the next clip's range kernel, whose two
+// CTAs per SM leave ~5 K registers free - a CTA that does not fit there would wait for a range CTA to leave
+// and, worse, a spinning merge CTA that got in first would keep a range CTA out (measured at N=2 with
+// 256-thread CTAs: +90 us per step).
+constexpr int kMergeThreads = 64;
+static_assert(kMergeThreads >= kMaxRanks, "one thread per rank polls a flag");
+
 template <bool PEER>
-__global__ void __launch_bounds__(256) merge_ranges_kernel(const MergeParams p) {
+__global__ void __launch_bounds__(kMergeThreads) merge_ranges_kernel(const MergeParams p) {
   __shared__ int s_fe;
   __shared__ int s_ok;
   const int tid = threadIdx.x;
@@ -164,8 +171,8 @@ __global__ void publish_kernel(const RangeHooks h) {
 }
 
 int merge_grid(int64_t total) {
-  int64_t blocks = (total + 2047) / 2048;
-  if (blocks > 32) blocks = 32;       // few CTAs: this kernel shares the GPU with the next clip's range kernel
+  int64_t blocks = (total + 1023) / 1024;
+  if (blocks > 74) blocks = 74;       // few, small CTAs: this kernel shares the GPU with the next clip's range kernel
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
@@ -240,7 +247,7 @@ int ff_merge_ranges(const int32_t* gathered_dev, int world, int64_t block_cap_fr
   p.pos_out = pos_out_dev;
   p.count_out = count_out_dev;
   p.first_exit_out = first_exit_out_dev;
-  merge_ranges_kernel<false><<<merge_grid(total_frames), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  merge_ranges_kernel<false><<<merge_grid(total_frames), kMergeThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   FF_CUDA_TRY(cudaGetLastError());
   return FF_OK;
 }
@@ -389,7 +396,7 @@ int ff_exchange_finish(ff_exchange* x, int64_t total_frames, int32_t* pos_out_de
   p.publish = 0;
   p.ticket = reinterpret_cast<unsigned int*>(x->local + x->ticket_off);
   p.spin_limit = x->spin_limit;
-  merge_ranges_kernel<true><<<merge_grid(total_frames), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  merge_ranges_kernel<true><<<merge_grid(total_frames), kMergeThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   FF_CUDA_TRY(cudaGetLastError());
   return FF_OK;
 }

@@ -30,17 +30,18 @@ int process_range_impl(const RangeJob& j, cudaStream_t st) {
                    j.init_first_exit ? j.first_exit : nullptr, j.ws, j.hooks, st);
     if (rc != FF_OK) return rc;
   }
-  // Programmatic dependent launch of the streaming kernel behind prep_kernel (FF_PDL=1): measured SLOWER - the
-  // early-launched CTAs of a one-wave persistent kernel are placed while prep's CTAs still occupy some SMs,
-  // end up unevenly spread and the doubled-up SMs decide the kernel time.  Kept as a knob.
-  static const bool use_pdl = getenv("FF_PDL") != nullptr && atoi(getenv("FF_PDL")) != 0;
-  const bool pdl = need_prep && use_pdl;
+  // Programmatic dependent launch behind prep_kernel: the range kernel's CTAs come up and its producer warps
+  // fetch tiles while prep still runs (C2 step 0.577 -> 0.572 ms).  Only for the range kernel, whose CTAs fill
+  // every SM to its resource limit: a one-CTA-per-SM stream kernel launched early is placed around prep's
+  // CTAs, ends up unevenly spread, and the doubled-up SMs decide its time (C4 uint16: 3.1 -> 4.9 ms).
+  // FF_PDL=0 / 1 forces it off / on for both.
+  static const int pdl_env = getenv("FF_PDL") != nullptr ? atoi(getenv("FF_PDL")) : -1;
   const int64_t px = (int64_t)j.height * j.width;
   if (range_is_fused(px, j.diff_dtype, j.decoded_out != nullptr, j.profile_out != nullptr))
-    return range_fused_impl(d, j.bits, j.empty_thr, pdl, st);
+    return range_fused_impl(d, j.bits, j.empty_thr, need_prep && pdl_env != 0, st);
   if (j.partial == nullptr) return FF_ERR_INVALID;
   rc = stream_frames_impl(j.frames, j.halo, j.n_frames, j.height, j.width, j.bits, j.scalars, j.empty_thr, j.diff_thr,
-                          j.skip, j.partial, j.diff_out, j.diff_dtype, j.decoded_out, st, pdl);
+                          j.skip, j.partial, j.diff_out, j.diff_dtype, j.decoded_out, st, need_prep && pdl_env == 1);
   if (rc != FF_OK) return rc;
   return launch_detect(d, j.bits, false, st);
 }

@@ -41,7 +41,6 @@ struct StreamParams {
   void* diff_out;
   uint16_t* decoded_out;
   int idle_ns;             // how long an idle detector warp sleeps between looks at the queue
-  int stats;               // diagnostics (FF_RANGE_STATS=1): detector warps add their cycle counters to ws->stats
   int slab_shift;          // range_kernel: 2^slab_shift consecutive items per slab (slabs are dealt to the CTAs round-robin)
   int slab_step_frames;    // (gridDim.x << slab_shift) = slab_step_frames * tiles_per_frame + slab_step_tiles:
   int slab_step_tiles;     // how far (frame, tile) moves from one slab of a CTA to its next
@@ -480,9 +479,19 @@ __global__ void __launch_bounds__(kCountThreads) count12_kernel(const StreamPara
 
 int sm_count_cached();
 
+// The streaming kernels are ONE wave of long-lived CTAs, `ctas` per SM by design (bytes in flight per SM are
+// tuned).  The hardware would happily put more of them on an SM when another small kernel (prep, the merge of
+// the previous clip on its side stream, a PDL predecessor) occupies some other SM at launch time - and the
+// doubled-up SMs then decide the kernel's time (measured: C4 uint16 1.55 -> 2.26 ms next to a 2-CTA merge).
+// Asking for at least 1/(ctas+1) of an SM's shared memory makes `ctas` per SM the only possible placement.
+constexpr int kSmemPerSm = 227 * 1024;
+constexpr int pinned_smem(int needed, int ctas) {
+  return needed > kSmemPerSm / (ctas + 1) + 1024 ? needed : kSmemPerSm / (ctas + 1) + 1024;
+}
+
 template <int BITS, int kCountStages>
 int launch_count12(StreamParams p, cudaStream_t st) {
-  constexpr int kSmem = kCountStages * (4 * kThreads * BITS) + 2 * kCountStages * 8;
+  constexpr int kSmem = pinned_smem(kCountStages * (4 * kThreads * BITS) + 2 * kCountStages * 8, kCountCtasPerSm);   // 2 per SM
   auto kern = count12_kernel<BITS, kCountStages>;
   static PerDeviceInt cache;
   int ctas = 1;
@@ -625,9 +634,7 @@ __global__ void __launch_bounds__(kFusedThreads) range_kernel(const StreamParams
     // An idle detector warp must not poll often: 8 of them per SM looking at the queue every 100 ns took 17 % of
     // the issue slots from the consumers (C2 step 0.619 -> 0.584 ms).  Back off while idle, be quick after work.
     int idle_ns = 250;
-    long long t_atom = 0, t_det = 0, t_done = 0, n_det = 0, n_iter = 0;
     for (;;) {
-      if (p.stats && t_done == 0 && ctl[1] == kWarpsPerCta) t_done = clock64();
       // the leading run of my filled queue slots, one per lane (kQueue / kDetWarps = 32 of mine fit the ring)
       const int slot = (head + lane * kDetWarps) % kQueue;
       const int fq = q_f[slot];
@@ -644,8 +651,6 @@ __global__ void __launch_bounds__(kFusedThreads) range_kernel(const StreamParams
       }
       idle_ns = 250;
       bool need = false;
-      const long long ta = p.stats ? clock64() : 0;
-      ++n_iter;
       if (lane < take) {
         const int cnt = q_cnt[slot];
         q_f[slot] = -1;
@@ -668,9 +673,6 @@ __global__ void __launch_bounds__(kFusedThreads) range_kernel(const StreamParams
       __syncwarp();
       if (lane == 0) ctl[4 + dw] = head;                   // my slots may be refilled
       unsigned pending = __ballot_sync(full_mask, need);
-      const long long tb = p.stats ? clock64() : 0;
-      t_atom += tb - ta;
-      n_det += __popc(pending);
       while (pending) {
         const int src = __ffs((int)pending) - 1;
         pending &= pending - 1;
@@ -678,17 +680,6 @@ __global__ void __launch_bounds__(kFusedThreads) range_kernel(const StreamParams
         const int pos = detect_one_frame<BITS>(d, rs, f, false, bg_raw, thr_floor, prof, raw_cur, raw_pri, lane);
         if (lane == 0) commit_position(d, f, pos);
       }
-      if (p.stats) t_det += clock64() - tb;
-    }
-    if (p.stats && lane == 0) {
-      unsigned long long* st = d.ws->stats;
-      atomicAdd(st + 0, (unsigned long long)t_atom);
-      atomicAdd(st + 1, (unsigned long long)t_det);
-      atomicAdd(st + 2, (unsigned long long)n_det);
-      atomicAdd(st + 3, (unsigned long long)n_iter);
-      atomicMax(st + 4, (unsigned long long)(t_done ? clock64() - t_done : 0));     // longest tail behind the consumers
-      atomicMax(st + 5, (unsigned long long)t_det);
-      atomicMax(st + 6, (unsigned long long)t_atom);
     }
     // the detector warp that leaves last finishes the CTA's part of the range
     int last = 0;
@@ -823,7 +814,6 @@ int launch_range_fused(StreamParams p, const DetectParams& d, cudaStream_t st) {
   int shift = 0;
   while ((2ll << shift) <= slab) ++shift;                  // largest power of two <= slab
   p.slab_shift = shift;
-  p.stats = getenv("FF_RANGE_STATS") != nullptr;
   static const int idle_env = getenv("FF_RANGE_IDLE_NS") ? atoi(getenv("FF_RANGE_IDLE_NS")) : 0;     // tuning knob
   p.idle_ns = idle_env > 0 ? idle_env : 4000;
   const int64_t n_slabs = (total_work + (1ll << shift) - 1) >> shift;
@@ -1053,25 +1043,26 @@ int sm_count_cached();
 
 template <int BITS, bool COUNT, bool DIFF, bool DECODED, int STAGES>
 int launch_streamx(StreamParams p, int ctas_cap, cudaStream_t st) {
-  constexpr int kSmem = STAGES * (4 * kThreads * BITS) + 2 * STAGES * 8;
+  constexpr int kNeeded = STAGES * (4 * kThreads * BITS) + 2 * STAGES * 8;
   auto kern = streamx_kernel<BITS, COUNT, DIFF, DECODED, STAGES>;
   static PerDeviceInt cache;
   int ctas = 1;
   int rc = cache.get([&](int* v) -> int {
-    FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerSm));
     int occ = 0;
-    FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kOutThreads, kSmem));
+    FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kOutThreads, kNeeded));
     if (occ > ctas_cap) occ = ctas_cap;
     *v = occ > 0 ? occ : 1;
     return FF_OK;
   }, &ctas);
   if (rc != FF_OK) return rc;
+  const int smem = pinned_smem(kNeeded, ctas);       // exactly `ctas` CTAs fit an SM, whatever else runs
   const int64_t wave = (int64_t)sm_count_cached() * ctas;
   const int64_t total_work = (int64_t)p.tiles_per_frame * p.n_frames;
   p.items_per_cta = (total_work + wave - 1) / wave;
   if (p.items_per_cta < 1) p.items_per_cta = 1;
   const int64_t grid = (total_work + p.items_per_cta - 1) / p.items_per_cta;
-  return launch_kernel(kern, dim3((unsigned)grid), dim3(kOutThreads), kSmem, st, p.pdl != 0, p);
+  return launch_kernel(kern, dim3((unsigned)grid), dim3(kOutThreads), smem, st, p.pdl != 0, p);
 }
 
 template <int BITS, bool COUNT, bool DIFF, bool DECODED>
@@ -1168,13 +1159,14 @@ template <int BITS, bool COUNT, int DIFF, bool DECODED, int K>
 int launch_stream(StreamParams p, cudaStream_t st) {
   auto kern = stream_kernel<BITS, COUNT, DIFF, DECODED, K>;
   constexpr int kStageBytes = K * kThreads * BITS;
-  constexpr int kSmem = kStages * kStageBytes + kStages * 8;
+  constexpr int kNeeded = kStages * kStageBytes + kStages * 8;
+  constexpr bool kCapped = DIFF == FF_DIFF_F64 || DIFF == FF_DIFF_F32;
   static PerDeviceInt cache;
   int ctas = 1;
   int rc = cache.get([&](int* v) -> int {
-    FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kCapped ? kSmemPerSm : kNeeded));
     int occ = 0;
-    FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, kSmem));
+    FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, kNeeded));
     // Write-heavy variants run faster with FEWER resident CTAs (fewer concurrent DRAM streams):
     // measured on C4, float64 difference 0.86 -> 0.95 of the copy rate at 1 CTA/SM, float32
     // 0.82 -> 0.87 at 2 (profiles/r01_count12_sweep.txt).  FF_STREAM_CTAS overrides (tuning knob).
@@ -1185,6 +1177,7 @@ int launch_stream(StreamParams p, cudaStream_t st) {
     return FF_OK;
   }, &ctas);
   if (rc != FF_OK) return rc;
+  const int smem = kCapped ? pinned_smem(kNeeded, ctas) : kNeeded;     // see pinned_smem
   // One resident wave: the (tile, frame) items are split evenly over SMs x CTAs/SM long-lived CTAs.
   const int64_t wave = (int64_t)sm_count_cached() * ctas;
   const int64_t total_work = (int64_t)p.tiles_per_frame * p.n_frames;
@@ -1192,7 +1185,7 @@ int launch_stream(StreamParams p, cudaStream_t st) {
   if (p.items_per_cta < 1) p.items_per_cta = 1;
   const int64_t grid = (total_work + p.items_per_cta - 1) / p.items_per_cta;
   if (grid > 0x7FFFFFFF) return FF_ERR_UNSUPPORTED;
-  return launch_kernel(kern, dim3((unsigned)grid), dim3(kThreads), kSmem, st, p.pdl != 0, p);
+  return launch_kernel(kern, dim3((unsigned)grid), dim3(kThreads), smem, st, p.pdl != 0, p);
 }
 
 template <int BITS, bool COUNT, int DIFF, bool DECODED>

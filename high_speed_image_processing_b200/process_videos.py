@@ -79,9 +79,12 @@ class VideoSourceConfig:
     use_absolute_time: bool = True
     skip_frames: List[int] = field(default_factory=list)
     file_calibrations: List[FileCalibration] = field(default_factory=list)
-    # README-era switch (README.md:55,62,132-141), absent from the reference's HEAD dataclass
-    detection_method: str = "half_maximum"
-    exit_margin_px: int = 10                 # README.md:146 (HEAD's detector uses 15, :193)
+    # "head" (default) = what the reference executes: FlameDetector (:220-663) with its FlameDetectorConfig
+    # defaults (exit margin 15, :193), the 7-column velocity file and the pre-/post-DDT files (:1561-1619).
+    # "threshold" / "gradient" / "half_maximum" = the README-era switch (README.md:55,62,132-141), absent from
+    # the reference's HEAD dataclass: opt-in extensions with the 4-column file of README.md:90-97.
+    detection_method: str = "head"
+    exit_margin_px: int = 10                 # README-era methods only: README.md:146
     frame_diff_threshold: float = 5.0        # FlameDetectorConfig.frame_diff_threshold (:169)
     min_gradient_strength: float = 10.0      # FlameDetectorConfig.min_gradient_strength (:174)
     min_run_px: int = 1
@@ -320,17 +323,57 @@ def _head_walk_range(eng, video: PhotonVideo, hp: HeadParams, calibration: float
     return track, flags, state, pending
 
 
+def _head_lines_range(eng, video: PhotonVideo, hp: HeadParams, a: int, b: int, skip_np: Optional[np.ndarray],
+                      frame0_dev, exit_known=None):
+    """The image part of the HEAD detector for frames [a, b) in chunks - upload (+ halo), streaming kernel,
+    band kernel - keeping only the two float64 centre rows and the flag of every frame on the device
+    (16 W + 1 bytes per frame).  Everything that costs PCIe or HBM bandwidth happens here, and none of it
+    depends on the tracker's state.  ``exit_known()`` (polled between chunks) ends the uploads early.
+    Returns ``([(c0, c1, lines, flags_dev), ...], pending scalars)``."""
+    import torch
+    (h, w), bits = video.frame_shape, video.storage_bits
+    fb = video.raw_frames(0, 1).size
+    step = _head_chunk_frames(fb)
+    chunks, pending = [], None
+    prev_dev, prev_hi = None, -1
+    for c0 in range(a, b, step):
+        if exit_known is not None and exit_known():
+            break
+        c1 = min(b, c0 + step)
+        halo_idx = c0 - 1
+        if skip_np is not None:
+            while halo_idx >= 0 and skip_np[halo_idx]:
+                halo_idx -= 1
+        if halo_idx < 0:
+            halo_dev = None
+        elif prev_dev is not None and halo_idx == prev_hi - 1:
+            halo_dev = prev_dev[-fb:].clone()
+        else:
+            halo_dev = eng.upload(video.raw_frames(halo_idx, halo_idx + 1))
+        prev_dev = None
+        frames_dev = eng.upload(video.raw_frames(c0, c1))
+        skip_dev = None if skip_np is None else torch.from_numpy(skip_np[c0:c1].copy()).to(eng.device)
+        lines, flags_dev, pend = eng.head_lines(frames_dev, c1 - c0, h, w, bits, hp, frame0=frame0_dev,
+                                                first_frame=c0, halo=halo_dev, skip=skip_dev)
+        pending = pending or pend
+        chunks.append((c0, c1, lines, flags_dev))
+        prev_dev, prev_hi = frames_dev, c1
+    return chunks, pending
+
+
 def _process_video_head(video: PhotonVideo, config: VideoSourceConfig, calibration: float, offset: float,
                         eng, exchange=None) -> VideoResult:
     """HEAD-parity mode: the reference loop :1441-1516 with ``FlameDetector.detect`` on the GPU.
 
     The recording goes through the device in bounded chunks (``_head_walk_range``), and nothing is
     uploaded past the chunk in which the walk stops.  With an ``exchange`` over several ranks the clip
-    is split into contiguous frame ranges like the other methods: every rank runs the image pipeline on
-    its range (``engine.head_lines`` - all of the HBM and PCIe traffic); the search, sequential only
-    through (last frame, last position), runs range after range: a rank receives that 3-int state from
-    its predecessor, walks its range (``ff_head_track``, ~0.1 ms) and passes the state on; one
-    all-gather of the int32 result rows finishes the clip.  Results are identical on every rank."""
+    is split into contiguous frame ranges like the other methods: every rank FIRST runs the image pipeline
+    on its range (``_head_lines_range`` - all of the HBM and PCIe traffic, in parallel on all ranks) and keeps
+    the centre rows on the device; the search, sequential only through (last frame, last position), then
+    runs range after range: a rank receives that 3-int state from its predecessor (requested before the
+    image pipeline, waited for after it), walks its stored rows (``ff_head_track``, ~0.1 ms) and passes the
+    state on; one all-gather of the int32 result rows finishes the clip.  A rank stops uploading as soon
+    as its predecessor reports that the flame left before its range.  Results are identical on every rank."""
     import torch
     import torch.distributed as dist
     from ._cabi import FF_NO_EXIT
@@ -359,11 +402,30 @@ def _process_video_head(video: PhotonVideo, config: VideoSourceConfig, calibrati
         a, b = exchange.my_range(n)
         rank, size, group = exchange.rank, exchange.size, exchange.group
         peer = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+        from .head import max_displacement_px
         state = torch.tensor(start, dtype=torch.int32, device=eng.device)
-        if rank > 0:
-            dist.recv(state, src=peer(rank - 1), group=group)
-        track, flags, after, pending = _head_walk_range(eng, video, hp, calibration, a, b, skip_np, frame0,
-                                                        tuple(int(v) for v in state.tolist()))
+        # The predecessor's tracker state is asked for FIRST and waited for LAST: every rank runs its image
+        # pipeline (all PCIe and HBM traffic) at once; only the search (~0.1 ms per range) goes rank by rank.
+        req = dist.irecv(state, src=peer(rank - 1), group=group) if rank > 0 else None
+
+        def exit_before_my_range() -> bool:      # the predecessor is done and the flame has left already
+            return req is not None and req.is_completed() and int(state[0].item()) != FF_NO_EXIT
+
+        chunks, pending = _head_lines_range(eng, video, hp, a, b, skip_np, frame0, exit_before_my_range)
+        if req is not None:
+            req.wait()
+        after = tuple(int(v) for v in state.tolist())
+        track = np.full((b - a, 5), -1, dtype=np.int32)
+        flags = np.zeros(b - a, dtype=np.uint8)
+        maxdisp = max_displacement_px(video.frame_rate, calibration, hp)
+        for c0, c1, lines, flags_dev in chunks:
+            if after[0] != FF_NO_EXIT:
+                break
+            track_dev, stop_dev = eng.head_track_lines(lines, flags_dev, c0, w, hp, maxdisp, (after[1], after[2]))
+            track[c0 - a:c1 - a] = track_dev.cpu().numpy()
+            flags[c0 - a:c1 - a] = flags_dev.cpu().numpy()
+            after = tuple(int(v) for v in stop_dev.tolist())
+        del chunks
         if rank + 1 < size:
             dist.send(torch.tensor(after, dtype=torch.int32, device=eng.device), dst=peer(rank + 1), group=group)
         cap = exchange.block_cap(n)
@@ -571,12 +633,13 @@ def process_collection(collection, configs, engine=None, exchange=None, balance:
     return dict(sorted(merged.items()))
 
 
-def default_configs() -> List[VideoSourceConfig]:
-    """The two sources hard-coded in the reference's main() (:1646-1685) with the README's
-    method choice per camera (README.md:55,62)."""
+def default_configs(readme_methods: bool = False) -> List[VideoSourceConfig]:
+    """The two sources hard-coded in the reference's main() (:1646-1685), processed like the reference does
+    (``detection_method = "head"``).  ``readme_methods=True`` selects the README's per-camera methods instead
+    (README.md:55,62: half_maximum for Nova, threshold for Mini)."""
     nova = VideoSourceConfig(name="Nova")
     nova.enabled = True
-    nova.detection_method = "half_maximum"
+    nova.detection_method = "half_maximum" if readme_methods else "head"
     nova.video_path = "./Nova-Video-Files"
     nova.output_dir = "./Processed-Photos/Nova-Output"
     nova.file_calibrations = [
@@ -586,7 +649,7 @@ def default_configs() -> List[VideoSourceConfig]:
     ]
     mini = VideoSourceConfig(name="Mini")
     mini.enabled = True
-    mini.detection_method = "threshold"
+    mini.detection_method = "threshold" if readme_methods else "head"
     mini.video_path = "./Mini-Video-Files"
     mini.output_dir = "./Processed-Photos/Mini-Output"
     mini.file_calibrations = [

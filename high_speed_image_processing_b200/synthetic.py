@@ -231,9 +231,13 @@ def write_clip(directory, stem: str, spec: SyntheticSpec, frames: Optional[np.nd
 # torch renderer (GPU) for benchmark-sized clips
 # --------------------------------------------------------------------------------------
 def render_packed_torch(spec: SyntheticSpec, device, start: int = 0, stop: Optional[int] = None,
-                        chunk: int = 512, out=None):
+                        chunk: Optional[int] = None, out=None):
     """Packed bytes of frames [start, stop) as a uint8 tensor on ``device`` (same model as the
-    NumPy renderer, torch's Philox stream).  Synthetic-data generation only - not the hot path."""
+    NumPy renderer, torch's Philox stream).  Synthetic-data generation only - not the hot path.
+
+    The noise is drawn per ALIGNED block of ``chunk`` frames (seeded with the block's first frame), so any
+    sub-range equals the same slice of the full render - ranks that render their own frame ranges, a halo
+    frame rendered on its own and a whole-clip render on one GPU all see the same recording."""
     import torch
     stop = spec.n_frames if stop is None else stop
     n = stop - start
@@ -241,15 +245,17 @@ def render_packed_torch(spec: SyntheticSpec, device, start: int = 0, stop: Optio
     if out is None:
         out = torch.empty(n * fb, dtype=torch.uint8, device=device)
     h, w = spec.height, spec.width
+    if chunk is None:                                    # a function of the frame shape only
+        chunk = max(16, min(512, (1 << 27) // (h * w)))
     gen = torch.Generator(device=device)
     rows = (torch.arange(h, device=device, dtype=torch.float32) - (h // 2)) / max(1.0, h / 2.0)
     lag = spec.curvature_px * rows ** 2                                    # [h]
     xs = torch.arange(w, device=device, dtype=torch.float32)
     inv = 1.0 / (math.sqrt(2.0) * spec.edge_sigma)
-    for a in range(start, stop, chunk):
-        b = min(stop, a + chunk)
-        gen.manual_seed(spec.seed * 1_000_003 + a)
-        img = torch.randn((b - a, h, w), generator=gen, device=device, dtype=torch.float32)
+    for blk in range((start // chunk) * chunk, stop, chunk):
+        a, b = max(start, blk), min(stop, blk + chunk)
+        gen.manual_seed(spec.seed * 1_000_003 + blk)
+        img = torch.randn((chunk, h, w), generator=gen, device=device, dtype=torch.float32)[a - blk:b - blk]
         img.mul_(spec.noise_std).add_(spec.noise_mean)
         t = torch.arange(a, b, device=device, dtype=torch.float32)
         xf = spec.x_enter + spec.velocity * (t - spec.t_enter)              # [n]
