@@ -544,9 +544,14 @@ constexpr int kFusedThreads = kThreads + 32 + 32 * kDetWarps;   // 8 consumer wa
 constexpr int kQueue = 128;                               // (frame, count) entries waiting for the detector warps
 constexpr int kSegRing = 16;                              // segment words in flight (warps drift < ring depth items apart)
 
-template <int BITS, int kCountStages>
+// An ITEM is kItemKB KiB of a frame's stored bytes whatever the bit depth (8-bit: 12288 / 24576 pixels, 12-bit:
+// 8192 / 16384, 16-bit: 6144 / 12288): the per-item costs - barrier round trip, warp reduction, lane-0
+// bookkeeping - are paid per byte moved, not per pixel (8-KB items of 8-bit pixels ran at 0.82 of the copy rate).
+template <int BITS, int kCountStages, int kItemKB>
 __global__ void __launch_bounds__(kFusedThreads) range_kernel(const StreamParams p, const DetectParams d) {
-  constexpr int kTileBytes = 4 * kThreads * BITS;
+  constexpr int kTileBytes = kItemKB * 1024;
+  constexpr int kTileGroups = kTileBytes / BITS;          // 8-pixel groups per item
+  static_assert(kTileBytes % (48 * kThreads) == 0, "an item is a whole number of 48-byte thread slices");
   constexpr int kMaxPx = BITS == 8 ? 255 : (BITS == 12 ? 4095 : 65535);
   static_assert(kCountStages < kSegRing, "segment ring must outlast the tile ring");
   extern __shared__ __align__(128) uint8_t smem[];
@@ -605,8 +610,8 @@ __global__ void __launch_bounds__(kFusedThreads) range_kernel(const StreamParams
         for (int64_t i = i0; i < i1; ++i, ++it) {
           const int s = it % kCountStages;
           mbar_wait(&empty[s], ((it / kCountStages) & 1) ^ 1);   // first pass: fresh barriers pass at once
-          const int64_t g0 = (int64_t)tile * (4 * kThreads);
-          const uint32_t bytes = (uint32_t)min((int64_t)(4 * kThreads), groups_per_frame - g0) * (uint32_t)BITS;
+          const int64_t g0 = (int64_t)tile * kTileGroups;
+          const uint32_t bytes = (uint32_t)min((int64_t)kTileGroups, groups_per_frame - g0) * (uint32_t)BITS;
           mbar_arrive_expect_tx(&full[s], bytes);
           bulk_g2s(smem + s * kTileBytes, p.frames + f * p.frame_bytes + (int64_t)tile * kTileBytes, bytes, &full[s], policy);
           if (++tile == T) { tile = 0; ++f; }
@@ -698,7 +703,6 @@ __global__ void __launch_bounds__(kFusedThreads) range_kernel(const StreamParams
   const uint32_t kA2 = kA * 0x00010001u;
   const uint32_t nkA2 = ((0x10000u - kA) & 0xFFFFu) * 0x00010001u;
   const uint32_t nc2 = ((0x10000u - c) & 0xFFFFu) * 0x00010001u;
-  const int my_group = tid * 4;
 
   uint32_t it = 0;
   unsigned seg_no = 0;                   // segments this warp has finished (the same sequence in every warp)
@@ -714,14 +718,18 @@ __global__ void __launch_bounds__(kFusedThreads) range_kernel(const StreamParams
     for (int64_t i = i0; i < i1; ++i, ++it) {
       const int s = it % kCountStages;
       mbar_wait(&full[s], (it / kCountStages) & 1);
-      const int tile_groups = (int)min((int64_t)(4 * kThreads), groups_per_frame - (int64_t)tile * (4 * kThreads));
+      const int tile_groups = (int)min((int64_t)kTileGroups, groups_per_frame - (int64_t)tile * kTileGroups);
       uint32_t acc = 0;
       if (BITS == 12) {
-        if (my_group < tile_groups) {        // groups per frame are a multiple of 4: all four or none
-          const uint4* qq = reinterpret_cast<const uint4*>(smem + s * kTileBytes + tid * 48);
-          const uint4 q0 = qq[0], q1 = qq[1], q2 = qq[2];
-          acc = count12x8_simd(q0.x, q0.y, q0.z, kA2, nkA2, nc2) + count12x8_simd(q0.w, q1.x, q1.y, kA2, nkA2, nc2) +
-                count12x8_simd(q1.z, q1.w, q2.x, kA2, nkA2, nc2) + count12x8_simd(q2.y, q2.z, q2.w, kA2, nkA2, nc2);
+#pragma unroll
+        for (int c4 = 0; c4 < kTileBytes / (48 * kThreads); ++c4) {
+          const int g = (c4 * kThreads + tid) * 4;       // groups per frame are a multiple of 4: all four or none
+          if (g < tile_groups) {
+            const uint4* qq = reinterpret_cast<const uint4*>(smem + s * kTileBytes + (c4 * kThreads + tid) * 48);
+            const uint4 q0 = qq[0], q1 = qq[1], q2 = qq[2];
+            acc += count12x8_simd(q0.x, q0.y, q0.z, kA2, nkA2, nc2) + count12x8_simd(q0.w, q1.x, q1.y, kA2, nkA2, nc2) +
+                   count12x8_simd(q1.z, q1.w, q2.x, kA2, nkA2, nc2) + count12x8_simd(q2.y, q2.z, q2.w, kA2, nkA2, nc2);
+          }
         }
       } else {
         const uint32_t one2 = 0x00010001u;
@@ -776,11 +784,12 @@ __global__ void __launch_bounds__(kFusedThreads) range_kernel(const StreamParams
   }
 }
 
-template <int BITS, int kCountStages>
+template <int BITS, int kCountStages, int kItemKB>
 int launch_range_fused(StreamParams p, const DetectParams& d, cudaStream_t st) {
-  const size_t smem = (size_t)kCountStages * (4 * kThreads * BITS) + 2 * kCountStages * 8 + 2 * kQueue * 4 +
+  const size_t smem = (size_t)kCountStages * (kItemKB * 1024) + 2 * kCountStages * 8 + 2 * kQueue * 4 +
                       (4 + kDetWarps) * 4 + kSegRing * 4 + kDetWarps * detect_warp_smem(d.width, BITS);
-  auto kern = range_kernel<BITS, kCountStages>;
+  auto kern = range_kernel<BITS, kCountStages, kItemKB>;
+  p.tiles_per_frame = (int)((p.px_per_frame / kGroupPx + (kItemKB * 1024 / BITS) - 1) / (kItemKB * 1024 / BITS));
   // launch configuration per device, recomputed only when the frame width (detector smem) changes
   static std::mutex m;
   static size_t have_smem[64] = {};
@@ -1268,13 +1277,25 @@ int range_fused_impl(const DetectParams& d, int bits, int32_t empty_thr, bool pd
   p.diff_thr = d.diff_thr;
   p.skip = d.skip;
   p.pdl = pdl ? 1 : 0;
-  static const int stages = getenv("FF_COUNT12_STAGES") ? atoi(getenv("FF_COUNT12_STAGES")) : 4;   // tuning knob
-  if (bits == 16) return launch_range_fused<16, 4>(p, d, st);
-  if (bits == 8) return launch_range_fused<8, 6>(p, d, st);
+  // Ring geometry, measured (profiles/r02_range_item_sweep.txt; GB/s of algorithmic bytes at C2):
+  //   12-bit  12 KiB x 4 stages 6870   24 KiB x 3 stages 6700        -> 12 KiB (72 KiB in flight per SM)
+  //   16-bit  12 KiB x 4        7140   24 KiB x 3        6820        -> 12 KiB
+  //    8-bit  12 KiB x 4        6140   24 KiB x 3        6770        -> 24 KiB (96 KiB in flight per SM)
+  // FF_RANGE_ITEM_KB / FF_COUNT12_STAGES override (tuning knobs).
+  static const int stages = getenv("FF_COUNT12_STAGES") ? atoi(getenv("FF_COUNT12_STAGES")) : 4;
+  static const int item_env = getenv("FF_RANGE_ITEM_KB") ? atoi(getenv("FF_RANGE_ITEM_KB")) : 0;
+  const int item_kb = item_env > 0 ? item_env : (bits == 8 ? 24 : 12);
+  if (item_kb == 24) {
+    if (bits == 16) return launch_range_fused<16, 3, 24>(p, d, st);
+    if (bits == 8) return launch_range_fused<8, 3, 24>(p, d, st);
+    return launch_range_fused<12, 3, 24>(p, d, st);
+  }
+  if (bits == 16) return launch_range_fused<16, 4, 12>(p, d, st);
+  if (bits == 8) return launch_range_fused<8, 4, 12>(p, d, st);
   switch (stages) {
-    case 3: return launch_range_fused<12, 3>(p, d, st);
-    case 6: return launch_range_fused<12, 6>(p, d, st);
-    default: return launch_range_fused<12, 4>(p, d, st);
+    case 3: return launch_range_fused<12, 3, 12>(p, d, st);
+    case 6: return launch_range_fused<12, 6, 12>(p, d, st);
+    default: return launch_range_fused<12, 4, 12>(p, d, st);
   }
 }
 
