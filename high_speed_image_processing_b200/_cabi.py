@@ -111,8 +111,8 @@ SIGNATURES = {
     "ff_exchange_finish": (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "ff_exchange_status": (_int, [_vp, C.POINTER(_i32), _vp]),
     "ff_exchange_destroy": (_int, [_vp]),
-    "ff_head_lines": (_int, [_vp, _vp, _i64, _int, _int, _int, _vp, _vp, _i64, _i32, C.POINTER(C.c_double), _int, _vp,
-                             _vp, _vp, _vp, _vp]),
+    "ff_head_lines": (_int, [_vp, _vp, _i64, _int, _int, _int, _vp, _vp, _i64, _i32, _int, C.POINTER(C.c_double), _int,
+                             _vp, _vp, _vp, _vp, _vp]),
     "ff_head_track_scratch_len": (_int, [_i64, C.POINTER(_i64)]),
     "ff_head_track": (_int, [_vp, _vp, _i64, _i64, _int, _i32, _i32, _i32, C.c_double, C.c_double, _i32, _i32, _i32,
                              _vp, _vp, _vp, _vp]),

@@ -23,7 +23,7 @@ void set_cuda_error(cudaError_t e, const char* where) {
 }
 
 int head_lines_impl(const void*, const void*, int64_t, int, int, int, const int32_t*, const int32_t*, int64_t, int32_t,
-                    const double*, int, const uint8_t*, double*, uint8_t*, int32_t*, cudaStream_t);
+                    int, const double*, int, const uint8_t*, double*, uint8_t*, int32_t*, cudaStream_t);
 int head_track_impl(const double*, const uint8_t*, int64_t, int64_t, int, int32_t, int32_t, int32_t, double, double,
                     int32_t, int32_t, int32_t, int32_t*, int32_t*, int32_t*, cudaStream_t);
 int64_t head_track_scratch_len(int64_t);
@@ -329,11 +329,11 @@ int ff_truncate(int32_t* pos_dev, int64_t n_frames, int64_t first_frame, const i
 
 int ff_head_lines(const void* frames_dev, const void* halo_dev, int64_t n_frames, int height, int width, int bits,
                   const int32_t* bg_dev, const int32_t* partial_dev, int64_t min_signal_count, int32_t diff_thr,
-                  const double* gauss_weights_host, int radius, const uint8_t* skip_dev, double* lines_out_dev,
-                  uint8_t* flags_out_dev, int32_t* scratch_dev, void* stream) {
+                  int morphology_size, const double* gauss_weights_host, int radius, const uint8_t* skip_dev,
+                  double* lines_out_dev, uint8_t* flags_out_dev, int32_t* scratch_dev, void* stream) {
   return head_lines_impl(frames_dev, halo_dev, n_frames, height, width, bits, bg_dev, partial_dev, min_signal_count,
-                         diff_thr, gauss_weights_host, radius, skip_dev, lines_out_dev, flags_out_dev, scratch_dev,
-                         static_cast<cudaStream_t>(stream));
+                         diff_thr, morphology_size, gauss_weights_host, radius, skip_dev, lines_out_dev, flags_out_dev,
+                         scratch_dev, static_cast<cudaStream_t>(stream));
 }
 
 int ff_head_track_scratch_len(int64_t n_frames, int64_t* n_elems) {

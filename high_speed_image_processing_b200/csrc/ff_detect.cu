@@ -107,6 +107,12 @@ struct PrepParams {
   int32_t* first_exit;       // nullable
   RangeWorkspace* ws;
   RangeHooks hooks;
+  // NumPy's pairwise summation of W values as tables (a function of W only, built on the host):
+  // leaves [off, off + len) and the additions that combine their sums, in the order of the recursion
+  int n_leaves;
+  uint16_t leaf_off[96];
+  uint8_t leaf_len[96];      // <= 128
+  uint8_t op_a[96], op_b[96];   // sum[op_a[k]] += sum[op_b[k]], k = 0 .. n_leaves - 2; the total ends in sum[0]
 };
 
 constexpr int kPrepThreads = 256;
@@ -116,67 +122,40 @@ constexpr int kMaxLeaves = 96;      // W <= 4096: at most 64 leaves of NumPy's p
 // n < 8 plain loop; n <= 128 eight strided accumulators combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))
 // plus the n % 8 tail; else split at n2 = n/2 - (n/2) % 8.  The leaves (n <= 128) are summed by groups of
 // eight threads, one accumulator each; one thread then adds the leaf sums in the order of the recursion.
-__device__ int pairwise_leaves(int n, int* off, int* len) {
-  int so[16], sn[16], sp = 0, count = 0;
-  so[0] = 0;
-  sn[0] = n;
-  while (sp >= 0) {
-    const int o = so[sp], m = sn[sp];
-    --sp;
-    if (m <= 128) {
-      off[count] = o;
-      len[count] = m;
-      ++count;
-    } else {
+// Host side: the recursion as tables (PrepParams::leaf_*, op_*).  Returns the number of leaves.
+int pairwise_tables(int n, uint16_t* off, uint8_t* len, uint8_t* op_a, uint8_t* op_b) {
+  int n_leaves = 0, n_ops = 0;
+  // post-order walk; every node returns the index of the leaf slot that accumulates its sum (its first leaf)
+  struct Walk {
+    uint16_t* off; uint8_t* len; uint8_t* a; uint8_t* b; int* nl; int* no;
+    int go(int o, int m) {
+      if (m <= 128) {
+        off[*nl] = (uint16_t)o;
+        len[*nl] = (uint8_t)m;
+        return (*nl)++;
+      }
       int n2 = m / 2;
       n2 -= n2 % 8;
-      ++sp; so[sp] = o + n2; sn[sp] = m - n2;     // right half: popped after the left one
-      ++sp; so[sp] = o;      sn[sp] = n2;
+      const int l = go(o, n2);
+      const int r = go(o + n2, m - n2);
+      a[*no] = (uint8_t)l;
+      b[*no] = (uint8_t)r;
+      ++*no;
+      return l;
     }
-  }
-  return count;
+  } w{off, len, op_a, op_b, &n_leaves, &n_ops};
+  w.go(0, n);
+  return n_leaves;
 }
-__device__ double pairwise_combine(int n, const double* leaf) {
-  int ns[16], st[16], sp = 0, next = 0;
-  double acc[16], ret = 0.0;
-  ns[0] = n;
-  st[0] = 0;
-  while (sp >= 0) {
-    const int m = ns[sp];
-    if (m <= 128) {
-      ret = leaf[next++];
-      --sp;
-      continue;
-    }
-    int n2 = m / 2;
-    n2 -= n2 % 8;
-    if (st[sp] == 0) {
-      st[sp] = 1;
-      ns[sp + 1] = n2;
-      st[sp + 1] = 0;
-      ++sp;
-    } else if (st[sp] == 1) {
-      acc[sp] = ret;
-      st[sp] = 2;
-      ns[sp + 1] = m - n2;
-      st[sp + 1] = 0;
-      ++sp;
-    } else {
-      ret = __dadd_rn(acc[sp], ret);
-      --sp;
-    }
-  }
-  return ret;
-}
-// Whole CTA: np.add.reduce(xs[0:n]).  leaf_* are shared arrays; result valid in every thread.
-__device__ double cta_pairwise_sum(const double* xs, int n, const int* leaf_off, const int* leaf_len, int n_leaves,
-                                   double* leaf_sum, double* result) {
+
+// Whole CTA: np.add.reduce(xs[0:n]) with the tables in p.  leaf_sum: shared array; result valid in every thread.
+__device__ double cta_pairwise_sum(const PrepParams& p, const double* xs, double* leaf_sum) {
   const int gid = threadIdx.x >> 3, j = threadIdx.x & 7;
-  for (int it = 0; it * (kPrepThreads / 8) < n_leaves; ++it) {
+  for (int it = 0; it * (kPrepThreads / 8) < p.n_leaves; ++it) {
     const int L = it * (kPrepThreads / 8) + gid;
-    const bool valid = L < n_leaves;
-    const int off = valid ? leaf_off[L] : 0;
-    const int len = valid ? leaf_len[L] : 0;
+    const bool valid = L < p.n_leaves;
+    const int off = valid ? p.leaf_off[L] : 0;
+    const int len = valid ? p.leaf_len[L] : 0;
     double r = 0.0;
     const int body = len - (len % 8);
     if (len >= 8) {
@@ -197,9 +176,12 @@ __device__ double cta_pairwise_sum(const double* xs, int n, const int* leaf_off,
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) *result = pairwise_combine(n, leaf_sum);
+  if (threadIdx.x == 0)
+    for (int k = 0; k + 1 < p.n_leaves; ++k) leaf_sum[p.op_a[k]] = __dadd_rn(leaf_sum[p.op_a[k]], leaf_sum[p.op_b[k]]);
   __syncthreads();
-  return *result;
+  const double total = leaf_sum[0];
+  __syncthreads();          // leaf_sum is reused by the next reduction
+  return total;
 }
 
 template <int BITS>
@@ -271,10 +253,6 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepParams p) 
   // ---- float64 statistics of the centre row, NumPy's order of operations ------------------------------
   double* xs = reinterpret_cast<double*>(smem);                 // [W]
   double* leaf_sum = xs + W;                                    // [kMaxLeaves]
-  double* result = leaf_sum + kMaxLeaves;                       // [1]
-  int* leaf_off = reinterpret_cast<int*>(result + 1);           // [kMaxLeaves]
-  int* leaf_len = leaf_off + kMaxLeaves;                        // [kMaxLeaves]
-  __shared__ int s_leaves;
   int mx = 0;
   for (int x = tid; x < W; x += kPrepThreads) {
     const int v = load_px_generic<BITS>(p.frame0, q0 + x);
@@ -283,18 +261,16 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepParams p) 
   }
   mx = __reduce_max_sync(0xFFFFFFFFu, mx);
   if ((tid & 31) == 0) s_max[tid >> 5] = mx;
-  if (tid == 0) s_leaves = pairwise_leaves(W, leaf_off, leaf_len);
   __syncthreads();
   mx = 0;
   for (int k = 0; k < kPrepThreads / 32; ++k) mx = max(mx, s_max[k]);
-  const int n_leaves = s_leaves;
-  const double mean = __ddiv_rn(cta_pairwise_sum(xs, W, leaf_off, leaf_len, n_leaves, leaf_sum, result), (double)W);
+  const double mean = __ddiv_rn(cta_pairwise_sum(p, xs, leaf_sum), (double)W);
   for (int x = tid; x < W; x += kPrepThreads) {
     const double d = __dsub_rn(xs[x], mean);                    // arr - arrmean
     xs[x] = __dmul_rn(d, d);                                    // multiply(x, x)
   }
   __syncthreads();
-  const double var = __ddiv_rn(cta_pairwise_sum(xs, W, leaf_off, leaf_len, n_leaves, leaf_sum, result), (double)W);
+  const double var = __ddiv_rn(cta_pairwise_sum(p, xs, leaf_sum), (double)W);
   if (tid == 0) {
     const double sd = __dsqrt_rn(var);
     const double a = __dadd_rn(mean, __dmul_rn(5.0, sd));       // mean + 5 * std           (:1367)
@@ -437,13 +413,18 @@ int prep_impl(const void* frame0, int height, int width, int bits, int32_t* scal
   p.first_exit = first_exit;
   p.ws = ws;
   p.hooks = hooks;
+  if (p.want_stats) p.n_leaves = pairwise_tables(width, p.leaf_off, p.leaf_len, p.op_a, p.op_b);
   int64_t blocks = 1;
   if (frame0 != nullptr) {
     blocks = (px + kPrepThreads * 32 - 1) / (kPrepThreads * 32);        // ~32 pixels per thread
     if (blocks > kPrepMaxCtas) blocks = kPrepMaxCtas;
     if (blocks < 1) blocks = 1;
   }
-  const size_t smem = p.want_stats ? (size_t)width * 8 + kMaxLeaves * 8 + 8 + 2 * kMaxLeaves * 4 : 0;
+  const size_t smem = p.want_stats ? (size_t)width * 8 + kMaxLeaves * 8 : 0;
+  static const bool once = (cudaFuncSetAttribute(prep_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared),
+                            cudaFuncSetAttribute(prep_kernel<12>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared),
+                            cudaFuncSetAttribute(prep_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), true);
+  (void)once;       // same shared-memory split as the range kernel it runs next to (PDL)
   switch (bits) {
     case 8: return launch_kernel(prep_kernel<8>, dim3((unsigned)blocks), dim3(kPrepThreads), smem, st, false, p);
     case 12: return launch_kernel(prep_kernel<12>, dim3((unsigned)blocks), dim3(kPrepThreads), smem, st, false, p);

@@ -170,6 +170,13 @@ __global__ void publish_kernel(const RangeHooks h) {
   }
 }
 
+// The small kernels of the exchange run next to a range kernel that configures its SMs for maximum shared
+// memory; they ask for the same split so that their CTAs can be placed on those SMs (once per process).
+template <class Kern>
+void share_sm_with_range_kernel(Kern kern) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 int merge_grid(int64_t total) {
   int64_t blocks = (total + 1023) / 1024;
   if (blocks > 74) blocks = 74;       // few, small CTAs: this kernel shares the GPU with the next clip's range kernel
@@ -181,6 +188,8 @@ int merge_grid(int64_t total) {
 
 int publish_impl(const RangeHooks& hooks, cudaStream_t st) {
   if (hooks.table == nullptr) return FF_OK;
+  static const bool once = (share_sm_with_range_kernel(publish_kernel), true);
+  (void)once;
   publish_kernel<<<1, 32, 0, st>>>(hooks);
   FF_CUDA_TRY(cudaGetLastError());
   return FF_OK;
@@ -396,6 +405,8 @@ int ff_exchange_finish(ff_exchange* x, int64_t total_frames, int32_t* pos_out_de
   p.publish = 0;
   p.ticket = reinterpret_cast<unsigned int*>(x->local + x->ticket_off);
   p.spin_limit = x->spin_limit;
+  static const bool once = (share_sm_with_range_kernel(merge_ranges_kernel<true>), true);
+  (void)once;
   merge_ranges_kernel<true><<<merge_grid(total_frames), kMergeThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   FF_CUDA_TRY(cudaGetLastError());
   return FF_OK;

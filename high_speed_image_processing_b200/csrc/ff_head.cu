@@ -42,6 +42,8 @@ struct HeadBandParams {
   const uint8_t* skip;
   double w[2 * kMaxRadius + 1];
   int radius;
+  int morph;       // half size of the k x k grey opening (k = 2 * morph + 1; the reference's default k = 3)
+  int halo_px;     // band half height / column halo: radius + 2 * morph + 1
   double* lines;   // [n][2][W]  (sobel row, gradient row)
   uint8_t* flags;  // [n]  0 = not processed (skipped / empty), 1 = lines valid, 2 = processed, no prior frame
   int32_t* scratch;  // [0] number of frames with flag 1, [4 + k] their indices (any order)
@@ -83,18 +85,18 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 
 // The float64 stages shared by both band kernels.  `band` holds the opened difference image as uint16,
 // band row i / band column j at band[i * stride + j + col0]; rows HALO-1-R .. HALO+1+R and columns
-// [2, LW-2) must be valid.  G0 = Gaussian along rows (axis 0) for band rows HALO-1, HALO, HALO+1; BL =
+// [2 morph, LW - 2 morph) must be valid (HALO = R + 2 morph + 1).  G0 = Gaussian along rows (axis 0) for band rows HALO-1, HALO, HALO+1; BL =
 // Gaussian along columns (axis 1), valid columns [HALO-1, LW-HALO+1); then Sobel(axis=1) and
 // np.gradient(axis=1) of the centre row.  scipy NI_Correlate1D order: centre tap first, then symmetric
 // pairs outermost -> innermost, explicit round-to-nearest mul/add (no FMA).  Ends with a CTA barrier.
 __device__ __forceinline__ void band_float_stages(const HeadBandParams& p, const uint16_t* band, int stride, int col0,
                                                   int LW, int tw, int x_begin, int f, double* g0, double* bl) {
   const int tid = threadIdx.x;
-  const int R = p.radius, HALO = R + 3, W = p.width;
+  const int R = p.radius, HALO = p.halo_px, W = p.width, M2 = 2 * p.morph;
   for (int e = tid; e < 3 * LW; e += kHeadThreads) {
     const int b = e / LW, j = e - b * LW;
     double tmp = 0.0;
-    if (j >= 2 && j < LW - 2) {
+    if (j >= M2 && j < LW - M2) {
       const uint16_t* col = band + (HALO - 1 + b) * stride + j + col0;
       tmp = __dmul_rn((double)col[0], p.w[R]);
       for (int jj = -R; jj < 0; ++jj) {
@@ -145,8 +147,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_band_kernel(const HeadBandP
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x;
   const int W = p.width, H = p.height;
-  const int R = p.radius;
-  const int HALO = R + 3;
+  const int HALO = p.halo_px;
+  const int MH = p.morph;
   const int NB = 2 * HALO + 1;            // band rows
   const int c = H / 2;
   const int tiles_x = (W + kHeadTileW - 1) / kHeadTileW;
@@ -185,32 +187,28 @@ __global__ void __launch_bounds__(kHeadThreads) head_band_kernel(const HeadBandP
     }
   }
   __syncthreads();
-  // ---- E = 3x3 minimum (valid rows [1,NB-1), cols [1,LW-1)) --------------------------------------
+  // ---- E = k x k minimum (valid rows [MH,NB-MH), cols [MH,LW-MH)); k = 2 MH + 1 (:403-404) -------
   for (int i = warp; i < NB; i += kHeadThreads / 32) {
-    const bool row_ok = i >= 1 && i < NB - 1;
+    const bool row_ok = i >= MH && i < NB - MH;
     for (int j = lane; j < LW; j += 32) {
       unsigned m = 0;
-      if (row_ok && j >= 1 && j < LW - 1) {
+      if (row_ok && j >= MH && j < LW - MH) {
         m = 0xFFFFu;
-#pragma unroll
-        for (int di = -1; di <= 1; ++di)
-#pragma unroll
-          for (int dj = -1; dj <= 1; ++dj) m = min(m, (unsigned)bufA[(i + di) * LW + j + dj]);
+        for (int di = -MH; di <= MH; ++di)
+          for (int dj = -MH; dj <= MH; ++dj) m = min(m, (unsigned)bufA[(i + di) * LW + j + dj]);
       }
       bufB[i * LW + j] = (uint16_t)m;
     }
   }
   __syncthreads();
-  // ---- NR = 3x3 maximum of E (valid rows [2,NB-2), cols [2,LW-2)) ---------------------------------
+  // ---- NR = k x k maximum of E (valid rows [2MH,NB-2MH), cols [2MH,LW-2MH)) ------------------------
   for (int i = warp; i < NB; i += kHeadThreads / 32) {
-    const bool row_ok = i >= 2 && i < NB - 2;
+    const bool row_ok = i >= 2 * MH && i < NB - 2 * MH;
     for (int j = lane; j < LW; j += 32) {
       unsigned m = 0;
-      if (row_ok && j >= 2 && j < LW - 2) {
-#pragma unroll
-        for (int di = -1; di <= 1; ++di)
-#pragma unroll
-          for (int dj = -1; dj <= 1; ++dj) m = max(m, (unsigned)bufB[(i + di) * LW + j + dj]);
+      if (row_ok && j >= 2 * MH && j < LW - 2 * MH) {
+        for (int di = -MH; di <= MH; ++di)
+          for (int dj = -MH; dj <= MH; ++dj) m = max(m, (unsigned)bufB[(i + di) * LW + j + dj]);
       }
       bufA[i * LW + j] = (uint16_t)m;
     }
@@ -986,14 +984,15 @@ int64_t head_track_scratch_len(int64_t n_frames) {
 
 int head_lines_impl(const void* frames, const void* halo, int64_t n_frames, int height, int width, int bits,
                     const int32_t* bg_dev, const int32_t* partial, int64_t min_signal_count, int32_t diff_thr,
-                    const double* gauss_weights_host, int radius, const uint8_t* skip, double* lines_out,
-                    uint8_t* flags_out, int32_t* scratch, cudaStream_t st) {
+                    int morphology_size, const double* gauss_weights_host, int radius, const uint8_t* skip,
+                    double* lines_out, uint8_t* flags_out, int32_t* scratch, cudaStream_t st) {
   if (frames == nullptr || bg_dev == nullptr || partial == nullptr || gauss_weights_host == nullptr ||
       lines_out == nullptr || flags_out == nullptr || scratch == nullptr)
     return FF_ERR_INVALID;
   if (n_frames <= 0 || height <= 0 || width < 2 || n_frames > 0x7FFFFFFF) return FF_ERR_INVALID;
   if (bits != 8 && bits != 12 && bits != 16) return FF_ERR_UNSUPPORTED;
   if (radius < 0 || radius > kMaxRadius) return FF_ERR_UNSUPPORTED;
+  if (morphology_size < 1 || morphology_size > 7 || (morphology_size & 1) == 0) return FF_ERR_UNSUPPORTED;
   if (diff_thr < 0) return FF_ERR_UNSUPPORTED;       // band is held as uint16
   const int64_t px = (int64_t)height * width;
   if (bits == 12 && (px & 1)) return FF_ERR_UNSUPPORTED;
@@ -1011,11 +1010,13 @@ int head_lines_impl(const void* frames, const void* halo, int64_t n_frames, int 
   p.diff_thr = diff_thr;
   p.skip = skip;
   p.radius = radius;
+  p.morph = (morphology_size - 1) / 2;
+  p.halo_px = radius + 2 * p.morph + 1;
   for (int i = 0; i < 2 * radius + 1; ++i) p.w[i] = gauss_weights_host[i];
   p.lines = lines_out;
   p.flags = flags_out;
 
-  const int halo_px = radius + 3;
+  const int halo_px = p.halo_px;
   const int nb = 2 * halo_px + 1;
   const int lw = kHeadTileW + 2 * halo_px;
   const size_t smem = (((size_t)2 * nb * lw * sizeof(uint16_t) + 15) & ~(size_t)15) + (size_t)6 * lw * sizeof(double);
@@ -1026,7 +1027,7 @@ int head_lines_impl(const void* frames, const void* halo, int64_t n_frames, int 
   head_flags_kernel<<<(unsigned)((n_frames + warps - 1) / warps), kHeadThreads, 0, st>>>(p);
   FF_CUDA_TRY(cudaGetLastError());
   const int tiles_x = (width + kHeadTileW - 1) / kHeadTileW;
-  const bool fast = (width % 8) == 0 && (p.frame_bytes % 4) == 0 && getenv("FF_BAND_GENERAL") == nullptr &&
+  const bool fast = morphology_size == 3 && (width % 8) == 0 && (p.frame_bytes % 4) == 0 && getenv("FF_BAND_GENERAL") == nullptr &&
                     (reinterpret_cast<uintptr_t>(frames) % 4) == 0 &&
                     (halo == nullptr || (reinterpret_cast<uintptr_t>(halo) % 4) == 0);
   const size_t smem_general = smem;

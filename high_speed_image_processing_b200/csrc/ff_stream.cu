@@ -801,6 +801,9 @@ int launch_range_fused(StreamParams p, const DetectParams& d, cudaStream_t st) {
     std::lock_guard<std::mutex> g(m);
     if (have_smem[dev] != smem) {
       FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      // the SM's shared-memory / L1 split at its maximum, like the small kernels that run NEXT TO this one
+      // (merge of the previous clip, prep): CTAs of kernels that ask for different splits cannot share an SM
+      FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kFusedThreads, smem));
       int cap = kCountCtasPerSm;             // bytes in flight per SM: see launch_count12
       if (const char* e = getenv("FF_COUNT12_CTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;   // tuning knob
@@ -1058,6 +1061,7 @@ int launch_streamx(StreamParams p, int ctas_cap, cudaStream_t st) {
   int ctas = 1;
   int rc = cache.get([&](int* v) -> int {
     FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerSm));
+    FF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int occ = 0;
     FF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kOutThreads, kNeeded));
     if (occ > ctas_cap) occ = ctas_cap;

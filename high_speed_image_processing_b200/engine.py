@@ -323,16 +323,17 @@ class FlameFrontEngine:
         pinned buffers (side stream, behind everything launched so far) without waiting for them."""
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream(self.device)
-        if self._scalar_ring is None:
-            self._scalar_ring = [None] * self._SCALAR_RING
-            self._scalar_ring_gen = [0] * self._SCALAR_RING
+        if self._scalar_ring is None or self._scalar_ring[0][1].numel() < width:
+            # ONE pinned allocation for the whole ring (cudaHostAlloc synchronises the device and takes
+            # milliseconds when several ranks pin memory at once - never inside a sequence of steps)
+            cols = max(width, 1024)
+            blocks = torch.empty((self._SCALAR_RING, SCALAR_BLOCK), dtype=torch.int32).pin_memory()
+            rows = torch.empty((self._SCALAR_RING, cols), dtype=torch.uint16).pin_memory()
+            self._scalar_ring = [(blocks[i], rows[i]) for i in range(self._SCALAR_RING)]
+            self._scalar_ring_gen = [g + 1 for g in (self._scalar_ring_gen or [0] * self._SCALAR_RING)]
         slot = self._scalar_ring_next % self._SCALAR_RING
         self._scalar_ring_next += 1
         buf = self._scalar_ring[slot]
-        if buf is None or buf[1].numel() < width:
-            buf = (torch.empty(SCALAR_BLOCK, dtype=torch.int32).pin_memory(),
-                   torch.empty(max(width, 1024), dtype=torch.uint16).pin_memory())
-            self._scalar_ring[slot] = buf
         self._scalar_ring_gen[slot] += 1
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(self.device))
@@ -541,7 +542,8 @@ class FlameFrontEngine:
             _cabi.check(self._lib.ff_head_lines(
                 frames.data_ptr(), _ptr(halo), n_frames, height, width, bits, bg_dev.data_ptr(),
                 partial.data_ptr(), min_signal_count(height * width, params.min_signal_fraction), diff_thr,
-                weights.ctypes.data_as(C.POINTER(C.c_double)), radius, _ptr(skip), lines.data_ptr(),
+                int(params.morphology_kernel_size), weights.ctypes.data_as(C.POINTER(C.c_double)), radius, _ptr(skip),
+                lines.data_ptr(),
                 flags.data_ptr(), scratch.data_ptr(), st), "ff_head_lines")
         self.launches += 3      # stream, flags, band
         return lines, flags, pending

@@ -32,8 +32,8 @@ class HeadParams:
     min_signal_fraction: float = 0.0005      # is_empty_frame call at :1459
 
     def __post_init__(self) -> None:
-        if self.morphology_kernel_size != 3:
-            raise ValueError("the GPU band kernel implements the reference's 3x3 opening only")
+        if self.morphology_kernel_size not in (1, 3, 5, 7):
+            raise ValueError("morphology_kernel_size must be odd and at most 7 (1, 3, 5 or 7)")
         if self.frame_diff_threshold < 0:
             raise ValueError("frame_diff_threshold must be >= 0")
 

@@ -270,7 +270,8 @@ int ff_exchange_destroy(ff_exchange* x);
 
 /* ---- HEAD-parity detector (the code the reference executes at HEAD) ------------------------------
  * ff_head_lines replaces, per non-empty frame, the image pipeline of FlameDetector.detect
- * (scripts/process_videos.py:397-418): thresholded frame difference -> grey_opening 3x3 ->
+ * (scripts/process_videos.py:397-418): thresholded frame difference -> grey_opening k x k
+ * (morphology_size = FlameDetectorConfig.morphology_kernel_size, :170; odd, 1..7; 3 takes the fast kernel) ->
  * gaussian_filter(sigma) -> sobel(axis=1) and np.gradient(axis=1), evaluated only on the band of
  * rows that reaches the centre row, in float64 with SciPy's operation order (bit-identical).
  *   gauss_weights_host  2*radius+1 float64 taps (scipy _gaussian_kernel1d), HOST pointer
@@ -290,8 +291,9 @@ int ff_exchange_destroy(ff_exchange* x);
  *             parallel; without it one warp validates the segments one after the other.  Same results. */
 int ff_head_lines(const void* frames_dev, const void* halo_dev, int64_t n_frames, int height, int width,
                   int bits, const int32_t* bg_dev, const int32_t* partial_dev, int64_t min_signal_count,
-                  int32_t diff_thr, const double* gauss_weights_host, int radius, const uint8_t* skip_dev,
-                  double* lines_out_dev, uint8_t* flags_out_dev, int32_t* scratch_dev, void* stream);
+                  int32_t diff_thr, int morphology_size, const double* gauss_weights_host, int radius,
+                  const uint8_t* skip_dev, double* lines_out_dev, uint8_t* flags_out_dev, int32_t* scratch_dev,
+                  void* stream);
 int ff_head_track_scratch_len(int64_t n_frames, int64_t* n_elems);
 int ff_head_track(const double* lines_dev, const uint8_t* flags_dev, int64_t n_frames, int64_t first_frame,
                   int width, int32_t edge_margin_px, int32_t max_displacement_px, int32_t search_window_px,

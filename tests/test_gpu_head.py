@@ -439,3 +439,53 @@ def test_driver_files_with_trigger_relative_time_match_the_reference(tmp_path, c
     process_video_source(cfg, None, verbose=False)
     produced = {p.name: p.read_text() for p in (tmp_path / "out").glob("*.txt")}
     assert produced == g["outputs"]
+
+
+@pytest.mark.parametrize("run_name", ["defaults", "k5_sigma1_thr3.5_gaps", "k1_sigma2"])
+def test_whole_clip_kernels_reproduce_the_reference_detector_runs(engine, golden, run_name):
+    """The reference's FlameDetector runs recorded in the golden file (tests/golden/reference_golden.json,
+    ``detector_api``: defaults; 5x5 opening / sigma 1 / threshold 3.5 / frame gaps; 1x1 opening / sigma 2)
+    through the WHOLE-CLIP kernels - ff_head_lines (band kernel with a k x k opening) + ff_head_track - instead
+    of one detect() call per frame: frames that were not fed to the detector are skip_frames entries, the
+    background scalar is the one the reference was called with, no frame counts as empty."""
+    from conftest import GOLDEN
+    from high_speed_image_processing_b200.head import HeadParams, max_displacement_px
+    api = golden["detector_api"]
+    frames = np.load(GOLDEN / "detector_frames.npz")["frames"]
+    run = next(r for r in api["runs"] if r["name"] == run_name)
+    cfg = run["cfg"]
+    hp = HeadParams(frame_diff_threshold=cfg.get("frame_diff_threshold", 5.0),
+                    morphology_kernel_size=cfg.get("morphology_kernel_size", 3),
+                    gaussian_sigma=cfg.get("gaussian_sigma", 1.5),
+                    min_gradient_strength=cfg.get("min_gradient_strength", 10.0),
+                    edge_margin_px=cfg.get("edge_margin_px", 10),
+                    sobel_threshold_fraction=cfg.get("sobel_threshold_fraction", 0.1),
+                    search_window_px=cfg.get("search_window_px", 100), min_signal_fraction=0.0)
+    n, h, w = frames.shape
+    order = run["order"]
+    first, last = order[0], order[-1] + 1
+    skip = np.ones(n, np.uint8)
+    skip[order] = 0
+    packed = torch.from_numpy(syn.pack_frames(frames, 16)).to(engine.device)
+    fb = h * w * 2
+    # ff_background takes the max of "frame 0": a frame filled with the background scalar of the recorded run
+    frame0 = torch.from_numpy(np.full((h, w), int(run["background"]), np.uint16).view(np.uint8).reshape(-1)).to(engine.device)
+    lines, flags, pending = engine.head_lines(packed[first * fb:last * fb], last - first, h, w, 16, hp, frame0=frame0,
+                                              first_frame=first, skip=torch.from_numpy(skip[first:last].copy()).to(engine.device))
+    assert engine.head_scalars(pending).background == run["background"]
+    maxdisp = max_displacement_px(api["frame_rate"], run["calibration"], hp)
+    assert maxdisp == run["max_displacement_px"]
+    track, stop = engine.head_track_lines(lines, flags, first, w, hp, maxdisp)
+    track, flags = track.cpu().numpy(), flags.cpu().numpy()
+    none = lambda v: None if v < 0 else int(v)      # noqa: E731
+    for call in run["calls"]:
+        i = call["frame"] - first
+        got = track[i]
+        assert flags[i] == (2 if call["sha1"]["frame_diff"] is None else 1), (run_name, call["frame"])
+        if flags[i] == 2:             # the first frame fed: no prior frame, detect() returns no position
+            assert call["final"] is None
+            continue
+        assert (none(got[0]), none(got[1]), none(got[2])) == (call["final"], call["min_gradient"], call["rightmost_sobel"]), \
+            (run_name, call["frame"])
+        assert [int(got[3]), int(got[4])] == call["search"], (run_name, call["frame"])
+    assert (flags[skip[first:last] == 1] == 0).all()

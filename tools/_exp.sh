@@ -1,4 +1,8 @@
-for kb in 12 24; do for pdl in 1; do echo "== item_kb=$kb"; FF_RANGE_ITEM_KB=$kb timeout 200 python tools/bench_variants.py --only C2:None,C3:None,C2/16:None,C2/8:None --reps 7 2>&1 | grep -o '"config": "C[0-9/]*".*"whole_path_ms": [0-9.]*' | sed 's/"frames.*"stream_kernel_ms"/ kernel_ms/; s/"stream_kernel_gbs.*"stream_kernel_frac_of_measured_peak"/frac/'; FF_RANGE_ITEM_KB=$kb timeout 200 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-pageable --no-head --legs c3_strong --e2e-steps 1 2>/dev/null | python -c "
+run() { timeout 200 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-pageable --no-head --legs c3_strong --e2e-steps 1 2>/dev/null | python -c "
 import sys,json
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('bench C2 ms', round(d['ms_per_step'],4), 'kernel', round(d['roofline']['kernel_ms'],4), 'C3 ms', round(d['c3_strong']['ms_per_step'],4))"; done; done
+print('C2 ms', round(d['ms_per_step'],4), 'kernel', round(d['roofline']['kernel_ms'],4), 'C3 ms', round(d['c3_strong']['ms_per_step'],4), 'C3 kernel', round(d['c3_strong']['range_kernel_ms_slowest_rank'],4))"; }
+echo "== default"; run
+for st in 3 6; do echo "== stages=$st"; FF_COUNT12_STAGES=$st run; done
+for ct in 1 3; do echo "== ctas=$ct stages 6"; FF_COUNT12_CTAS=$ct FF_COUNT12_STAGES=6 run; done
+echo "== item 24KB x3"; FF_RANGE_ITEM_KB=24 run
