@@ -75,6 +75,12 @@ __global__ void __launch_bounds__(kDetectWarps * 32) detect_kernel(const DetectP
       const int f = (int)(base + (int64_t)src * nw);
       const int cnt = __shfl_sync(full, cnt_c, src);
       const bool empty = (int64_t)cnt < p.min_signal_count;
+      int skip_it = 0;
+      if (lane == 0) skip_it = p.profile_out == nullptr && behind_global_exit(p, f);
+      if (__shfl_sync(full, skip_it, 0)) {                 // another rank saw the exit before this frame: it will be dropped
+        if (lane == 0) p.pos_out[f] = FF_POS_NONE;
+        continue;
+      }
       const int pos = detect_one_frame<BITS>(p, rs, f, empty, bg, thr_floor, prof, raw_cur, raw_pri, lane);
       if (lane == 0) commit_position(p, f, pos);
     }

@@ -287,6 +287,16 @@ __device__ __forceinline__ void commit_position(const DetectParams& p, int f, in
   }
 }
 
+// Range-sharded runs: has ANY rank already seen the flame leave before frame f of this range?  Then the frame
+// will be dropped by the merge whatever its position is (README.md:145-149; the reference never looks at it,
+// scripts/process_videos.py:1494) and the detecting warp need not resolve it.  Reads this rank's copy of the
+// clip-global exit word, which the peers' detecting warps keep up to date (commit_position).
+__device__ __forceinline__ bool behind_global_exit(const DetectParams& p, int f) {
+  if (p.hooks.table == nullptr) return false;
+  const PeerTable* t = p.hooks.table;
+  return (int64_t)ld_relaxed_sys(t->base[p.hooks.rank] + t->exit_off + (p.hooks.epoch & 1)) < p.first_frame + f;
+}
+
 // Called by one whole warp of every CTA when the CTA has written all its results.  The warp of the
 // CTA that arrives last finishes the range: frames at or after the range's first exit frame are
 // dropped (README.md:145-149) and, in a range-sharded run, this rank's block is published to its

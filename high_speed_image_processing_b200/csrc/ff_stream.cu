@@ -682,6 +682,12 @@ __global__ void __launch_bounds__(kFusedThreads) range_kernel(const StreamParams
         const int src = __ffs((int)pending) - 1;
         pending &= pending - 1;
         const int f = __shfl_sync(full_mask, fq, src);
+        int skip_it = 0;
+        if (lane == 0) skip_it = behind_global_exit(d, f);
+        if (__shfl_sync(full_mask, skip_it, 0)) {          // another rank saw the exit before this frame: it will be dropped
+          if (lane == 0) d.pos_out[f] = FF_POS_NONE;
+          continue;
+        }
         const int pos = detect_one_frame<BITS>(d, rs, f, false, bg_raw, thr_floor, prof, raw_cur, raw_pri, lane);
         if (lane == 0) commit_position(d, f, pos);
       }

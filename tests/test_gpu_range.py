@@ -238,7 +238,9 @@ def test_host_streamed_range_into_a_block_stops_at_the_global_exit(engine):
             else:
                 assert 70 - 40 <= res.frames_done <= 70 - 40 + 8                         # the chunk that reaches frame 70
                 got = pos.cpu().numpy()[:res.frames_done]
-                assert np.array_equal(got, want.pos_px[40:40 + res.frames_done])
+                assert np.array_equal(got[:31], want.pos_px[40:71])                      # frames up to the peer's exit frame
+                # frames behind it will be dropped by the merge: the detecting warps may skip them (position "none")
+                assert all(g in (-1, w) for g, w in zip(got[31:], want.pos_px[71:40 + res.frames_done]))
     finally:
         lib.ff_exchange_destroy(x)
         eng.close()
