@@ -264,6 +264,9 @@ __device__ __forceinline__ int32_t ld_relaxed_sys(const int32_t* p) {
 __device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(int32_t* p, int32_t v) {
+  asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void red_min_sys(int32_t* p, int32_t v) {
   asm volatile("red.relaxed.sys.global.min.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }

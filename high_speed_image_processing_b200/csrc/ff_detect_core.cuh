@@ -320,11 +320,9 @@ __device__ __forceinline__ void range_tail(const DetectParams& p, int lane) {
   }
   if (p.hooks.table != nullptr && (p.hooks.flags & FF_HOOK_PUBLISH)) {
     __syncwarp();                                    // the truncation stores of all lanes come first
-    if (lane == 0) {
-      __threadfence_system();
-      const PeerTable* t = p.hooks.table;
-      for (int r = 0; r < p.hooks.world; ++r) st_release_sys(t->base[r] + t->flags_off + p.hooks.rank, p.hooks.epoch);
-    }
+    __threadfence_system();                          // ONE system-scope fence, then relaxed flag stores, one lane per peer
+    const PeerTable* t = p.hooks.table;              // (a release store per peer would repeat the fence world times)
+    for (int r = lane; r < p.hooks.world; r += 32) st_relaxed_sys(t->base[r] + t->flags_off + p.hooks.rank, p.hooks.epoch);
   }
 }
 #endif  // __CUDACC__

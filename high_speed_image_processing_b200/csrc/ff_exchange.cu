@@ -163,11 +163,9 @@ __global__ void __launch_bounds__(kMergeThreads) merge_ranges_kernel(const Merge
 // Block filled by hand (results that came back from somewhere else): wait for the peers' acks and
 // reset the header (what prep_kernel does for ff_process_range) / publish the finished block.
 __global__ void publish_kernel(const RangeHooks h) {
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    const PeerTable* t = h.table;
-    for (int r = 0; r < h.world; ++r) st_release_sys(t->base[r] + t->flags_off + h.rank, h.epoch);
-  }
+  __threadfence_system();
+  const PeerTable* t = h.table;
+  for (int r = threadIdx.x; r < h.world; r += blockDim.x) st_relaxed_sys(t->base[r] + t->flags_off + h.rank, h.epoch);
 }
 
 // The small kernels of the exchange run next to a range kernel that configures its SMs for maximum shared

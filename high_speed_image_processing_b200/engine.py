@@ -238,7 +238,9 @@ class FlameFrontEngine:
         self.launches = 0                             # kernels launched through this engine
         self._side_stream = None
         self._pinned = {}
-        self._stream_events = None                    # bench hook: [(start, stop)] around ff_stream_frames
+        self._stream_events = None                    # bench hook: [(start, stop)] around every 4th ff_process_range
+        self._stream_event_tick = 0
+        self._stream_events_every = 4
 
     # ------------------------------------------------------------------ helpers
     def _stream(self) -> int:
@@ -478,6 +480,10 @@ class FlameFrontEngine:
         st = self._stream()
         with torch.cuda.device(self.device):
             ev = self._stream_events
+            if ev is not None:            # bench hook: time every 4th call (a timing event between two kernels costs
+                self._stream_event_tick += 1          # the stream a few microseconds, so not around every step)
+                if self._stream_events_every > 1 and self._stream_event_tick % self._stream_events_every != 1:
+                    ev = None
             if ev is not None:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)

@@ -146,6 +146,7 @@ def main() -> None:
             continue
 
         eng._stream_events = []
+        eng._stream_events_every = 1
         out = {}
 
         def run():

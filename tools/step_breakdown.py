@@ -19,6 +19,7 @@ import argparse
 import json
 import os
 import sys
+import time
 from pathlib import Path
 
 REPO = Path(__file__).resolve().parent.parent
@@ -63,6 +64,7 @@ def main() -> None:
     frame0 = syn.render_packed_torch(spec, device, 0, 1)
     halo = syn.render_packed_torch(spec, device, a - 1, a) if a else None
     params = DetectionParams(method=method)
+    host_ms = []
 
     def timed(step, join=None):
         for _ in range(5):
@@ -73,12 +75,14 @@ def main() -> None:
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0 = time.perf_counter()
         e0.record()
         for _ in range(args.steps):
             step()
         if join:
             join()
         e1.record()
+        host_ms.append((time.perf_counter() - h0) / args.steps * 1e3)      # what the host needs to ENQUEUE a step
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / args.steps
 
@@ -116,7 +120,8 @@ def main() -> None:
     else:
         allt = [t.cpu().tolist()]
     if rank == 0:
-        rep = {"config": args.config, "n_gpus": world, "frames_per_rank": n, "steps": args.steps, "transport": ex.transport if world > 1 else None}
+        rep = {"config": args.config, "n_gpus": world, "frames_per_rank": n, "steps": args.steps, "transport": ex.transport if world > 1 else None,
+               "host_enqueue_ms_per_step_rank0": [round(v, 4) for v in host_ms]}
         for k, name in enumerate(("plain", "side", "main")):
             col = [r[k] for r in allt]
             if world == 1 and name != "plain":
