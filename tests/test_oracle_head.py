@@ -108,5 +108,7 @@ def test_ddt_and_velocity_drop_rules():
     s2 = finish_head_track(track2, flags, 0, w, 10000.0, 0.01, 0.0, lambda i: i / 10000.0, hp)
     assert s2.stop == ("velocity_drop", 30) and s2.rows[-1][0] == 29
     assert s2.velocity_history[-2][3] is None           # central difference cleared (:654-663)
-    with pytest.raises(ValueError):
-        HeadParams(morphology_kernel_size=5)
+    assert HeadParams(morphology_kernel_size=5).morphology_kernel_size == 5       # odd sizes up to 7 run on the GPU
+    for bad in (0, 2, 4, 9):
+        with pytest.raises(ValueError):
+            HeadParams(morphology_kernel_size=bad)
