@@ -426,7 +426,7 @@ def leg_c2(cx: Ctx, line: dict) -> None:
     if rank == 0 and args.clock_period_ms > 0:
         sampler.start()
         time.sleep(0.25)
-    eng._stream_events = []
+    eng._stream_events, eng._stream_event_tick = [], 0
     launches0 = eng.launches
     ms_per_step, (out, res) = cx.timed_steps(step_device, args.steps, 0, join=exchange.join if world > 1 else None)
     exchange.check()
@@ -741,7 +741,7 @@ def leg_c3(cx: Ctx) -> dict:
         return eng.process_range(packed, n, h, w, 12, params, frame0=frame0, first_frame=a, halo=halo,
                                  want_scalars=False)
 
-    eng._stream_events = []
+    eng._stream_events, eng._stream_event_tick = [], 0
     ms_dev, out = cx.timed_steps(step_device, steps, warm, join=exchange.join if world > 1 else None)
     ev = eng._stream_events[1:]            # (every 4th call is timed; the first sample is a warm-up step)
     eng._stream_events = None
@@ -888,10 +888,10 @@ def leg_c4(cx: Ctx) -> dict:
                                             diff_dtype=dtype, want_scalars=False)
             return keep["res"]
 
-        eng._stream_events = []
+        eng._stream_events, eng._stream_events_every = [], 1      # multi-millisecond steps: time every one of them
         ms, g = cx.timed_steps(step, steps, 3, join=exchange.join if world > 1 else None)
-        ev = eng._stream_events[1:]        # (every 4th call is timed; the first sample is a warm-up step)
-        eng._stream_events = None
+        ev = eng._stream_events[3:]
+        eng._stream_events, eng._stream_events_every = None, 4
         kernel_ms = cx.max_over_ranks(sum(e0.elapsed_time(e1) for e0, e1 in ev) / len(ev))
         exchange.check()
         pos = g.pos.cpu().numpy()
