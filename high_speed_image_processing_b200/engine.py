@@ -122,36 +122,32 @@ def derive_kernel_bounds(scalars: ClipScalars, params: DetectionParams, n_pixels
 
 
 class PendingScalars:
-    """The clip's frame-0 statistics on their way to the host: the clip-scalar block and the centre row of
-    frame 0 are copied to pinned memory on a side stream behind the launches of ``process_range``; the
-    float64 statistics are evaluated with NumPy (the reference's own expressions,
-    scripts/process_videos.py:1362-1370) when somebody asks for them - the host never waits inside
-    ``process_range``.  For the threshold method the value the kernels used (computed on the device in
-    NumPy's order of operations) is compared with NumPy's and a difference raises."""
+    """The clip's frame-0 statistics, still on the device: the clip-scalar block and the centre row of frame 0
+    that the prep kernel wrote.  They are copied to the host and the float64 statistics are evaluated with
+    NumPy (the reference's own expressions, scripts/process_videos.py:1362-1370) only when somebody asks for
+    them - nothing is queued and the host never waits inside ``process_range``.  For the threshold method the
+    value the kernels used (computed on the device in NumPy's order of operations) is compared with NumPy's
+    and a difference raises."""
 
-    def __init__(self, engine: "FlameFrontEngine", done: torch.cuda.Event, slot: int, generation: int,
-                 width: int, check_threshold: bool):
-        self._engine, self._done, self._slot, self._generation = engine, done, slot, generation
-        self._width, self._check = width, check_threshold
+    def __init__(self, scal_dev: torch.Tensor, line_dev: torch.Tensor, check_threshold: bool):
+        self._scal_dev, self._line_dev, self._check = scal_dev, line_dev, check_threshold
         self._value: Optional[ClipScalars] = None
+        self.block: Optional[np.ndarray] = None       # the int32[16] clip-scalar block as the kernels saw it
 
     def get(self) -> ClipScalars:
         if self._value is None:
-            eng = self._engine
-            self._done.synchronize()
-            if eng._scalar_ring_gen[self._slot] != self._generation:
-                raise RuntimeError("the clip scalars of this result were overwritten by later process_range calls; "
-                                   f"read RangeResult.scalars within {len(eng._scalar_ring_gen)} calls")
-            scal_host, line_host = eng._scalar_ring[self._slot]
-            value = ClipScalars.from_frame0_stats(int(scal_host[0].item()), line_host[:self._width].numpy())
+            block = self._scal_dev.cpu().numpy()
+            line = self._line_dev.cpu().numpy()
+            value = ClipScalars.from_frame0_stats(int(block[0]), line)
             if self._check:
-                dev_floor = int(scal_host[1].item())
+                dev_floor = int(block[1])
                 if dev_floor != _clamp_i32(math.floor(value.flame_threshold)):
                     raise RuntimeError(
                         f"flame threshold evaluated on the device (floor {dev_floor}) differs from NumPy's "
                         f"({value.flame_threshold!r}): this NumPy sums in another order than the prep kernel "
                         "assumes - pass scalars=/bg_dev= from clip_scalars() instead of frame0")
-            self._value = value
+            self._value, self.block = value, block
+            self._scal_dev = self._line_dev = None
         return self._value
 
 
@@ -232,9 +228,6 @@ class FlameFrontEngine:
                 self._copy_threads = max(1, min(8, (os.cpu_count() or 2) // int(ranks)))
         self._host_ctx: Optional[C.c_void_p] = None
         self._ws: Optional[torch.Tensor] = None        # ff_process_range workspace (kept zero-filled by the kernels)
-        self._scalar_ring = None                      # pinned (scalar block, centre row) buffers of _scalars_to_host
-        self._scalar_ring_gen = None
-        self._scalar_ring_next = 0
         self.launches = 0                             # kernels launched through this engine
         self._side_stream = None
         self._pinned = {}
@@ -316,39 +309,6 @@ class FlameFrontEngine:
             done = torch.cuda.Event()
             done.record(side)
         return done, bg_host, line_host
-
-    _SCALAR_RING = 64
-
-    def _scalars_to_host(self, scal_dev: torch.Tensor, line_dev: torch.Tensor, width: int,
-                         check_threshold: bool) -> "PendingScalars":
-        """Queue the copies of the clip-scalar block and the centre row into the next slot of a ring of
-        pinned buffers (side stream, behind everything launched so far) without waiting for them."""
-        if self._side_stream is None:
-            self._side_stream = torch.cuda.Stream(self.device)
-        if self._scalar_ring is None or self._scalar_ring[0][1].numel() < width:
-            # ONE pinned allocation for the whole ring (cudaHostAlloc synchronises the device and takes
-            # milliseconds when several ranks pin memory at once - never inside a sequence of steps)
-            cols = max(width, 1024)
-            blocks = torch.empty((self._SCALAR_RING, SCALAR_BLOCK), dtype=torch.int32).pin_memory()
-            rows = torch.empty((self._SCALAR_RING, cols), dtype=torch.uint16).pin_memory()
-            self._scalar_ring = [(blocks[i], rows[i]) for i in range(self._SCALAR_RING)]
-            self._scalar_ring_gen = [g + 1 for g in (self._scalar_ring_gen or [0] * self._SCALAR_RING)]
-        slot = self._scalar_ring_next % self._SCALAR_RING
-        self._scalar_ring_next += 1
-        buf = self._scalar_ring[slot]
-        self._scalar_ring_gen[slot] += 1
-        ready = torch.cuda.Event()
-        ready.record(torch.cuda.current_stream(self.device))
-        side = self._side_stream
-        side.wait_event(ready)
-        with torch.cuda.stream(side):
-            buf[0].copy_(scal_dev, non_blocking=True)
-            buf[1][:width].copy_(line_dev, non_blocking=True)
-            scal_dev.record_stream(side)
-            line_dev.record_stream(side)
-            done = torch.cuda.Event()
-            done.record(side)
-        return PendingScalars(self, done, slot, self._scalar_ring_gen[slot], width, check_threshold)
 
     def clip_scalars(self, frame0: torch.Tensor, height: int, width: int, bits: int):
         """Background reduction + host-side float64 statistics.  Synchronises on two tiny D2H
@@ -498,7 +458,7 @@ class FlameFrontEngine:
         has_prep = scalars is None or init_first_exit or hooks is not None
         self.launches += (1 if has_prep else 0) + (1 if fused.value else 2)
         if scalars is None and want_scalars:
-            scalars = self._scalars_to_host(scal_dev, line_dev, width, params.method == "threshold")
+            scalars = PendingScalars(scal_dev, line_dev, params.method == "threshold")
         return RangeResult(first_frame, pos, counts, first_exit, diff, profiles, decoded, scalars)
 
     # ------------------------------------------------------------------ HEAD-parity detector

@@ -45,10 +45,11 @@ def test_device_threshold_is_numpys_float64(engine, bits, h, w):
     packed = dev(syn.pack_frames(frames, bits), engine)
     res = engine.process_range(packed, 3, h, w, bits, DetectionParams(method="threshold"))
     want = ClipScalars.from_frame0_stats(int(frames[0].max()), frames[0][h // 2])
+    pending = res._scalars
     got = res.scalars                       # NumPy on the copied-back row + cross-check of the device's floor
     assert got == want
-    pend_block = engine._scalar_ring[(engine._scalar_ring_next - 1) % engine._SCALAR_RING][0]
-    stats = pend_block[4:12].numpy().view(np.float64)
+    pend_block = pending.block              # the clip-scalar block the kernels used
+    stats = pend_block[4:12].view(np.float64)
     assert int(pend_block[0]) == int(frames[0].max())
     assert (stats[0], stats[1], stats[2], stats[3]) == (want.centerline_mean, want.centerline_std, want.centerline_max,
                                                         want.flame_threshold)
