@@ -18,6 +18,7 @@
 //     order); head_track_generic_kernel is the plain sequential walk kept as its cross-check.
 #include <climits>
 #include <cstdlib>
+#include <type_traits>
 
 #include "ff_common.cuh"
 
@@ -219,57 +220,127 @@ __global__ void __launch_bounds__(kHeadThreads) head_band_kernel(const HeadBandP
 }
 
 // ---- fast band kernel: rows that start on an 8-pixel boundary (W % 8 == 0, 4-byte aligned frames) --
-// The general kernel above spends half its instructions on per-pixel address arithmetic and byte
-// loads (ncu: 153 warp instructions per 32 pixels in stage D, issue-bound at 71 % issue slots busy).
-// Here stage D works on aligned groups of 8 pixels - three 32-bit loads per frame for packed
-// 12-bit - written to shared memory as one 16-byte store, and the 3x3 opening runs separably on
-// 16x2 SIMD words (vertical min, horizontal min, vertical max, horizontal max: 3 loads + 2 VMIN
-// per pixel PAIR and pass).  The band buffer therefore starts at the aligned column x_begin - 16
-// (band column j lives at buffer column j + 16 - HALO) and is 288 columns wide.
+// The general kernel above is issue-bound on per-pixel address arithmetic and byte loads.  Here stage D
+// works on aligned groups of 8 pixels (three 32-bit loads per frame for packed 12-bit), decodes them to
+// 16x2 words and takes the thresholded difference with DPX three-input min/max (10 instructions per pixel
+// PAIR); the 3x3 opening never goes back to shared memory between its four passes (a lane walks down one
+// word column with the last three rows in registers and trades edge pixels by shuffle); the Gaussian is
+// unrolled for the radius (template) and shares one pass over the opened rows between its three output
+// rows.  The band buffer starts at the aligned column x_begin - 16 (band column j lives at buffer column
+// j + 16 - HALO) and is 288 columns wide.
 constexpr int kBandPad = 16;
 constexpr int kBandLWA = kHeadTileW + 2 * kBandPad;      // 288
 constexpr int kBandGroups = kBandLWA / 8;                // 36 groups of 8 pixels per band row
 constexpr int kBandWords = kBandLWA / 2;                 // 144 16x2 words per band row
 
 template <int BITS>
-__device__ __forceinline__ void load8_global(const uint8_t* __restrict__ base, int64_t q0, int (&v)[8]) {
+__device__ __forceinline__ void load8_16x2(const uint8_t* __restrict__ base, int64_t q0, uint32_t (&x)[4]) {
   if (BITS == 12) {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(base + (q0 >> 1) * 3);
-    decode12x8(__ldg(w), __ldg(w + 1), __ldg(w + 2), v);
+    decode12x8_16x2(__ldg(w), __ldg(w + 1), __ldg(w + 2), x);
   } else if (BITS == 16) {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(base + q0 * 2);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t u = __ldg(w + k);
-      v[2 * k] = (int)(u & 0xFFFFu);
-      v[2 * k + 1] = (int)(u >> 16);
-    }
+    for (int k = 0; k < 4; ++k) x[k] = __ldg(w + k);
   } else {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(base + q0);
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const uint32_t u = __ldg(w + k);
-#pragma unroll
-      for (int b = 0; b < 4; ++b) v[4 * k + b] = (int)((u >> (8 * b)) & 0xFFu);
-    }
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
+    x[0] = __byte_perm(w0, 0u, 0x4140);
+    x[1] = __byte_perm(w0, 0u, 0x4342);
+    x[2] = __byte_perm(w1, 0u, 0x4140);
+    x[3] = __byte_perm(w1, 0u, 0x4342);
   }
 }
 
-template <int BITS>
+// (double)n for 0 <= n < 2^32 without the conversion pipe: 2^52 + n is exact, and so is the subtraction
+__device__ __forceinline__ double u2d(uint32_t n) {
+  return __dsub_rn(__hiloint2double(0x43300000, (int)n), 4503599627370496.0);
+}
+
+// Sobel(axis=1) and np.gradient(axis=1) of the centre row from the three blurred rows `bl`
+__device__ __forceinline__ void band_lines_out(const HeadBandParams& p, const double* bl, int LW, int HALO, int tw,
+                                               int x_begin, int f) {
+  const int W = p.width;
+  double* out_s = p.lines + ((int64_t)f * 2 + 0) * W;
+  double* out_g = p.lines + ((int64_t)f * 2 + 1) * W;
+  for (int t = threadIdx.x; t < tw; t += kHeadThreads) {
+    const int j = HALO + t;
+    const int x = x_begin + t;
+    double s3[3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const double* v = bl + b * LW;
+      // correlate1d([-1,0,1]): tmp = in[0]*0; tmp += (in[-1] - in[+1]) * (-1)
+      s3[b] = __dadd_rn(__dmul_rn(v[j], 0.0), __dmul_rn(__dsub_rn(v[j - 1], v[j + 1]), -1.0));
+    }
+    // correlate1d([1,2,1]) along rows: tmp = in[0]*2; tmp += (in[-1] + in[+1]) * 1
+    out_s[x] = __dadd_rn(__dmul_rn(s3[1], 2.0), __dmul_rn(__dadd_rn(s3[0], s3[2]), 1.0));
+    const double* v = bl + 1 * LW;
+    double g;
+    if (x == 0) g = __ddiv_rn(__dsub_rn(v[j + 1], v[j]), 1.0);
+    else if (x == W - 1) g = __ddiv_rn(__dsub_rn(v[j], v[j - 1]), 1.0);
+    else g = __ddiv_rn(__dsub_rn(v[j + 1], v[j - 1]), 2.0);
+    out_g[x] = g;
+  }
+}
+
+// The float64 stages with the radius known at compile time: one thread per column builds all three
+// row-blurred values from ONE pass over the 2R+3 opened rows (a symmetric pair of uint16 is summed as an
+// integer before its single conversion: exact, so the same double as scipy's in[-k] + in[+k]); taps come
+// straight from the constant bank.  Same operation order as band_float_stages.
+template <int R>
+__device__ __forceinline__ void band_float_stages_fast(const HeadBandParams& p, const uint16_t* band, int off, int LW,
+                                                       int tw, int x_begin, int f, double* g0, double* bl) {
+  constexpr int HALO = R + 3;
+  const int tid = threadIdx.x;
+  for (int j = 2 + tid; j < LW - 2; j += kHeadThreads) {
+    const uint16_t* col = band + (HALO - 1 - R) * kBandLWA + j + off;
+    uint32_t v[2 * R + 3];
+#pragma unroll
+    for (int k = 0; k < 2 * R + 3; ++k) v[k] = col[k * kBandLWA];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      double tmp = __dmul_rn(u2d(v[R + b]), p.w[R]);
+#pragma unroll
+      for (int jj = -R; jj < 0; ++jj) tmp = __dadd_rn(tmp, __dmul_rn(u2d(v[R + b + jj] + v[R + b - jj]), p.w[R + jj]));
+      g0[b * LW + j] = tmp;
+    }
+  }
+  __syncthreads();
+  const int cols = tw + 2;
+  for (int e = tid; e < 3 * cols; e += kHeadThreads) {
+    const int b = (e >= cols) + (e >= 2 * cols);
+    const int j = HALO - 1 + e - b * cols;
+    const double* g = g0 + b * LW + j;
+    double tmp = __dmul_rn(g[0], p.w[R]);
+#pragma unroll
+    for (int jj = -R; jj < 0; ++jj) tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(g[jj], g[-jj]), p.w[R + jj]));
+    bl[b * LW + j] = tmp;
+  }
+  __syncthreads();
+  band_lines_out(p, bl, LW, HALO, tw, x_begin, f);
+  __syncthreads();      // the next work item reuses the shared-memory band
+}
+
+// RT = the Gaussian radius when it is one of the instantiated ones (2, 4, 6, 8: sigma 0.5 .. 2), else 0
+template <int BITS, int RT>
 __global__ void __launch_bounds__(kHeadThreads) head_band_fast_kernel(const HeadBandParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x;
   const int W = p.width, H = p.height;
-  const int R = p.radius;
+  const int R = RT ? RT : p.radius;
   const int HALO = R + 3;
   const int NB = 2 * HALO + 1;
   const int off = kBandPad - HALO;          // >= 5: kMaxRadius + 3 = 11 <= kBandPad
   const int c = H / 2;
   const int tiles_x = (W + kHeadTileW - 1) / kHeadTileW;
   const int n_work = __ldg(p.scratch) * tiles_x;
-  const int bg = __ldg(p.bg_dev);
-  uint16_t* bufA = reinterpret_cast<uint16_t*>(smem);                    // [NB][kBandLWA]
-  uint16_t* bufB = bufA + NB * kBandLWA;                                  // [NB][kBandLWA]
+  const uint32_t bg = (uint32_t)__ldg(p.bg_dev);
+  const uint32_t bg2 = bg | (bg << 16);
+  const uint32_t tm1 = (uint32_t)max(p.diff_thr, 1) - 1u;      // d >= 0 always: thresholds 0 and 1 keep the same pixels
+  const uint32_t t2 = tm1 | (tm1 << 16);
+  uint16_t* bufA = reinterpret_cast<uint16_t*>(smem);                    // [NB][kBandLWA]  difference
+  uint16_t* bufB = bufA + NB * kBandLWA;                                  // [NB][kBandLWA]  opened difference
   uint32_t* A32 = reinterpret_cast<uint32_t*>(bufA);
   uint32_t* B32 = reinterpret_cast<uint32_t*>(bufB);
   const int LWmax = kHeadTileW + 2 * HALO;
@@ -289,23 +360,23 @@ __global__ void __launch_bounds__(kHeadThreads) head_band_fast_kernel(const Head
     const uint8_t* prior = hf >= 0 ? p.frames + (int64_t)hf * p.frame_bytes : p.halo;
     const uint8_t* cur = p.frames + (int64_t)f * p.frame_bytes;
 
-    // ---- D: thresholded difference, 8 pixels per task; groups outside the image are mirrored below ----
+    // ---- D: thresholded difference on 16x2 words, 8 pixels per task; groups outside the image are mirrored below
     for (int t = tid; t < NB * kBandGroups; t += kHeadThreads) {
       const int i = t / kBandGroups, g = t - i * kBandGroups;
       const int xg = x_begin - kBandPad + 8 * g;
       if (g >= groups || xg < 0 || xg + 8 > W) continue;
       const int64_t q0 = (int64_t)reflect_idx(c - HALO + i, H) * W + xg;
-      int a[8], b[8];
-      load8_global<BITS>(cur, q0, a);
-      load8_global<BITS>(prior, q0, b);
-      uint32_t o[4];
+      uint32_t a[4], b[4], o[4];
+      load8_16x2<BITS>(cur, q0, a);
+      load8_16x2<BITS>(prior, q0, b);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        int d0 = max(a[2 * k] - bg, 0) - max(b[2 * k] - bg, 0);
-        int d1 = max(a[2 * k + 1] - bg, 0) - max(b[2 * k + 1] - bg, 0);
-        if (d0 < p.diff_thr) d0 = 0;
-        if (d1 < p.diff_thr) d1 = 0;
-        o[k] = (uint32_t)d0 | ((uint32_t)d1 << 16);      // diff_thr >= 0 (launcher): 0 <= d <= 65535
+        const uint32_t sa = __vimax3_u16x2(a[k], bg2, bg2) - bg2;          // max(a - bg, 0) per lane
+        const uint32_t sb = __vimax3_u16x2(b[k], bg2, bg2) - bg2;
+        const uint32_t rd = __vimax3_u16x2(sa, sb, sb) - sb;               // relu(d)
+        const uint32_t r2 = __vimax3_u16x2(rd, t2, t2) - t2;               // relu(relu(d) - (thr-1))
+        const uint32_t m2 = __vimin3_u16x2(r2, 0x00010001u, 0x00010001u);  // [d >= thr]
+        o[k] = r2 + m2 * tm1;                                              // d where d >= thr, else 0
       }
       *reinterpret_cast<uint4*>(bufA + i * kBandLWA + 8 * g) = make_uint4(o[0], o[1], o[2], o[3]);
     }
@@ -321,42 +392,42 @@ __global__ void __launch_bounds__(kHeadThreads) head_band_fast_kernel(const Head
       }
       __syncthreads();
     }
-    // ---- 3x3 opening, separable on 16x2 words: min rows, min columns, max rows, max columns ----------
-    // (buffer borders clamp; they lie outside the region the Gaussian reads, like the zeros of the
-    // general kernel).  One warp per band row, lanes over the words of the row.
+    // ---- 3x3 opening in registers: a lane owns one 16x2 word column and walks down the band rows, holding
+    // the last three difference rows (vertical min), exchanging with its neighbours by shuffle (horizontal
+    // min -> erosion row), then the same on the last three erosion rows with max.  A warp's first and last
+    // lane only feed their neighbours, so warps overlap by two words; opened rows [2, NB-2) x words
+    // [1, words-1) are written - a superset of what the Gaussian reads.
     {
       const int warp = tid >> 5, lane = tid & 31;
-      // rows: dst[i] = op(src[i-1], src[i], src[i+1])
-      auto rows_pass = [&](const uint32_t* src, uint32_t* dst, auto op) {
-        for (int i = warp; i < NB; i += kHeadThreads / 32) {
-          const uint32_t* up = src + max(i - 1, 0) * kBandWords;
-          const uint32_t* md = src + i * kBandWords;
-          const uint32_t* dn = src + min(i + 1, NB - 1) * kBandWords;
-          for (int w = lane; w < words; w += 32) dst[i * kBandWords + w] = op(op(up[w], md[w]), dn[w]);
-        }
-      };
-      // columns: neighbours straddle words - (pixel 2w-1, 2w) and (2w+1, 2w+2) via PRMT
-      auto cols_pass = [&](const uint32_t* src, uint32_t* dst, auto op) {
-        for (int i = warp; i < NB; i += kHeadThreads / 32) {
-          const uint32_t* md = src + i * kBandWords;
-          for (int w = lane; w < words; w += 32) {
-            const uint32_t l = md[max(w - 1, 0)], m = md[w], r = md[min(w + 1, words - 1)];
-            dst[i * kBandWords + w] = op(op(__byte_perm(l, m, 0x5432), m), __byte_perm(m, r, 0x5432));
+      const int n_chunks = (words - 2 + 29) / 30;
+      if (warp < n_chunks) {
+        const int w = 30 * warp + lane;
+        const bool st_ok = lane >= 1 && lane <= 30 && w <= words - 2;
+        const uint32_t* src = A32 + min(w, words - 1);
+        uint32_t* dst = B32 + w;
+        uint32_t d0 = src[0], d1 = src[kBandWords];
+        uint32_t e0 = 0u, e1 = 0u;
+        for (int i = 2; i < NB; ++i) {
+          const uint32_t d2 = src[i * kBandWords];
+          const uint32_t v = __vimin3_u16x2(d0, d1, d2);                     // rows i-2 .. i
+          d0 = d1;
+          d1 = d2;
+          const uint32_t vl = __shfl_up_sync(0xFFFFFFFFu, v, 1), vr = __shfl_down_sync(0xFFFFFFFFu, v, 1);
+          const uint32_t e2 = __vimin3_u16x2(__byte_perm(vl, v, 0x5432), v, __byte_perm(v, vr, 0x5432));   // erosion row i-1
+          if (i >= 4) {
+            const uint32_t x = __vimax3_u16x2(e0, e1, e2);                   // erosion rows i-3 .. i-1
+            const uint32_t xl = __shfl_up_sync(0xFFFFFFFFu, x, 1), xr = __shfl_down_sync(0xFFFFFFFFu, x, 1);
+            const uint32_t o = __vimax3_u16x2(__byte_perm(xl, x, 0x5432), x, __byte_perm(x, xr, 0x5432));  // opened row i-2
+            if (st_ok) dst[(i - 2) * kBandWords] = o;
           }
+          e0 = e1;
+          e1 = e2;
         }
-      };
-      auto vmin = [](uint32_t x, uint32_t y) { return __vminu2(x, y); };
-      auto vmax = [](uint32_t x, uint32_t y) { return __vmaxu2(x, y); };
-      rows_pass(A32, B32, vmin);
-      __syncthreads();
-      cols_pass(B32, A32, vmin);
-      __syncthreads();
-      rows_pass(A32, B32, vmax);
-      __syncthreads();
-      cols_pass(B32, A32, vmax);
+      }
       __syncthreads();
     }
-    band_float_stages(p, bufA, kBandLWA, off, LW, tw, x_begin, f, g0, bl);
+    if (RT) band_float_stages_fast<RT ? RT : 2>(p, bufB, off, LW, tw, x_begin, f, g0, bl);
+    else band_float_stages(p, bufB, kBandLWA, off, LW, tw, x_begin, f, g0, bl);
   }
 }
 
@@ -1027,7 +1098,7 @@ int head_lines_impl(const void* frames, const void* halo, int64_t n_frames, int 
   head_flags_kernel<<<(unsigned)((n_frames + warps - 1) / warps), kHeadThreads, 0, st>>>(p);
   FF_CUDA_TRY(cudaGetLastError());
   const int tiles_x = (width + kHeadTileW - 1) / kHeadTileW;
-  const bool fast = morphology_size == 3 && (width % 8) == 0 && (p.frame_bytes % 4) == 0 && getenv("FF_BAND_GENERAL") == nullptr &&
+  const bool fast = morphology_size == 3 && diff_thr <= 65535 && (width % 8) == 0 && (p.frame_bytes % 4) == 0 && getenv("FF_BAND_GENERAL") == nullptr &&
                     (reinterpret_cast<uintptr_t>(frames) % 4) == 0 &&
                     (halo == nullptr || (reinterpret_cast<uintptr_t>(halo) % 4) == 0);
   const size_t smem_general = smem;
@@ -1046,10 +1117,20 @@ int head_lines_impl(const void* frames, const void* halo, int64_t n_frames, int 
     return FF_OK;
   };
   if (fast) {
+    auto by_radius = [&](auto bits_tag) -> int {
+      constexpr int B = decltype(bits_tag)::value;
+      switch (radius) {
+        case 2: return launch(head_band_fast_kernel<B, 2>, smem_fast);
+        case 4: return launch(head_band_fast_kernel<B, 4>, smem_fast);
+        case 6: return launch(head_band_fast_kernel<B, 6>, smem_fast);
+        case 8: return launch(head_band_fast_kernel<B, 8>, smem_fast);
+        default: return launch(head_band_fast_kernel<B, 0>, smem_fast);
+      }
+    };
     switch (bits) {
-      case 8: return launch(head_band_fast_kernel<8>, smem_fast);
-      case 12: return launch(head_band_fast_kernel<12>, smem_fast);
-      default: return launch(head_band_fast_kernel<16>, smem_fast);
+      case 8: return by_radius(std::integral_constant<int, 8>{});
+      case 12: return by_radius(std::integral_constant<int, 12>{});
+      default: return by_radius(std::integral_constant<int, 16>{});
     }
   }
   switch (bits) {

@@ -40,6 +40,8 @@ struct StreamParams {
   int32_t* partial;
   void* diff_out;
   uint16_t* decoded_out;
+  int unit_frames;         // streamx_kernel with a retained difference: frames per unit (0: contiguous runs per CTA)
+  int64_t n_units;         // ... and the number of (frame segment, tile) units, dealt to the CTAs round-robin
   int idle_ns;             // how long an idle detector warp sleeps between looks at the queue
   int slab_shift;          // range_kernel: 2^slab_shift consecutive items per slab (slabs are dealt to the CTAs round-robin)
   int slab_step_frames;    // (gridDim.x << slab_shift) = slab_step_frames * tiles_per_frame + slab_step_tiles:
@@ -915,7 +917,13 @@ __global__ void __launch_bounds__(kOutThreads) streamx_kernel(const StreamParams
   const int64_t total_work = (int64_t)p.tiles_per_frame * p.n_frames;
   int64_t work = (int64_t)blockIdx.x * p.items_per_cta;
   const int64_t work_end = min(work + p.items_per_cta, total_work);
-  if (work >= work_end) return;
+  // Retained difference: the carry needs consecutive frames of ONE tile, so the work is cut into UNITS of
+  // unit_frames frames of one tile, numbered segment-major, and the units are dealt to the CTAs round-robin:
+  // at any moment all CTAs are in the same few frames - the reads of the whole GPU fall into a couple of
+  // contiguous frames and so do its writes, instead of 148 read and 148 write streams all over the clip.
+  const bool units = DIFF && p.unit_frames > 0;
+  int64_t unit = blockIdx.x;
+  if (!units && work >= work_end) return;
   const int64_t groups_per_frame = p.px_per_frame / kGroupPx;
   const bool producer = warp == kWarpsPerCta;
   if (producer && (tid & 31) != 0) return;
@@ -951,14 +959,22 @@ __global__ void __launch_bounds__(kOutThreads) streamx_kernel(const StreamParams
     for (int j = 0; j < 4; ++j) pn[k][j] = kUnsigned ? 0u : 0x40004000u;
   uint32_t git = 0;
 
-  while (work < work_end) {
+  while (units ? unit < p.n_units : work < work_end) {
     // ---- one segment: consecutive items that share the carry (DIFF) or simply the rest of the run
     int tile, f0, n_seg;
     const uint8_t* halo_ptr = nullptr;
     if (DIFF) {
-      tile = (int)(work / p.n_frames);
-      f0 = (int)(work - (int64_t)tile * p.n_frames);
-      n_seg = (int)min((int64_t)(p.n_frames - f0), work_end - work);
+      if (units) {
+        const int seg = (int)(unit / p.tiles_per_frame);
+        tile = (int)(unit - (int64_t)seg * p.tiles_per_frame);
+        f0 = seg * p.unit_frames;
+        n_seg = min(p.unit_frames, p.n_frames - f0);
+        unit += gridDim.x;
+      } else {
+        tile = (int)(work / p.n_frames);
+        f0 = (int)(work - (int64_t)tile * p.n_frames);
+        n_seg = (int)min((int64_t)(p.n_frames - f0), work_end - work);
+      }
       int hf = f0 - 1;
       if (p.skip != nullptr)
         while (hf >= 0 && p.skip[hf]) --hf;
@@ -1080,7 +1096,29 @@ int launch_streamx(StreamParams p, int ctas_cap, cudaStream_t st) {
   const int64_t total_work = (int64_t)p.tiles_per_frame * p.n_frames;
   p.items_per_cta = (total_work + wave - 1) / wave;
   if (p.items_per_cta < 1) p.items_per_cta = 1;
-  const int64_t grid = (total_work + p.items_per_cta - 1) / p.items_per_cta;
+  int64_t grid = (total_work + p.items_per_cta - 1) / p.items_per_cta;
+  static const bool sync_units = getenv("FF_STREAMX_SYNC") == nullptr || atoi(getenv("FF_STREAMX_SYNC")) != 0;   // tuning knob
+  p.unit_frames = 0;
+  if (DIFF && sync_units && p.n_frames >= 96) {
+    // frames per unit: long enough that the extra halo item per unit stays below ~2 %, and such that the
+    // units divide evenly over the wave (every CTA the same number of units)
+    int best_nseg = 1;
+    double best_cost = 1e30;
+    for (int nseg = (p.n_frames + 511) / 512; nseg <= p.n_frames / 48; ++nseg) {
+      const int len = (p.n_frames + nseg - 1) / nseg;
+      const int64_t units = (int64_t)p.tiles_per_frame * ((p.n_frames + len - 1) / len);
+      const int64_t rounds = (units + wave - 1) / wave;
+      const double cost = (double)(rounds * wave) / (double)units * (1.0 + 1.0 / len);      // imbalance x halo overhead
+      if (cost < best_cost - 1e-9) {
+        best_cost = cost;
+        best_nseg = nseg;
+      }
+      if (cost < 1.012) break;
+    }
+    p.unit_frames = (p.n_frames + best_nseg - 1) / best_nseg;
+    p.n_units = (int64_t)p.tiles_per_frame * ((p.n_frames + p.unit_frames - 1) / p.unit_frames);
+    grid = p.n_units < wave ? p.n_units : wave;
+  }
   return launch_kernel(kern, dim3((unsigned)grid), dim3(kOutThreads), smem, st, p.pdl != 0, p);
 }
 
