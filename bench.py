@@ -419,13 +419,15 @@ def leg_c2(cx: Ctx, line: dict) -> None:
         res = eng.process_range(packed, fpr, h, w, 12, params, frame0=frame0, first_frame=a, halo=halo)
         return res, res
 
-    for _ in range(args.warmup):
-        step_device()
-    cx.barrier()
+    # the clock sampler comes up BEFORE the warm-up steps: nothing idles the GPU between warm-up and timed region
     sampler = ClockSampler(cx.local_rank, period_ms=args.clock_period_ms)
     if rank == 0 and args.clock_period_ms > 0:
         sampler.start()
         time.sleep(0.25)
+    cx.barrier()
+    for _ in range(args.warmup):
+        step_device()
+    cx.barrier()
     eng._stream_events, eng._stream_event_tick = [], 0
     launches0 = eng.launches
     ms_per_step, (out, res) = cx.timed_steps(step_device, args.steps, 0, join=exchange.join if world > 1 else None)
@@ -581,7 +583,7 @@ def leg_c2(cx: Ctx, line: dict) -> None:
     # ---------------- the detector the reference executes at HEAD, same clip (rank 0, N=1 only) -------
     head = None
     if rank == 0 and world == 1 and not args.no_head:
-        head = leg_head(cx, spec, packed, frame0, fpr, h, w, fb)
+        head = leg_head(cx, spec, packed, frame0, fpr, h, w, fb, host=host)
 
     if rank == 0:
         achieved = fpr * alg_bytes_per_frame / (kernel_ms * 1e-3) / 1e9
@@ -620,20 +622,43 @@ def leg_c2(cx: Ctx, line: dict) -> None:
 
 def measured_traffic():
     """DRAM bytes per launch of the range kernel from the round's `ncu --set full` capture, only if that capture
-    was taken on the library that is loaded now (stamped with the .so's SHA-256); else null."""
-    import hashlib
+    was taken on a library built from the sources the loaded one was built from (`build.source_fingerprint`: nvcc's
+    output is not byte-reproducible, so the binary's own hash would change with every rebuild); else null."""
     tpath = REPO / "profiles" / "range_kernel_traffic.json"
     if not tpath.exists():
         return None, "no capture committed"
     rec = json.loads(tpath.read_text())
-    from high_speed_image_processing_b200._cabi import LIB_PATH
-    sha = hashlib.sha256(LIB_PATH.read_bytes()).hexdigest()
-    if rec.get("lib_sha256") != sha:
-        return None, f"profiles/range_kernel_traffic.json was captured on another build ({rec.get('lib_sha256', '?')[:12]})"
-    return rec.get("dram_bytes_per_launch"), f"ncu --set full, {rec.get('captured', '?')}, same libflamefront.so"
+    from high_speed_image_processing_b200 import build as ffbuild
+    built, now = ffbuild.built_fingerprint(), ffbuild.source_fingerprint()
+    if not built or built != now:
+        return None, "the loaded libflamefront.so was not built from the sources in the tree"
+    if rec.get("source_fingerprint") != built:
+        return None, (f"profiles/range_kernel_traffic.json was captured on a build of other sources "
+                      f"({str(rec.get('source_fingerprint', '?'))[:12]})")
+    return rec.get("dram_bytes_per_launch"), f"ncu --set full, {rec.get('captured', '?')}, library built from the same sources"
 
 
-def leg_head(cx: Ctx, spec, packed, frame0, fpr, h, w, fb) -> dict:
+class _HostClip:
+    """The part of PhotonVideo that process_video reads, over a clip that already sits in (pinned) host memory."""
+
+    def __init__(self, raw, n, h, w, bits, spec):
+        self.raw, self.n, self.frame_shape, self.storage_bits, self.spec = raw, n, (h, w), bits, spec
+        self.fb = h * w * bits // 8
+        self.frame_rate = int(spec.record_rate)
+
+    def __len__(self):
+        return self.n
+
+    def raw_frames(self, a, b):
+        return self.raw[a * self.fb:b * self.fb]
+
+    def get_absolute_time(self, i):
+        return (self.spec.start_frame + i * self.spec.skip_frame) / self.spec.record_rate
+
+    get_time = get_absolute_time
+
+
+def leg_head(cx: Ctx, spec, packed, frame0, fpr, h, w, fb, host=None) -> dict:
     """The same clip through the FlameDetector parity path, next to the reference's own code on the CPU."""
     import numpy as np
     torch, eng, args = cx.torch, cx.eng, cx.args
@@ -657,6 +682,28 @@ def leg_head(cx: Ctx, spec, packed, frame0, fpr, h, w, fb) -> dict:
                     "tracker) on the same clip, device-resident, steps back to back",
             "value": fpr / (head_ms * 1e-3), "unit": UNIT, "ms_per_clip": head_ms, "rows": len(got.rows),
             "stop": list(got.stop) if got.stop else None}
+    if host is not None:
+        # end to end through the public call: process_video(detection_method="head") on the clip in pinned host
+        # memory - chunked upload, streaming + band + tracker kernels, rows and velocities built on the host
+        from high_speed_image_processing_b200.process_videos import VideoSourceConfig, process_video
+        clip_h = _HostClip(host.numpy(), fpr, h, w, 12, spec)
+        cfg = VideoSourceConfig(name="bench", enabled=True, calibration=cal_h, position_offset=off_h,
+                                detection_method="head", head_params=hp)
+        vres = process_video(clip_h, cfg, cal_h, off_h, engine=eng)
+        n_e2e = max(1, min(args.steps, args.e2e_steps))
+        t_e = time.perf_counter()
+        for _ in range(n_e2e):
+            vres = process_video(clip_h, cfg, cal_h, off_h, engine=eng)
+        torch.cuda.synchronize()
+        t_e = (time.perf_counter() - t_e) / n_e2e
+        assert [list(r) for r in vres.rows] == [list(r) for r in got.rows] and vres.stop == got.stop, \
+            "HEAD rows from the host-resident clip differ from the device-resident run"
+        stop_f = got.stop[1] if got.stop else fpr
+        head["e2e"] = {"value": fpr / t_e, "unit": UNIT, "ms_per_clip": t_e * 1e3, "steps": n_e2e,
+                       "h2d_bytes_per_step": int(min(fpr, stop_f + 1) * fb + fb),
+                       "d2h_bytes_per_step": int(fpr * 21),
+                       "how": "process_video(detection_method='head') on the clip in pinned host memory: uploads in "
+                              "chunks of FF_HEAD_CHUNK_MB, kernels, result rows + velocities on the host"}
     if args.no_cpu_baseline:
         return head
     # frame 0 + a window that starts in the empty lead-in and runs into the flame, through the reference's OWN
@@ -702,7 +749,8 @@ def leg_head(cx: Ctx, spec, packed, frame0, fpr, h, w, fb) -> dict:
                 "value": (len(clip) - 1) / t_all, "unit": UNIT, "cores": cores, "kind": "reference",
                 "how": "same window, the reference's round-robin frame decomposition (parallel.py:99-100), one "
                        "worker process per core, each with its own FlameDetector as under mpiexec"}
-            head["e2e_ratio_vs_reference_all_cores"] = None       # filled by the caller once e2e is known
+            if "e2e" in head:
+                head["e2e_ratio_vs_reference_all_cores"] = head["e2e"]["value"] / head["cpu_baseline"]["all_cores"]["value"]
         except Exception as exc:
             head["cpu_baseline"]["all_cores"] = {"error": repr(exc)}
     return head
@@ -1031,7 +1079,6 @@ def own_arm(args) -> None:
         head = line.get("head_detector")
         if head and head.get("cpu_baseline", {}).get("all_cores", {}).get("value"):
             head["ratio_vs_reference_all_cores"] = head["value"] / head["cpu_baseline"]["all_cores"]["value"]
-            head.pop("e2e_ratio_vs_reference_all_cores", None)
         line["leg_seconds"] = {k: round(v, 1) for k, v in t_legs.items()}
         print(json.dumps(line), flush=True)
     cx.close()

@@ -7,6 +7,7 @@ this package.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Optional
 
@@ -139,7 +140,7 @@ def load(path: Optional[Path] = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = Path(path) if path is not None else LIB_PATH
+    p = Path(path) if path is not None else Path(os.environ.get("FF_LIB_PATH") or LIB_PATH)   # A/B knob for tools/
     if not p.exists():
         raise FlameFrontLibraryError(
             f"{p} not found - build it with `python -m high_speed_image_processing_b200.build` "

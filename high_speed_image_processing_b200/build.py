@@ -37,18 +37,40 @@ def find_nvcc() -> str:
     raise RuntimeError("nvcc not found; libflamefront.so cannot be built")
 
 
+STAMP_PATH = LIB_DIR / "libflamefront.so.sources"
+
+
+def source_fingerprint() -> str:
+    """SHA-256 over everything the library is compiled from (sources, headers, nvcc flags).  nvcc's output is not
+    byte-reproducible (the mangled names of anonymous namespaces differ from run to run), so measurements that
+    belong to one build - profiles/range_kernel_traffic.json - are stamped with this instead of a hash of the
+    binary; build() records next to the .so which sources it was made from."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted([CSRC / s for s in SOURCES] + HEADERS, key=lambda q: q.name):
+        h.update(f.name.encode() + b"\0" + f.read_bytes() + b"\0")
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def built_fingerprint() -> str:
+    """The fingerprint of the sources the library on disk was built from ('' if unknown)."""
+    return STAMP_PATH.read_text().strip() if STAMP_PATH.exists() and LIB_PATH.exists() else ""
+
+
 def is_stale() -> bool:
     if not LIB_PATH.exists():
         return True
     built = LIB_PATH.stat().st_mtime
     deps = [CSRC / s for s in SOURCES] + HEADERS + [Path(__file__)]
-    return any(d.stat().st_mtime > built for d in deps)
+    return any(d.stat().st_mtime > built for d in deps) or built_fingerprint() != source_fingerprint()
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not is_stale():
         return LIB_PATH
     LIB_DIR.mkdir(parents=True, exist_ok=True)
+    fingerprint = source_fingerprint()          # before compiling: what the compiler is about to read
     nvcc = find_nvcc()
     objs = []
     procs = []
@@ -74,6 +96,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}")
     os.replace(tmp, LIB_PATH)
+    STAMP_PATH.write_text(fingerprint + "\n")
     return LIB_PATH
 
 

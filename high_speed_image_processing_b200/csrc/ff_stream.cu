@@ -47,6 +47,8 @@ struct StreamParams {
   int slab_step_frames;    // (gridDim.x << slab_shift) = slab_step_frames * tiles_per_frame + slab_step_tiles:
   int slab_step_tiles;     // how far (frame, tile) moves from one slab of a CTA to its next
   int pdl;                 // host side only: launch with the programmatic-dependent-launch attribute
+  uint32_t neg_one;        // 0xFFFFFFFF, as a value the compiler cannot see: "c - x" written as x * neg_one + c is an
+                           // IMAD on the FMA pipe instead of one more instruction on the ALU pipe (streamx_kernel)
 };
 
 template <int BITS>
@@ -855,14 +857,19 @@ int launch_range_fused(StreamParams p, const DetectParams& d, cudaStream_t st) {
   return FF_OK;
 }
 
-// ---- uint16 difference image and / or decoded uint16 pixels (8-bit, packed 12-bit, 16-bit input) ---
+// ---- difference image (uint16 / float32 / float64) and / or decoded uint16 pixels (8-bit, packed 12-bit, 16-bit input) ---
 // Same skeleton as count12_kernel (producer warp, full/empty ring, no CTA-wide barrier), same
 // pixel ownership as the general template (thread t owns groups t, t+256, t+512, t+768 of the
 // tile, so every warp-level 16-byte store covers 512 contiguous bytes) and all arithmetic on
 // 16x2 SIMD lanes.  The previous frame is carried as Pn = 0x4000 - sub per lane, which turns the
-// lane-wise difference into a plain 32-bit add (E = sub + Pn = 0x4000 + d, no lane can overflow)
-// that ptxas is free to place on the FMA pipe: the ALU pipe, not HBM, was what held the first
-// version of this kernel at 0.85 of the copy rate (ncu: ALU 71 % busy, FMA 6 %).
+// lane-wise difference into a plain 32-bit add (E = sub + Pn = 0x4000 + d, no lane can overflow).
+// The ALU pipe, not HBM, is what held this kernel back (ncu, round 1: ALU 71 % busy -> 0.85 of the copy rate;
+// round 2: 64 % with math-pipe throttle at 2.25 warps per scheduler -> 0.90), so the inner loop is counted in ALU
+// instructions per 8 pixels: adds and the carry update are IMADs on the FMA pipe, no literal-zero operands
+// (kLaneMin2), no per-word selects, and the item header is strength-reduced by hand.  With that the ring depth
+// became the tuning parameter, sharply and differently per variant (launch_streamx_tuned).
+// float32 / float64 images are the same integer lanes widened on the way out (lane_to_float / lane_to_double:
+// exact), with lane pairs swapping words so that every store instruction of a warp writes whole 32-byte sectors.
 // Item order: tile-major with a halo item per segment when the difference is retained (the
 // carry needs consecutive frames of one tile); frame-major otherwise.
 // 8-bit pixels are widened to 16x2 lanes with two PRMTs per word and share the signed-lane
@@ -870,10 +877,26 @@ int launch_range_fused(StreamParams p, const DetectParams& d, cudaStream_t st) {
 // lanes are unsigned and every subtraction is "max, then subtract" (sub = max(x,bg) - bg,
 // relu(d) = max(sub,prev) - prev, ...), which cannot borrow across lanes.
 constexpr int kOutThreads = kThreads + 32;
+// "max(., 0)" is written as the RELU form of VIADDMNMX with the most negative lane value as its third operand:
+// a literal zero there is materialised into a register by ptxas again and again (one PRMT per use: 5 extra ALU
+// instructions per 8 pixels), any other value travels as an immediate.
+constexpr uint32_t kLaneMin2 = 0x80008000u;
 
 // Output stores are streaming (st.global.cs); plain and write-through stores measured the same
 // (C4 uint16 difference 0.920 / 0.925 / 0.926 of the copy rate).
 __device__ __forceinline__ void st_out(uint4* p, uint4 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_out(float4* p, float4 v) { __stcs(p, v); }
+
+// One 16-bit lane of a 16x2 word as float32, exactly: the lane becomes the low mantissa bits of 2^23 (one PRMT),
+// and 2^23 is subtracted again (one FADD) - no integer-to-float conversion unit involved.
+template <int HI>
+__device__ __forceinline__ float lane_to_float(uint32_t w) {
+  return __fadd_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, HI ? 0x7632 : 0x7610)), -8388608.0f);
+}
+template <int HI>
+__device__ __forceinline__ double lane_to_double(uint32_t w) {       // the same with 2^52
+  return __dadd_rn(__hiloint2double(0x43300000, (int)(HI ? w >> 16 : w & 0xFFFFu)), -4503599627370496.0);
+}
 
 template <int BITS>
 __device__ __forceinline__ void load_lanes(const uint8_t* stage, int g, uint32_t (&x)[4]) {
@@ -892,8 +915,14 @@ __device__ __forceinline__ void load_lanes(const uint8_t* stage, int g, uint32_t
   }
 }
 
-template <int BITS, bool COUNT, bool DIFF, bool DECODED, int STAGES>
+// (Sixteen consumer warps instead of eight - each thread two groups of a tile - were tried for latency hiding and
+// are slower, 0.93 against 0.97 on C4: the per-item header is paid per warp, and the kernel executed 27 % more
+// instructions; profiles/r02_streamx_stage_sweep.txt.)
+template <int BITS, bool COUNT, int DIFF, bool DECODED, int STAGES>
 __global__ void __launch_bounds__(kOutThreads) streamx_kernel(const StreamParams p) {
+  constexpr int NW = kWarpsPerCta;                         // consumer warps
+  constexpr int kCons = 32 * NW;                           // consumer threads
+  constexpr int kPerThread = 4 * kThreads / kCons;         // groups per thread and tile
   constexpr int kTileBytes = 4 * kThreads * BITS;          // 1024 groups of 8 pixels
   constexpr bool kUnsigned = BITS == 16;
   constexpr int kMaxPx = BITS == 8 ? 255 : (BITS == 12 ? 4095 : 65535);
@@ -908,7 +937,7 @@ __global__ void __launch_bounds__(kOutThreads) streamx_kernel(const StreamParams
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kWarpsPerCta);
+      mbar_init(&empty[s], NW);
     }
     fence_mbar_init();
   }
@@ -925,7 +954,7 @@ __global__ void __launch_bounds__(kOutThreads) streamx_kernel(const StreamParams
   int64_t unit = blockIdx.x;
   if (!units && work >= work_end) return;
   const int64_t groups_per_frame = p.px_per_frame / kGroupPx;
-  const bool producer = warp == kWarpsPerCta;
+  const bool producer = warp == NW;
   if (producer && (tid & 31) != 0) return;
   const uint64_t policy = producer ? policy_evict_first() : 0;
 
@@ -952,12 +981,16 @@ __global__ void __launch_bounds__(kOutThreads) streamx_kernel(const StreamParams
       k2 = ((uint32_t)(-(0x4000 + tm1)) & 0xFFFFu) * one2;  // relu(E + k) = relu(d - (thr-1))
     }
   }
-  uint32_t pn[4][4];       // carry, 16x2: 0x4000 - sub (signed lanes) or sub itself (unsigned lanes)
+  const uint32_t neg1 = p.neg_one;
+  uint32_t pn[kPerThread][4];       // carry, 16x2: 0x4000 - sub (signed lanes) or sub itself (unsigned lanes)
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+  for (int k = 0; k < kPerThread; ++k)
 #pragma unroll
     for (int j = 0; j < 4; ++j) pn[k][j] = kUnsigned ? 0u : 0x40004000u;
-  uint32_t git = 0;
+  int s = 0;                 // ring slot and its phase, carried across segments
+  uint32_t ph = 0;
+  const int last_tile = p.tiles_per_frame - 1;
+  const int last_groups = (int)(groups_per_frame - (int64_t)last_tile * kTileGroups);
 
   while (units ? unit < p.n_units : work < work_end) {
     // ---- one segment: consecutive items that share the carry (DIFF) or simply the rest of the run
@@ -989,28 +1022,35 @@ __global__ void __launch_bounds__(kOutThreads) streamx_kernel(const StreamParams
     const int n_items = n_seg + has_halo;
     bool have_prev = false;
 
-    for (int it = 0; it < n_items; ++it, ++git) {
-      // (frame, tile) of this item
-      int f, t;
-      if (DIFF) {
-        f = f0 + it - has_halo;
-        t = tile;
-      } else {
-        const int64_t w = (int64_t)tile + it;
-        f = f0 + (int)(w / p.tiles_per_frame);
-        t = (int)(w - (w / p.tiles_per_frame) * p.tiles_per_frame);
-      }
+    // Running state of the item loop, strength-reduced by hand (the item header - divisions, 64-bit products, the
+    // ring slot from a modulo - was a quarter of the consumers' instructions): DIFF items are consecutive frames of
+    // one tile (the halo item counts as frame f0 - 1), the others consecutive tiles in memory order.
+    int f = DIFF ? f0 - has_halo : f0;
+    int t = tile;
+    int64_t px0 = (int64_t)f * p.px_per_frame + (int64_t)t * (kTileGroups * kGroupPx);
+    int64_t pidx = ((int64_t)f * p.tiles_per_frame + t) * kWarpsPerCta + warp;
+    const uint8_t* src = p.frames + (int64_t)f * p.frame_bytes + (int64_t)t * kTileBytes;      // producer
+
+    for (int it = 0; it < n_items; ++it) {
       const bool is_halo = it < has_halo;
-      const int tile_groups = (int)min((int64_t)kTileGroups, groups_per_frame - (int64_t)t * kTileGroups);
-      const int s = git % STAGES;
-      const uint32_t ph = (git / STAGES) & 1u;
+      const int tile_groups = t == last_tile ? last_groups : kTileGroups;
 
       if (producer) {
         mbar_wait(&empty[s], ph ^ 1u);
-        const uint8_t* src = (is_halo ? halo_ptr : p.frames + (int64_t)f * p.frame_bytes) + (int64_t)t * kTileBytes;
         const uint32_t bytes = (uint32_t)tile_groups * (uint32_t)BITS;
         mbar_arrive_expect_tx(&full[s], bytes);
-        bulk_g2s(smem + s * kTileBytes, src, bytes, &full[s], policy);
+        bulk_g2s(smem + s * kTileBytes, is_halo ? halo_ptr + (int64_t)t * kTileBytes : src, bytes, &full[s], policy);
+        if (DIFF) {
+          src += p.frame_bytes;
+          ++f;
+        } else {
+          src += bytes;
+          if (++t == p.tiles_per_frame) t = 0;
+        }
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
         continue;
       }
 
@@ -1018,11 +1058,15 @@ __global__ void __launch_bounds__(kOutThreads) streamx_kernel(const StreamParams
       const uint8_t* stage = smem + s * kTileBytes;
       const bool skipped = DIFF && !is_halo && p.skip != nullptr && p.skip[f] != 0;
       const bool diff_valid = have_prev && !skipped;
-      const int64_t px0 = (int64_t)f * p.px_per_frame + (int64_t)t * (kTileGroups * kGroupPx);
+      // a frame without a valid difference (first of the clip, skipped) stores zeros: its threshold term is pushed
+      // below every possible lane value instead of selecting per output word (signed lanes)
+      const uint32_t kd2 = diff_valid ? k2 : 0x80018001u;
       uint32_t acc2 = 0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int g = tid + k * kThreads;
+      for (int k = 0; k < kPerThread; ++k) {
+        const int g = tid + k * kCons;
+        // (tiles end on a multiple of four groups: the two lanes of an exchanging pair are inside or outside together)
+        const uint32_t in_mask = (DIFF == FF_DIFF_F32 || DIFF == FF_DIFF_F64) ? __ballot_sync(0xFFFFFFFFu, g < tile_groups) : 0u;
         if (g < tile_groups) {
           uint32_t x[4];
           load_lanes<BITS>(stage, g, x);
@@ -1046,17 +1090,43 @@ __global__ void __launch_bounds__(kOutThreads) streamx_kernel(const StreamParams
                 o[j] = r2 + m2 * (uint32_t)tm1;                                              // d where d >= thr, else 0
                 if (!skipped) pn[k][j] = sub2;
               } else {
-                const uint32_t sub2 = __viaddmax_s16x2(x[j], nbg2, 0u);            // max(x - bg, 0)
+                const uint32_t sub2 = __viaddmax_s16x2_relu(x[j], nbg2, kLaneMin2);  // max(x - bg, 0)
                 const uint32_t e2 = sub2 + pn[k][j];                                // 0x4000 + d per lane
-                const uint32_t r2 = __viaddmax_s16x2_relu(e2, k2, 0u);              // relu(d - (thr-1))
+                const uint32_t r2 = __viaddmax_s16x2_relu(e2, kd2, kLaneMin2);       // relu(d - (thr-1))
                 const uint32_t m2 = __vimin_s16x2_relu(r2, one2);                   // [d >= thr]
                 o[j] = r2 + m2 * (uint32_t)tm1;                                     // d where d >= thr, else 0
-                if (!skipped) pn[k][j] = 0x40004000u - sub2;
+                if (!skipped) pn[k][j] = sub2 * neg1 + 0x40004000u;                  // 0x4000 - sub per lane
               }
             }
             if (!is_halo) {
-              uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.diff_out) + px0 + (int64_t)g * kGroupPx);
-              st_out(dst, diff_valid ? make_uint4(o[0], o[1], o[2], o[3]) : make_uint4(0u, 0u, 0u, 0u));
+              if (kUnsigned && !diff_valid) o[0] = o[1] = o[2] = o[3] = 0u;
+              if (DIFF == FF_DIFF_U16) {
+                uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.diff_out) + px0 + (int64_t)g * kGroupPx);
+                st_out(dst, make_uint4(o[0], o[1], o[2], o[3]));
+              } else if (DIFF == FF_DIFF_F64) {
+                // float64 image (the reference's dtype): 64 bytes per thread.  Lanes 2i and 2i+1 swap two words so
+                // that store instruction q of the warp writes sector q of every pair's 128 bytes in full: the even
+                // lane the first two pixels of the sector, the odd lane the other two.
+                const bool odd = (tid & 1) != 0;
+                const uint32_t r0 = __shfl_xor_sync(in_mask, odd ? o[0] : o[1], 1);
+                const uint32_t r1 = __shfl_xor_sync(in_mask, odd ? o[2] : o[3], 1);
+                const uint32_t a[4] = {odd ? r0 : o[0], odd ? r1 : o[2], odd ? o[1] : r0, odd ? o[3] : r1};
+                double2* pair = reinterpret_cast<double2*>(static_cast<double*>(p.diff_out) + px0 + (int64_t)(g & ~1) * kGroupPx) + (odd ? 1 : 0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) __stcs(pair + 2 * q, make_double2(lane_to_double<0>(a[q]), lane_to_double<1>(a[q])));
+              } else {                  // float32 image: the integer lanes widened exactly (lane_to_float)
+                // Lanes 2i and 2i+1 hold 16 consecutive pixels = 64 bytes of output: they swap halves so that each of
+                // the two store instructions of the warp writes whole 32-byte sectors (two 16-byte stores per thread
+                // straight from its own lanes leave every sector half-written twice: 0.859 against 0.875 on C4).
+                const bool odd = (tid & 1) != 0;
+                const uint32_t r0 = __shfl_xor_sync(in_mask, odd ? o[0] : o[2], 1);
+                const uint32_t r1 = __shfl_xor_sync(in_mask, odd ? o[1] : o[3], 1);
+                const uint32_t a0 = odd ? r0 : o[0], a1 = odd ? r1 : o[1];          // pixels 4 (tid & 1) .. + 3 of the pair
+                const uint32_t b0 = odd ? o[2] : r0, b1 = odd ? o[3] : r1;          // pixels 8 + 4 (tid & 1) ..
+                float4* pair = reinterpret_cast<float4*>(static_cast<float*>(p.diff_out) + px0 + (int64_t)(g & ~1) * kGroupPx) + (odd ? 1 : 0);
+                st_out(pair, make_float4(lane_to_float<0>(a0), lane_to_float<1>(a0), lane_to_float<0>(a1), lane_to_float<1>(a1)));
+                st_out(pair + 2, make_float4(lane_to_float<0>(b0), lane_to_float<1>(b0), lane_to_float<0>(b1), lane_to_float<1>(b1)));
+              }
             }
           }
         }
@@ -1067,7 +1137,23 @@ __global__ void __launch_bounds__(kOutThreads) streamx_kernel(const StreamParams
       else __syncwarp();
       if ((tid & 31) == 0) {
         mbar_arrive(&empty[s]);
-        if (COUNT && !is_halo) p.partial[((int64_t)f * p.tiles_per_frame + t) * kWarpsPerCta + warp] = cnt;
+        if (COUNT && !is_halo) p.partial[pidx] = cnt;
+      }
+      if (DIFF) {
+        ++f;
+        px0 += p.px_per_frame;
+        pidx += (int64_t)p.tiles_per_frame * kWarpsPerCta;
+      } else {
+        px0 += tile_groups * kGroupPx;
+        pidx += kWarpsPerCta;
+        if (++t == p.tiles_per_frame) {
+          t = 0;
+          ++f;
+        }
+      }
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1u;
       }
     }
   }
@@ -1075,7 +1161,7 @@ __global__ void __launch_bounds__(kOutThreads) streamx_kernel(const StreamParams
 
 int sm_count_cached();
 
-template <int BITS, bool COUNT, bool DIFF, bool DECODED, int STAGES>
+template <int BITS, bool COUNT, int DIFF, bool DECODED, int STAGES>
 int launch_streamx(StreamParams p, int ctas_cap, cudaStream_t st) {
   constexpr int kNeeded = STAGES * (4 * kThreads * BITS) + 2 * STAGES * 8;
   auto kern = streamx_kernel<BITS, COUNT, DIFF, DECODED, STAGES>;
@@ -1099,6 +1185,7 @@ int launch_streamx(StreamParams p, int ctas_cap, cudaStream_t st) {
   int64_t grid = (total_work + p.items_per_cta - 1) / p.items_per_cta;
   static const bool sync_units = getenv("FF_STREAMX_SYNC") == nullptr || atoi(getenv("FF_STREAMX_SYNC")) != 0;   // tuning knob
   p.unit_frames = 0;
+  p.neg_one = 0xFFFFFFFFu;
   if (DIFF && sync_units && p.n_frames >= 96) {
     // frames per unit: long enough that the extra halo item per unit stays below ~2 %, and such that the
     // units divide evenly over the wave (every CTA the same number of units)
@@ -1122,15 +1209,20 @@ int launch_streamx(StreamParams p, int ctas_cap, cudaStream_t st) {
   return launch_kernel(kern, dim3((unsigned)grid), dim3(kOutThreads), smem, st, p.pdl != 0, p);
 }
 
-template <int BITS, bool COUNT, bool DIFF, bool DECODED>
+template <int BITS, bool COUNT, int DIFF, bool DECODED>
 int launch_streamx_tuned(const StreamParams& p, cudaStream_t st) {
   // One CTA per SM with a 5-deep ring (48 KB of reads in flight per SM at 12 bits) is the measured
   // optimum for the read+write variants - fewer concurrent DRAM streams beat more parallelism (C4
   // uint16 diff: 0.85 of the copy rate at 3 CTAs x 4 stages, 0.92 at 1 x 5;
   // profiles/r01_stream12_sweep.txt).
-  static const int stages = getenv("FF_STREAM12_STAGES") ? atoi(getenv("FF_STREAM12_STAGES")) : 5;   // tuning knobs
+  // The ring depth is tuned per variant (profiles/r02_streamx_stage_sweep.txt; one stage more or less costs 3-10 %):
+  // the more of the traffic is writes, the fewer reads want to be in flight.
+  constexpr int kDefaultStages = DIFF == FF_DIFF_F32 ? 3 : DIFF == FF_DIFF_F64 ? 2
+                                 : DIFF == FF_DIFF_U16 ? (BITS == 16 ? 4 : 5) : 4;
+  static const int stages = getenv("FF_STREAM12_STAGES") ? atoi(getenv("FF_STREAM12_STAGES")) : kDefaultStages;   // tuning knobs
   static const int ctas = getenv("FF_STREAM12_CTAS") ? atoi(getenv("FF_STREAM12_CTAS")) : 1;
   switch (stages) {
+    case 2: return launch_streamx<BITS, COUNT, DIFF, DECODED, 2>(p, ctas, st);
     case 3: return launch_streamx<BITS, COUNT, DIFF, DECODED, 3>(p, ctas, st);
     case 4: return launch_streamx<BITS, COUNT, DIFF, DECODED, 4>(p, ctas, st);
     case 6: return launch_streamx<BITS, COUNT, DIFF, DECODED, 6>(p, ctas, st);
@@ -1325,6 +1417,7 @@ int range_fused_impl(const DetectParams& d, int bits, int32_t empty_thr, bool pd
   p.diff_thr = d.diff_thr;
   p.skip = d.skip;
   p.pdl = pdl ? 1 : 0;
+  p.neg_one = 0xFFFFFFFFu;
   // Ring geometry, measured (profiles/r02_range_item_sweep.txt; GB/s of algorithmic bytes at C2):
   //   12-bit  12 KiB x 4 stages 6870   24 KiB x 3 stages 6700        -> 12 KiB (72 KiB in flight per SM)
   //   16-bit  12 KiB x 4        7140   24 KiB x 3        6820        -> 12 KiB
@@ -1378,6 +1471,7 @@ int stream_frames_impl(const void* frames, const void* halo, int64_t n_frames, i
   p.diff_out = diff_out;
   p.decoded_out = decoded_out;
   p.pdl = pdl ? 1 : 0;
+  p.neg_one = 0xFFFFFFFFu;
 
   const bool aligned = ((reinterpret_cast<uintptr_t>(frames) | reinterpret_cast<uintptr_t>(halo) |
                          reinterpret_cast<uintptr_t>(diff_out) | reinterpret_cast<uintptr_t>(decoded_out)) & 15u) == 0;
@@ -1401,6 +1495,18 @@ int stream_frames_impl(const void* frames, const void* halo, int64_t n_frames, i
       if (!dec) return bits == 16 ? launch_streamx_tuned<16, true, true, false>(p, st)
                                   : launch_streamx_tuned<8, true, true, false>(p, st);
     }
+    // float32 / float64 difference images: the same 16x2 arithmetic, lanes widened on the way out.
+    // FF_STREAMX_F32=0 / FF_STREAMX_F64=0 select the general template (pixel pair per lane, scalar arithmetic).
+    static const int f32_mode = getenv("FF_STREAMX_F32") ? atoi(getenv("FF_STREAMX_F32")) : 1;     // tuning knobs
+    if (t.k == 4 && diff_dtype == FF_DIFF_F32 && decoded_out == nullptr && f32_mode != 0)
+      return bits == 12 ? launch_streamx_tuned<12, true, FF_DIFF_F32, false>(p, st)
+                        : (bits == 16 ? launch_streamx_tuned<16, true, FF_DIFF_F32, false>(p, st)
+                                      : launch_streamx_tuned<8, true, FF_DIFF_F32, false>(p, st));
+    static const int f64_mode = getenv("FF_STREAMX_F64") ? atoi(getenv("FF_STREAMX_F64")) : 1;     // tuning knob
+    if (t.k == 4 && diff_dtype == FF_DIFF_F64 && decoded_out == nullptr && f64_mode != 0)
+      return bits == 12 ? launch_streamx_tuned<12, true, FF_DIFF_F64, false>(p, st)
+                        : (bits == 16 ? launch_streamx_tuned<16, true, FF_DIFF_F64, false>(p, st)
+                                      : launch_streamx_tuned<8, true, FF_DIFF_F64, false>(p, st));
     if (t.k == 4 && bits == 12 && diff_dtype == FF_DIFF_NONE)        // counts + decoded (counts alone: count12)
       return launch_streamx_tuned<12, true, false, true>(p, st);
     switch (bits) {

@@ -278,6 +278,49 @@ def test_big_tile_kernels_with_skips_halo_and_ragged_tiles(engine):
         assert np.array_equal(r.diff.cpu().numpy().astype(np.float64), w_.diffs), bits
 
 
+@pytest.mark.parametrize("dtype,np_dtype", [("float32", np.float32), ("float64", np.float64)])
+def test_big_tile_float_difference(engine, dtype, np_dtype):
+    """float32 / float64 difference image at the 8192-pixel tile size without a decoded output (streamx_kernel's float path:
+    16x2 arithmetic, lanes widened on the way out, lane pairs swapping halves before the stores): ragged last tile,
+    skip_frames, a sub-range whose halo is an earlier frame, zero threshold, 12-, 16- and 8-bit storage."""
+    frames = small_clip(w=1024, h=130, n=23, seed=43, style="mini")
+    n = len(frames)
+    skip = [3, 4, 9, 22]
+    mask = np.zeros(n, dtype=np.uint8)
+    mask[skip] = 1
+    live = mask == 0
+    want = fo.process_clip(frames, fo.ClipParams(method="threshold", skip_frames=skip, keep_diffs=True))
+    res, _ = run_range(engine, frames, 12, DetectionParams(method="threshold"), skip=dev(mask, engine),
+                       diff_dtype=dtype)
+    got = res.diff.cpu().numpy()
+    assert got.dtype == np_dtype and np.array_equal(got.astype(np.float64), want.diffs)
+    assert np.array_equal(res.counts.cpu().numpy()[live], want.nonempty.astype(np.int32)[live])
+    assert np.array_equal(res.pos.cpu().numpy(), oracle_pos(want))
+    a = 10
+    halo = dev(syn.pack_frames(frames[8:9], 12), engine)
+    sub, _ = run_range(engine, frames[a:], 12, DetectionParams(method="threshold"), frame0=frames[0], first_frame=a,
+                       halo=halo, skip=dev(mask[a:], engine), diff_dtype=dtype, truncate=False)
+    assert np.array_equal(sub.diff.cpu().numpy().astype(np.float64), want.diffs[a:])
+    z, _ = run_range(engine, frames[:6], 12, DetectionParams(method="gradient", frame_diff_threshold=0.0),
+                     diff_dtype=dtype)
+    wz = fo.process_clip(frames[:6], fo.ClipParams(method="gradient", frame_diff_threshold=0.0, keep_diffs=True))
+    assert np.array_equal(z.diff.cpu().numpy().astype(np.float64), wz.diffs)
+    for bits in (16, 8):
+        fr = small_clip(bits=bits, w=1024, h=130, n=7, seed=bits + 1, style="mini")
+        r, _ = run_range(engine, fr, bits, DetectionParams(method="gradient"), diff_dtype=dtype)
+        w_ = fo.process_clip(fr, fo.ClipParams(method="gradient", keep_diffs=True))
+        assert np.array_equal(r.counts.cpu().numpy(), w_.nonempty.astype(np.int32)), bits
+        assert np.array_equal(r.pos.cpu().numpy(), oracle_pos(w_)), bits
+        assert np.array_equal(r.diff.cpu().numpy().astype(np.float64), w_.diffs), bits
+    # a long clip (frame-synchronous units with their halo items; >= 96 frames) of full tiles
+    long = small_clip(w=1024, h=128, n=130, seed=7, style="nova")
+    wl = fo.process_clip(long, fo.ClipParams(method="half_maximum", keep_diffs=True))
+    for dt in (dtype, "uint16"):
+        rl, _ = run_range(engine, long, 12, DetectionParams(method="half_maximum"), diff_dtype=dt)
+        assert np.array_equal(rl.diff.cpu().numpy().astype(np.float64), wl.diffs), dt
+        assert np.array_equal(rl.pos.cpu().numpy(), oracle_pos(wl)), dt
+
+
 def test_empty_and_degenerate_inputs(engine):
     # all-dark clip: every frame empty, nothing detected, no exit
     dark = np.full((10, 8, 64), 40, dtype=np.uint16)

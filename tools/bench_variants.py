@@ -94,6 +94,9 @@ def main() -> None:
         ("C2/16", "half_maximum", None, False),    # same clip stored as 16-bit little-endian MRAW
         ("C2/8", "half_maximum", None, False),     # ... and as 8-bit
         ("C4/16", "gradient", "uint16", False),
+        ("C4/16", "gradient", "float32", False),
+        ("C4/8", "gradient", "uint16", False),
+        ("C4/8", "gradient", "float32", False),
         ("C3", "unpack", None, False),            # stage 1 alone: ff_unpack, packed 12-bit -> uint16
         ("C2", "head", None, False),              # the detector the reference runs at HEAD
         ("C4", "head", None, False),

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Turn an `ncu --set full` report of the range kernel into profiles/range_kernel_traffic.json, stamped with the
-SHA-256 of the libflamefront.so it was captured on (bench.py reports `roofline.traffic` only when the stamp matches
-the library that is loaded).
+fingerprint of the sources the libflamefront.so it was captured on was built from (bench.py reports
+`roofline.traffic` only when the loaded library was built from the same sources; nvcc's output itself is not
+byte-reproducible).
 
     # on the GPU box (gpurun):
     ncu --set full --clock-control none --import-source on -k regex:range_kernel -c 1 -o gpurun_out/range_c2 \\
@@ -12,7 +13,6 @@ the library that is loaded).
 from __future__ import annotations
 
 import csv
-import hashlib
 import io
 import json
 import subprocess
@@ -21,7 +21,8 @@ import time
 from pathlib import Path
 
 REPO = Path(__file__).resolve().parent.parent
-LIB = REPO / "high_speed_image_processing_b200" / "lib" / "libflamefront.so"
+sys.path.insert(0, str(REPO))
+from high_speed_image_processing_b200 import build as ffbuild  # noqa: E402
 
 
 def main() -> None:
@@ -47,7 +48,7 @@ def main() -> None:
         m.get("dram__throughput.avg.pct_of_peak_sustained_elapsed", ("", ""))[0] else None,
         "registers_per_thread": int(float(m["launch__registers_per_thread"][0])),
         "grid": m.get("launch__grid_size", ("?", ""))[0], "block": m.get("launch__block_size", ("?", ""))[0],
-        "lib_sha256": hashlib.sha256(LIB.read_bytes()).hexdigest(),
+        "source_fingerprint": ffbuild.built_fingerprint(),
         "captured": time.strftime("%Y-%m-%d"), "report": rep.name,
         "how": "ncu --set full --clock-control none, one launch of the C2 range kernel (20000 frames 1024x128, packed 12-bit)",
     }
