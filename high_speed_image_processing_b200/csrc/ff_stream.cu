@@ -360,8 +360,15 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const StreamParams p) 
 constexpr int kCountThreads = kThreads + 32;              // 8 consumer warps + 1 producer warp
 constexpr int kCountCtasPerSm = 2;
 
+#ifndef FF_COUNT_FMA_ADDS
+#define FF_COUNT_FMA_ADDS 1
+#endif
+// acc + the number of the 8 packed-12 pixels in (w0, w1, w2) above the threshold, per 16-bit lane.  With
+// FF_COUNT_FMA_ADDS (default) the four flag words are added as x * one + acc (one = 1 at run time: IMADs on the
+// otherwise idle FMA pipe instead of two 3-input adds on the ALU pipe, which ncu shows 70 % busy; measured
+// C3 1.1053 -> 1.1014 ms, C2 0.5649 -> 0.5644 ms; -DFF_COUNT_FMA_ADDS=0 builds the 3-input adds).
 __device__ __forceinline__ uint32_t count12x8_simd(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t kA2,
-                                                   uint32_t nkA2, uint32_t nc2) {
+                                                   uint32_t nkA2, uint32_t nc2, uint32_t acc = 0, uint32_t one = 1) {
   const uint32_t one2 = 0x00010001u;
   const uint32_t a0 = __byte_perm(w0, w1, 0x3401);                 // b1 b0 | b4 b3   (LSB first)
   const uint32_t a1 = __byte_perm(w1, w2, 0x5623);                 // b7 b6 | b10 b9
@@ -372,7 +379,16 @@ __device__ __forceinline__ uint32_t count12x8_simd(uint32_t w0, uint32_t w1, uin
   const uint32_t fa1 = __viaddmin_u16x2(__vimax3_u16x2(a1, kA2, kA2), nkA2, one2);
   const uint32_t fb0 = __viaddmin_s16x2_relu(b0, nc2, one2);
   const uint32_t fb1 = __viaddmin_s16x2_relu(b1, nc2, one2);
-  return (fa0 + fa1) + (fb0 + fb1);
+#if FF_COUNT_FMA_ADDS
+  // (inline PTX: written in C the compiler factors `one` out and is back to 3-input adds)
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(fa0), "r"(one));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(fa1), "r"(one));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(fb0), "r"(one));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(fb1), "r"(one));
+  return acc;
+#else
+  return acc + (fa0 + fa1) + (fb0 + fb1);
+#endif
 }
 
 template <int BITS, int kCountStages>
@@ -435,19 +451,26 @@ __global__ void __launch_bounds__(kCountThreads) count12_kernel(const StreamPara
   const uint32_t kA2 = kA * 0x00010001u;
   const uint32_t nkA2 = ((0x10000u - kA) & 0xFFFFu) * 0x00010001u;
   const uint32_t nc2 = ((0x10000u - c) & 0xFFFFu) * 0x00010001u;
+  const uint32_t one_rt = p.neg_one * p.neg_one;       // 1, unknown to the compiler (FF_COUNT_FMA_ADDS)
   const int my_group = tid * 4;
+  // running values instead of a modulo, a 64-bit min and a 64-bit index product per item (see range_kernel)
+  const int last_groups = (int)(groups_per_frame - (int64_t)(p.tiles_per_frame - 1) * (4 * kThreads));
+  int32_t* out = p.partial + ((int64_t)f * p.tiles_per_frame + tile) * kWarpsPerCta + warp;
+  int s = 0;
+  uint32_t ph = 0;
 
   for (int it = 0; it < n_items; ++it) {
-    const int s = it % kCountStages;
-    mbar_wait(&full[s], (it / kCountStages) & 1);
-    const int tile_groups = (int)min((int64_t)(4 * kThreads), groups_per_frame - (int64_t)tile * (4 * kThreads));
+    mbar_wait(&full[s], ph);
+    const int tile_groups = tile + 1 == p.tiles_per_frame ? last_groups : 4 * kThreads;
     uint32_t acc = 0;
     if (BITS == 12) {
       if (my_group < tile_groups) {        // groups per frame are a multiple of 4: all four or none
         const uint4* q = reinterpret_cast<const uint4*>(smem + s * kTileBytes + tid * 48);
         const uint4 q0 = q[0], q1 = q[1], q2 = q[2];
-        acc = count12x8_simd(q0.x, q0.y, q0.z, kA2, nkA2, nc2) + count12x8_simd(q0.w, q1.x, q1.y, kA2, nkA2, nc2) +
-              count12x8_simd(q1.z, q1.w, q2.x, kA2, nkA2, nc2) + count12x8_simd(q2.y, q2.z, q2.w, kA2, nkA2, nc2);
+        acc = count12x8_simd(q0.x, q0.y, q0.z, kA2, nkA2, nc2, acc, one_rt);
+        acc = count12x8_simd(q0.w, q1.x, q1.y, kA2, nkA2, nc2, acc, one_rt);
+        acc = count12x8_simd(q1.z, q1.w, q2.x, kA2, nkA2, nc2, acc, one_rt);
+        acc = count12x8_simd(q2.y, q2.z, q2.w, kA2, nkA2, nc2, acc, one_rt);
       }
     } else {
       const uint32_t one2 = 0x00010001u;
@@ -475,9 +498,14 @@ __global__ void __launch_bounds__(kCountThreads) count12_kernel(const StreamPara
     cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);      // also orders every lane's smem reads before the release
     if ((tid & 31) == 0) {
       mbar_arrive(&empty[s]);
-      p.partial[((int64_t)f * p.tiles_per_frame + tile) * kWarpsPerCta + warp] = cnt;
+      *out = cnt;
     }
+    out += kWarpsPerCta;                            // frame-major items: (f, tile) -> the next eight counts
     advance();
+    if (++s == kCountStages) {
+      s = 0;
+      ph ^= 1u;
+    }
   }
 }
 
@@ -713,22 +741,29 @@ __global__ void __launch_bounds__(kFusedThreads) range_kernel(const StreamParams
   const uint32_t kA2 = kA * 0x00010001u;
   const uint32_t nkA2 = ((0x10000u - kA) & 0xFFFFu) * 0x00010001u;
   const uint32_t nc2 = ((0x10000u - c) & 0xFFFFu) * 0x00010001u;
+  const uint32_t one_rt = p.neg_one * p.neg_one;       // 1, unknown to the compiler (FF_COUNT_FMA_ADDS)
 
-  uint32_t it = 0;
+  // The item loop is counted in ALU instructions (ncu: ALU pipe 70 % busy at 85 % of the DRAM pin rate; a third of
+  // them were the item header): 32-bit trip count, ring slot and phase as running values, the ragged last tile
+  // from a compare.
   unsigned seg_no = 0;                   // segments this warp has finished (the same sequence in every warp)
   int fs = f0, ts = tile0;
+  int s = 0;                             // ring slot and its phase
+  uint32_t ph = 0;
+  const int last_groups = (int)(groups_per_frame - (int64_t)(T - 1) * kTileGroups);
   for (int64_t slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
-    const int64_t i0 = slab << sh, i1 = min(i0 + S, total_work);
+    const int64_t i0 = slab << sh;
+    const int n_it = (int)(min(i0 + S, total_work) - i0);
     int f = fs;
     int tile = ts;
     fs += p.slab_step_frames;
     ts += p.slab_step_tiles;
     if (ts >= T) { ts -= T; ++fs; }
     int wcnt = 0;
-    for (int64_t i = i0; i < i1; ++i, ++it) {
-      const int s = it % kCountStages;
-      mbar_wait(&full[s], (it / kCountStages) & 1);
-      const int tile_groups = (int)min((int64_t)kTileGroups, groups_per_frame - (int64_t)tile * kTileGroups);
+    for (int k_it = 0; k_it < n_it; ++k_it) {
+      mbar_wait(&full[s], ph);
+      const bool last_of_frame = tile + 1 == T;
+      const int tile_groups = last_of_frame ? last_groups : kTileGroups;
       uint32_t acc = 0;
       if (BITS == 12) {
 #pragma unroll
@@ -737,8 +772,10 @@ __global__ void __launch_bounds__(kFusedThreads) range_kernel(const StreamParams
           if (g < tile_groups) {
             const uint4* qq = reinterpret_cast<const uint4*>(smem + s * kTileBytes + (c4 * kThreads + tid) * 48);
             const uint4 q0 = qq[0], q1 = qq[1], q2 = qq[2];
-            acc += count12x8_simd(q0.x, q0.y, q0.z, kA2, nkA2, nc2) + count12x8_simd(q0.w, q1.x, q1.y, kA2, nkA2, nc2) +
-                   count12x8_simd(q1.z, q1.w, q2.x, kA2, nkA2, nc2) + count12x8_simd(q2.y, q2.z, q2.w, kA2, nkA2, nc2);
+            acc = count12x8_simd(q0.x, q0.y, q0.z, kA2, nkA2, nc2, acc, one_rt);
+            acc = count12x8_simd(q0.w, q1.x, q1.y, kA2, nkA2, nc2, acc, one_rt);
+            acc = count12x8_simd(q1.z, q1.w, q2.x, kA2, nkA2, nc2, acc, one_rt);
+            acc = count12x8_simd(q2.y, q2.z, q2.w, kA2, nkA2, nc2, acc, one_rt);
           }
         }
       } else {
@@ -765,11 +802,10 @@ __global__ void __launch_bounds__(kFusedThreads) range_kernel(const StreamParams
       }
       int cnt = (int)(acc & 0xFFFFu) + (int)(acc >> 16);
       cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);      // also orders every lane's smem reads before the release
-      const bool last_of_frame = tile + 1 == T;
       if (lane == 0) {
         mbar_arrive(&empty[s]);
         wcnt += cnt;
-        if (last_of_frame || i + 1 == i1) {           // the segment ends: leaving the frame, or the slab
+        if (last_of_frame || k_it + 1 == n_it) {      // the segment ends: leaving the frame, or the slab
           unsigned* word = seg + (seg_no & (kSegRing - 1));
           ++seg_no;
           const unsigned old = atomicAdd(word, (1u << 24) | (unsigned)wcnt);
@@ -786,6 +822,10 @@ __global__ void __launch_bounds__(kFusedThreads) range_kernel(const StreamParams
         }
       }
       if (last_of_frame) { tile = 0; ++f; } else { ++tile; }
+      if (++s == kCountStages) {
+        s = 0;
+        ph ^= 1u;
+      }
     }
   }
   if (lane == 0) {

@@ -394,10 +394,19 @@ def _process_video_head(video: PhotonVideo, config: VideoSourceConfig, calibrati
     frame0 = eng.upload(video.raw_frames(0, 1))
     start = (FF_NO_EXIT, -1, -1)
     multi = exchange is not None and exchange.size > 1
+    summary = None
     if not multi:
-        # the host-side stop rules (exit, velocity drop: :1486-1509) end the uploads as well
+        # the host-side stop rules (exit, velocity drop: :1486-1509) end the uploads as well; the bookkeeping of
+        # the last look is the clip's (frames behind it were never walked: flags 0), so it is not repeated below
+        last_look = []
+
+        def stopped(t, f) -> bool:
+            last_look[:] = [finish(t, f)]
+            return last_look[0].stop is not None
+
         track, flags, _, pending = _head_walk_range(eng, video, hp, calibration, 0, n, skip_np, frame0, start,
-                                                    stopped=lambda t, f: finish(t, f).stop is not None)
+                                                    stopped=stopped)
+        summary = last_look[0] if last_look else None
     else:
         a, b = exchange.my_range(n)
         rank, size, group = exchange.rank, exchange.size, exchange.group
@@ -444,7 +453,8 @@ def _process_video_head(video: PhotonVideo, config: VideoSourceConfig, calibrati
         if pending is None:              # this rank uploaded nothing: it still reports the clip's scalars
             _, _, pending = eng.head_lines(frame0, 1, h, w, bits, hp)
     scalars = eng.head_scalars(pending)
-    summary = finish(track, flags)
+    if summary is None:
+        summary = finish(track, flags)
     pos = np.full(n, -1, dtype=np.int32)
     for frame_idx, _, px, _, _ in summary.rows:
         pos[frame_idx] = px
