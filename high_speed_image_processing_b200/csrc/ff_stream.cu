@@ -260,9 +260,9 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const StreamParams p) 
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if (COUNT) acc2 += __viaddmin_s16x2_relu(x[j], s_ncthr, dup);           // [x > cthr] per lane
-            const uint32_t sub2 = __viaddmax_s16x2(x[j], s_nbg, 0u);                // max(x - bg, 0)
+            const uint32_t sub2 = __viaddmax_s16x2_relu(x[j], s_nbg, 0x80008000u);  // max(x - bg, 0) (see kLaneMin2)
             const uint32_t e2 = __viaddmax_s16x2(sub2, prev[k][j], 0x80008000u);    // sub + ~prev = d - 1
-            const uint32_t r2 = __viaddmax_s16x2_relu(e2, s_k, 0u);                 // relu(d - (thr-1))
+            const uint32_t r2 = __viaddmax_s16x2_relu(e2, s_k, 0x80008000u);        // relu(d - (thr-1))
             const uint32_t m2 = __vimin_s16x2_relu(r2, dup);                         // [d >= thr]
             o[j] = diff_valid ? r2 + m2 * (uint32_t)tm1 : 0u;                       // d where d >= thr, else 0
             if (!skipped) prev[k][j] = ~sub2;
