@@ -78,11 +78,12 @@ __device__ __forceinline__ void owner_of(int64_t i, int64_t base, int64_t extra,
 // CTAs per SM leave ~5 K registers free - a CTA that does not fit there would wait for a range CTA to leave
 // and, worse, a spinning merge CTA that got in first would keep a range CTA out (measured at N=2 with
 // 256-thread CTAs: +90 us per step).
+// (64 registers by launch bound: 2 warps x 2048 registers fit the 5.6 K the range kernel leaves free.)
 constexpr int kMergeThreads = 64;
 static_assert(kMergeThreads >= kMaxRanks, "one thread per rank polls a flag");
 
 template <bool PEER>
-__global__ void __launch_bounds__(kMergeThreads) merge_ranges_kernel(const MergeParams p) {
+__global__ void __launch_bounds__(kMergeThreads, 16) merge_ranges_kernel(const MergeParams p) {
   __shared__ int s_fe;
   __shared__ int s_ok;
   const int tid = threadIdx.x;
@@ -120,21 +121,37 @@ __global__ void __launch_bounds__(kMergeThreads) merge_ranges_kernel(const Merge
   if (blockIdx.x == 0 && tid == 0) *p.first_exit_out = s_fe;
 
   const int64_t base = p.total / p.world, extra = p.total % p.world;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < p.total; i += (int64_t)gridDim.x * blockDim.x) {
-    if (!ok) {               // a peer never arrived: defined outputs, the status word tells
-      p.pos_out[i] = FF_POS_NONE;
-      if (p.count_out != nullptr) p.count_out[i] = 0;
-      continue;
+  // Four elements per thread and round, all loads issued before the first store: the peers' blocks are read over
+  // NVLink - or over PCIe where a box gives its GPUs no NVLink path - and a thread that waits for one remote load at a
+  // time makes the merge a chain of round trips (measured on such a box at N = 2: merges of ~0.7 ms, longer than the
+  // step they are meant to hide behind).
+  constexpr int kUnroll = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + tid; i0 < p.total; i0 += kUnroll * stride) {
+    int32_t v[kUnroll], c[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t i = i0 + u * stride;
+      v[u] = FF_POS_NONE;
+      c[u] = 0;
+      if (i < p.total && ok) {        // (a peer that never arrived: defined outputs, the status word tells)
+        int r;
+        int64_t off;
+        owner_of(i, base, extra, r, off);
+        const int32_t* b = PEER ? t->base[r] + p.slot_off : p.gathered + (int64_t)r * p.stride;
+        const int32_t* src_pos = b + kHdr + off;
+        v[u] = PEER ? __ldcv(src_pos) : *src_pos;
+        if (p.count_out != nullptr) c[u] = PEER ? __ldcv(src_pos + p.cap) : src_pos[p.cap];
+      }
     }
-    int r;
-    int64_t off;
-    owner_of(i, base, extra, r, off);
-    const int32_t* b = PEER ? t->base[r] + p.slot_off : p.gathered + (int64_t)r * p.stride;
-    const int32_t* src_pos = b + kHdr + off;
-    const int32_t* src_cnt = b + kHdr + p.cap + off;
-    const int32_t v = PEER ? __ldcv(src_pos) : *src_pos;
-    p.pos_out[i] = i >= fe ? FF_POS_DROPPED : v;
-    if (p.count_out != nullptr) p.count_out[i] = PEER ? __ldcv(src_cnt) : *src_cnt;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < p.total) {
+        p.pos_out[i] = (ok && i >= fe) ? FF_POS_DROPPED : v[u];
+        if (p.count_out != nullptr) p.count_out[i] = c[u];
+      }
+    }
   }
   if (PEER) {
     // last CTA: nobody writes this epoch's exit word any more (every rank has published) - reset it
