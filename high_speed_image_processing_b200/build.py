@@ -149,10 +149,9 @@ def sass_summary(out_path=None) -> str:
         res = subprocess.run([filt], input="\n".join(names), stdout=subprocess.PIPE, text=True)
         if res.returncode == 0:
             pretty = dict(zip(names, res.stdout.splitlines()))
-    import hashlib
     cols = [k for k, _, _ in SASS_MNEMONICS]
     lines = ["# SASS summary of libflamefront.so (round 2)", "",
-             f"`cuobjdump -sass` of `{LIB_PATH.relative_to(PKG_DIR.parent)}` (sha256 `{hashlib.sha256(LIB_PATH.read_bytes()).hexdigest()[:16]}`), "
+             f"`cuobjdump -sass` of `{LIB_PATH.relative_to(PKG_DIR.parent)}` (built from sources `{built_fingerprint()[:16]}`), "
              f"{len(kernels)} kernels, architectures: {', '.join(sorted(arch)) or '?'}.  Regenerate with "
              "`python -m high_speed_image_processing_b200.build --force --verbose`.", "",
              "| kernel | instr | " + " | ".join(cols) + " |", "|---|---|" + "---|" * len(cols)]
