@@ -622,20 +622,22 @@ def leg_c2(cx: Ctx, line: dict) -> None:
 
 def measured_traffic():
     """DRAM bytes per launch of the range kernel from the round's `ncu --set full` capture, only if that capture
-    was taken on a library built from the sources the loaded one was built from (`build.source_fingerprint`: nvcc's
-    output is not byte-reproducible, so the binary's own hash would change with every rebuild); else null."""
+    was taken on a library whose ff_stream.cu (where range_kernel lives) was compiled from the same source, headers
+    and flags as the loaded one (`build.unit_fingerprint`: nvcc's output is not byte-reproducible, so the binary's
+    own hash would change with every rebuild); else null."""
     tpath = REPO / "profiles" / "range_kernel_traffic.json"
     if not tpath.exists():
         return None, "no capture committed"
     rec = json.loads(tpath.read_text())
     from high_speed_image_processing_b200 import build as ffbuild
-    built, now = ffbuild.built_fingerprint(), ffbuild.source_fingerprint()
+    unit = rec.get("unit", "ff_stream.cu")
+    built, now = ffbuild.built_unit_fingerprint(unit), ffbuild.unit_fingerprint(unit)
     if not built or built != now:
         return None, "the loaded libflamefront.so was not built from the sources in the tree"
-    if rec.get("source_fingerprint") != built:
+    if rec.get("unit_fingerprint") != built:
         return None, (f"profiles/range_kernel_traffic.json was captured on a build of other sources "
-                      f"({str(rec.get('source_fingerprint', '?'))[:12]})")
-    return rec.get("dram_bytes_per_launch"), f"ncu --set full, {rec.get('captured', '?')}, library built from the same sources"
+                      f"({str(rec.get('unit_fingerprint', '?'))[:12]})")
+    return rec.get("dram_bytes_per_launch"), f"ncu --set full, {rec.get('captured', '?')}, {unit} built from the same sources"
 
 
 class _HostClip:

@@ -40,22 +40,43 @@ def find_nvcc() -> str:
 STAMP_PATH = LIB_DIR / "libflamefront.so.sources"
 
 
-def source_fingerprint() -> str:
-    """SHA-256 over everything the library is compiled from (sources, headers, nvcc flags).  nvcc's output is not
-    byte-reproducible (the mangled names of anonymous namespaces differ from run to run), so measurements that
-    belong to one build - profiles/range_kernel_traffic.json - are stamped with this instead of a hash of the
-    binary; build() records next to the .so which sources it was made from."""
+def unit_fingerprint(src: str) -> str:
+    """SHA-256 over one translation unit: its source, the headers and the nvcc flags - what decides the SASS of the
+    kernels defined in it.  Measurements of one kernel (profiles/range_kernel_traffic.json: range_kernel lives in
+    ff_stream.cu) are stamped with this, so that a change to another kernel's file does not orphan them."""
     import hashlib
     h = hashlib.sha256()
-    for f in sorted([CSRC / s for s in SOURCES] + HEADERS, key=lambda q: q.name):
+    for f in [CSRC / src] + sorted(HEADERS, key=lambda q: q.name):
         h.update(f.name.encode() + b"\0" + f.read_bytes() + b"\0")
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
 
+def source_fingerprint() -> str:
+    """SHA-256 over everything the library is compiled from (every unit_fingerprint).  nvcc's output is not
+    byte-reproducible (the mangled names of anonymous namespaces differ from run to run), so a build is identified
+    by this instead of a hash of the binary; build() records next to the .so which sources it was made from."""
+    import hashlib
+    return hashlib.sha256("".join(unit_fingerprint(s) for s in SOURCES).encode()).hexdigest()
+
+
+def _stamp() -> dict:
+    import json
+    if not (STAMP_PATH.exists() and LIB_PATH.exists()):
+        return {}
+    try:
+        return json.loads(STAMP_PATH.read_text())
+    except ValueError:
+        return {}
+
+
 def built_fingerprint() -> str:
     """The fingerprint of the sources the library on disk was built from ('' if unknown)."""
-    return STAMP_PATH.read_text().strip() if STAMP_PATH.exists() and LIB_PATH.exists() else ""
+    return _stamp().get("all", "")
+
+
+def built_unit_fingerprint(src: str) -> str:
+    return _stamp().get("units", {}).get(src, "")
 
 
 def is_stale() -> bool:
@@ -70,7 +91,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not is_stale():
         return LIB_PATH
     LIB_DIR.mkdir(parents=True, exist_ok=True)
-    fingerprint = source_fingerprint()          # before compiling: what the compiler is about to read
+    import json
+    # before compiling: what the compiler is about to read
+    fingerprint = json.dumps({"all": source_fingerprint(), "units": {s: unit_fingerprint(s) for s in SOURCES}}, indent=1)
     nvcc = find_nvcc()
     objs = []
     procs = []

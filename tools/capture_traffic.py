@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Turn an `ncu --set full` report of the range kernel into profiles/range_kernel_traffic.json, stamped with the
-fingerprint of the sources the libflamefront.so it was captured on was built from (bench.py reports
-`roofline.traffic` only when the loaded library was built from the same sources; nvcc's output itself is not
-byte-reproducible).
+fingerprint of the translation unit (ff_stream.cu + headers + nvcc flags) the range kernel of the libflamefront.so it
+was captured on was compiled from (bench.py reports `roofline.traffic` only when the loaded library's unit was built
+from the same sources; nvcc's output itself is not byte-reproducible).
 
     # on the GPU box (gpurun):
     ncu --set full --clock-control none --import-source on -k regex:range_kernel -c 1 -o gpurun_out/range_c2 \\
@@ -48,7 +48,7 @@ def main() -> None:
         m.get("dram__throughput.avg.pct_of_peak_sustained_elapsed", ("", ""))[0] else None,
         "registers_per_thread": int(float(m["launch__registers_per_thread"][0])),
         "grid": m.get("launch__grid_size", ("?", ""))[0], "block": m.get("launch__block_size", ("?", ""))[0],
-        "source_fingerprint": ffbuild.built_fingerprint(),
+        "unit": "ff_stream.cu", "unit_fingerprint": ffbuild.built_unit_fingerprint("ff_stream.cu"),
         "captured": time.strftime("%Y-%m-%d"), "report": rep.name,
         "how": "ncu --set full --clock-control none, one launch of the C2 range kernel (20000 frames 1024x128, packed 12-bit)",
     }
