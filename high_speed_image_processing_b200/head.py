@@ -136,9 +136,9 @@ def finish_head_track(track: np.ndarray, flags: np.ndarray, first_frame: int, wi
     out = HeadTrackSummary()
     book = VelocityBook(frame_rate, calibration, params.ddt_velocity_jump_m_s)
     vel = out.velocity_history = book.velocities
-    for i in np.nonzero(flags)[0].tolist():
+    active = np.nonzero(flags)[0]
+    for i, (final, pos_a, pos_b, s0, s1) in zip(active.tolist(), track[active].tolist()):   # Python ints, one conversion
         frame_idx = first_frame + i
-        final, pos_a, pos_b, s0, s1 = (int(v) for v in track[i])
         if s0 < 0 and s1 < 0 and final < 0 and pos_a < 0:
             break                                   # the device tracker stopped before this frame
         final_position = final if final >= 0 else None
