@@ -262,6 +262,11 @@ def reference_arm(args) -> None:
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if head:          # (the default workload keeps the b200 arm's config verbatim; this one names what it ran)
+        line["config"].update(
+            workload="C2 clip (Nova-style synthetic 1024x128, packed 12-bit MRAW) through the detector the reference "
+                     "executes at HEAD: FlameDetector (3x3 opening, Gaussian, Sobel / gradient, windowed tracker)",
+            detection_method="head (FlameDetector)")
     print(json.dumps(line), flush=True)
 
 
