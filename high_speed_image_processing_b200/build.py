@@ -80,11 +80,17 @@ def built_unit_fingerprint(src: str) -> str:
 
 
 def is_stale() -> bool:
+    """True when the library on disk was not built from the sources in the tree: by the recorded fingerprint (copies
+    of the tree - the snapshot on the GPU box - do not keep modification times), by modification time only for a
+    library without a stamp."""
     if not LIB_PATH.exists():
         return True
-    built = LIB_PATH.stat().st_mtime
+    built = built_fingerprint()
+    if built:
+        return built != source_fingerprint()
+    mtime = LIB_PATH.stat().st_mtime
     deps = [CSRC / s for s in SOURCES] + HEADERS + [Path(__file__)]
-    return any(d.stat().st_mtime > built for d in deps) or built_fingerprint() != source_fingerprint()
+    return any(d.stat().st_mtime > mtime for d in deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:

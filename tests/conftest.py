@@ -14,6 +14,15 @@ GOLDEN = REPO / "tests" / "golden"
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # The suite tests the built library (symbols, structs, stamp; every GPU test calls through it): build it here if
+    # the tree holds none or a stale one and nvcc is around (it cross-compiles without a GPU).  No nvcc, no build -
+    # the tests that need the library then fail loudly, as the product does.
+    from high_speed_image_processing_b200 import build as ffbuild
+    try:
+        if ffbuild.is_stale():
+            ffbuild.build()
+    except RuntimeError as exc:
+        print(f"[conftest] libflamefront.so not rebuilt: {exc}", file=sys.stderr)
 
 
 def pytest_collection_modifyitems(config, items):
