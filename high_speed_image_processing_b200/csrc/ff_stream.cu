@@ -1435,7 +1435,12 @@ int dispatch_generic(const StreamParams& p, int diff, cudaStream_t st) {
 bool range_is_fused(int64_t px, int diff_dtype, bool decoded, bool profiles) {
   const Tiling t = choose_tiling(px);
   if (getenv("FF_RANGE_UNFUSED")) return false;       // tuning / cross-check knob: the three-kernel sequence
-  return t.fast && t.k == 4 && diff_dtype == FF_DIFF_NONE && !decoded && !profiles;
+  // Frames of at least 16384 pixels (BASELINE config 1: 512 x 64) take the range kernel as well: its items are
+  // 12 KiB of stored bytes whatever the frame size, and a small clip is launch-latency bound - two launches
+  // instead of three.  FF_RANGE_FUSE_SMALL=0 keeps them on the three-kernel form (cross-check knob).
+  const char* small = getenv("FF_RANGE_FUSE_SMALL");
+  const bool big_enough = t.k == 4 || ((small == nullptr || atoi(small) != 0) && px >= 16384);
+  return t.fast && big_enough && diff_dtype == FF_DIFF_NONE && !decoded && !profiles;
 }
 
 // range_kernel for the frames described by `d` (whose ws / hooks / truncate say what the last CTA does).

@@ -89,6 +89,54 @@ def test_fused_range_equals_oracle_and_unfused(engine, method, bits, h, w, n):
     assert torch.equal(res2.pos, res.pos) and torch.equal(res2.counts, res.counts) and torch.equal(res2.first_exit, res.first_exit)
 
 
+@pytest.mark.parametrize("method", ["half_maximum", "threshold", "gradient"])
+@pytest.mark.parametrize("bits,h,w,n", [(12, 64, 512, 140), (12, 66, 512, 77), (16, 64, 512, 60), (8, 64, 512, 60),
+                                        (12, 32, 512, 50), (12, 16, 1024, 64), (8, 16, 1024, 7)])
+def test_range_kernel_on_small_frames(engine, method, bits, h, w, n):
+    """Frames of BASELINE config 1's size (a few 12-KiB items per frame, ragged last item, frames smaller than one
+    item for 8-bit pixels) through the fused range kernel (FF_RANGE_FUSE_SMALL): the oracle's answers, the
+    three-kernel form's answers, skip_frames and a sub-range with a halo frame."""
+    spec, frames = clip(w, h, n, bits=bits, style="mini" if method == "threshold" else "nova")
+    packed = dev(syn.pack_frames(frames, bits), engine)
+    params = DetectionParams(method=method)
+    skip = [0, 5, 6, n - 1]
+    skip_np = np.zeros(n, np.uint8)
+    skip_np[skip] = 1
+    want = fo.process_clip(frames, fo.ClipParams(method=method))
+    want_s = fo.process_clip(frames, fo.ClipParams(method=method, skip_frames=skip))
+    fb = spec.frame_bytes
+    os.environ["FF_RANGE_FUSE_SMALL"] = "1"
+    try:
+        plan = [C.c_int64(0), C.c_int64(0), C.c_int(0)]
+        engine._lib.ff_process_range_plan(n, h, w, bits, 0, 0, 0, *(C.byref(x) for x in plan))
+        assert plan[2].value == 1 and plan[1].value == 0, "this shape must run as ONE kernel"
+        before = engine.launches
+        res = engine.process_range(packed, n, h, w, bits, params)
+        assert engine.launches == before + 2                   # prep + range kernel
+        res_s = engine.process_range(packed, n, h, w, bits, params, skip=dev(skip_np, engine))
+        a = n // 2
+        sub = engine.process_range(packed[a * fb:].clone(), n - a, h, w, bits, params, frame0=packed[:fb], first_frame=a,
+                                   halo=packed[(a - 1) * fb:a * fb].clone(), truncate=False)
+        assert int(engine._ws[:16].view(torch.int64).abs().sum().item()) == 0
+        assert int(engine._ws[512:].view(torch.int64).abs().sum().item()) == 0
+    finally:
+        del os.environ["FF_RANGE_FUSE_SMALL"]
+    assert np.array_equal(res.pos.cpu().numpy(), oracle_pos(want))
+    assert np.array_equal(res.counts.cpu().numpy(), want.nonempty.astype(np.int32))
+    assert int(res.first_exit.item()) == (want.first_exit if want.first_exit < n else FF_NO_EXIT)
+    assert res.scalars.flame_threshold == want.flame_threshold
+    assert np.array_equal(res_s.pos.cpu().numpy(), oracle_pos(want_s))
+    keep = skip_np == 0
+    assert np.array_equal(res_s.counts.cpu().numpy()[keep], want_s.nonempty.astype(np.int32)[keep])
+    assert np.array_equal(sub.pos.cpu().numpy(), want.pos_px[a:])
+    os.environ["FF_RANGE_UNFUSED"] = "1"
+    try:
+        res2 = engine.process_range(packed, n, h, w, bits, params)
+    finally:
+        del os.environ["FF_RANGE_UNFUSED"]
+    assert torch.equal(res2.pos, res.pos) and torch.equal(res2.counts, res.counts) and torch.equal(res2.first_exit, res.first_exit)
+
+
 def test_fused_range_skip_frames_halo_and_subranges(engine):
     h, w, n = 128, 1024, 120
     spec, frames = clip(w, h, n, t_enter=10.0, velocity=11.0)
