@@ -217,3 +217,46 @@ def test_lane_to_float_and_double_are_exact_for_every_lane_value():
     assert f.dtype == np.float32 and np.array_equal(f, v.astype(np.float32))
     d = ((np.uint64(0x43300000) << np.uint64(32)) | v.astype(np.uint64)).view(np.float64) - 4503599627370496.0
     assert np.array_equal(d, v.astype(np.float64))
+
+
+# ---- byte permutes: the selector constants of decode12x8_16x2 and count12x8_simd ------------------------------------
+def byte_perm(a, b, sel):
+    """__byte_perm / PRMT: result byte k = byte (sel >> 4k) & 7 of the 8-byte value {b, a} (a = bytes 0-3)."""
+    both = a | (b << 32)
+    out = 0
+    for k in range(4):
+        idx = (sel >> (4 * k)) & 7
+        out = out | (((both >> (8 * idx)) & 0xFF) << (8 * k))
+    return out
+
+
+def test_decode_and_count_selectors_on_whole_12_byte_groups():
+    """Eight packed 12-bit pixels = 12 bytes = three little-endian words, as the kernels read them from shared
+    memory.  decode12x8_16x2 must deliver the eight pixels (pixel 2j in the low lane of word j), count12x8_simd the
+    number of pixels above c; the pixel values come from the oracle's own unpack."""
+    from oracle import flame_oracle as fo
+    rng = np.random.default_rng(11)
+    n = 200_000
+    raw = rng.integers(0, 256, (n, 12), dtype=np.uint8)
+    px = fo.unpack12(raw.reshape(-1)).reshape(n, 8).astype(np.int64)
+    w = raw.view("<u4").astype(np.int64)                     # [n, 3]
+    w0, w1, w2 = w[:, 0], w[:, 1], w[:, 2]
+    # decode12x8_16x2 (ff_common.cuh)
+    p = [byte_perm(w0, 0, 0x1201), byte_perm(w0, w1, 0x4534), byte_perm(w1, w2, 0x3423), byte_perm(w2, 0, 0x2312)]
+    for j in range(4):
+        x = ((p[j] >> 4) & 0x00000FFF) | (p[j] & 0x0FFF0000)
+        lo, hi = lanes(x)
+        assert np.array_equal(lo, px[:, 2 * j]) and np.array_equal(hi, px[:, 2 * j + 1]), j
+    # count12x8_simd (ff_stream.cu)
+    for c in (0, 69, 2048, 4095):
+        k_a = (c << 4) | 15
+        a0, a1 = byte_perm(w0, w1, 0x3401), byte_perm(w1, w2, 0x5623)
+        b0, b1 = byte_perm(w0, w1, 0x4512) & 0x0FFF0FFF, byte_perm(w1, w2, 0x6734) & 0x0FFF0FFF
+        total = np.zeros(n, dtype=np.int64)
+        for a in (a0, a1):
+            total = add32(total, viaddmin_u16x2(vimax3_u16x2(a, dup(k_a), dup(k_a)), dup(0x10000 - k_a), ONE2))
+        for b in (b0, b1):
+            total = add32(total, viaddmnmx_s16x2(b, dup(-c), ONE2, use_max=False, relu=True))
+        lo, hi = lanes(total)
+        # one call covers two of the eight pixels per lane pair: four words x two lanes = the eight pixels
+        assert np.array_equal(lo + hi, (px > c).sum(1))
